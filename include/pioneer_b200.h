@@ -1,0 +1,175 @@
+/*
+ * pioneer_b200 — C-ABI of the batched Pioneer 6-DoF "reach" environment for NVIDIA B200 (sm_100a).
+ *
+ * The reference (xdralex/pioneer) has no FFI of its own: its only seams are the gym.Env
+ * contract (pioneer/launch/pioneer_knm_train.py:20-29) and the pybullet method set
+ * (pioneer/envs/bullet/bullet_scene.py).  This header is the boundary a maintainer binds
+ * instead of pybullet; each entry point names the reference interface it replaces.
+ * INTEGRATION.md shows the ctypes stub.
+ *
+ * Conventions
+ *   - plain C, no torch/CUDA types in signatures: streams travel as void* (a cudaStream_t),
+ *     device buffers as raw pointers (e.g. torch.Tensor.data_ptr()).
+ *   - every data pointer is CALLER-OWNED, row-major, contiguous; float buffers 16-byte aligned.
+ *     The library owns only its internal struct-of-arrays env state.
+ *   - every call returns 0 or a negative pnr_status and never throws; pnr_last_error() gives
+ *     the text for the calling thread.  Device work is asynchronous on the given stream.
+ *   - one handle per GPU; a handle is not thread-safe.
+ *   - there is NO CPU fallback: without a CUDA device pnr_create fails with PNR_ERR_CUDA.
+ */
+#ifndef PIONEER_B200_H_
+#define PIONEER_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PNR_ABI_VERSION 1
+#define PNR_DOF 6                 /* revolute joints of the Pioneer arm (pioneer_knm_env.py:213-215) */
+#define PNR_OBS_DIM 137           /* 21*dof + 11 (pioneer_knm_env.py:194-211)                          */
+#define PNR_MAX_CAPSULES 8
+#define PNR_MAX_OBSTACLES 4
+#define PNR_STATE_WORDS 24        /* 32-bit words of per-env state (6 float4 planes)                   */
+#define PNR_STATS_LEN 8
+
+typedef enum pnr_status {
+    PNR_OK = 0,
+    PNR_ERR_INVALID = -1,         /* bad argument (null pointer, shape, dof != PNR_DOF, ...)           */
+    PNR_ERR_CUDA = -2,            /* CUDA runtime error, text in pnr_last_error()                      */
+    PNR_ERR_ALLOC = -3,
+    PNR_ERR_UNSUPPORTED = -4
+} pnr_status;
+
+/* arithmetic of the joint integrator, see DESIGN.md "arithmetic modes" */
+#define PNR_ARITH_F32 0           /* float32 throughout = the reference source under NumPy >= 2        */
+#define PNR_ARITH_LEGACY64 1      /* NumPy 1.x scalar promotion: float64 intermediates, float32 stores */
+
+/* what `obs` holds for an env whose episode ended in this step */
+#define PNR_OBS_TERMINAL 0        /* terminal observation (what BulletEnv.step returns, bullet_env.py:192-197) */
+#define PNR_OBS_AUTORESET 1       /* first observation of the next episode (vector-env style)         */
+
+#define PNR_MODE_KINEMATIC 0      /* the reference env: act() integrator + teleport (pioneer_knm_env.py:111-148) */
+#define PNR_MODE_DYNAMIC 1        /* ABA forward dynamics + PD torque + semi-implicit Euler substeps   */
+
+/* bits of the per-env `done` byte */
+#define PNR_DONE 1                /* episode over (distance < done_distance, or time limit)            */
+#define PNR_TRUNCATED 2           /* gym TimeLimit's info['TimeLimit.truncated']                        */
+
+/* Flattened robot: serial chain with fixed joints folded into their parents.
+ * Replaces loadURDF/getJointInfo (bullet_env.py:105-138) — built once by pioneer_b200/urdf.py. */
+typedef struct pnr_model {
+    int32_t dof;                          /* must equal PNR_DOF                                         */
+    int32_t n_capsules;
+    double axis[PNR_DOF][3];              /* unit joint axis, joint frame                               */
+    double origin_xyz[PNR_DOF][3];        /* previous moving frame -> joint frame                       */
+    double origin_rot[PNR_DOF][9];        /* row-major 3x3                                              */
+    double tip_xyz[3];                    /* tracked point ('robot:pointer') in the last moving frame   */
+    double lower[PNR_DOF], upper[PNR_DOF];/* joint limits as written in the URDF (double)               */
+    double effort[PNR_DOF];               /* <limit effort>: torque clamp in dynamic mode               */
+    double damping[PNR_DOF];              /* <dynamics damping>                                         */
+    double body_mass[PNR_DOF];            /* composite rigid body of each moving frame                  */
+    double body_com[PNR_DOF][3];
+    double body_inertia[PNR_DOF][9];      /* about the COM, moving-frame axes                           */
+    int32_t capsule_body[PNR_MAX_CAPSULES];
+    double capsule_radius[PNR_MAX_CAPSULES];
+    double capsule_p0[PNR_MAX_CAPSULES][3];
+    double capsule_p1[PNR_MAX_CAPSULES][3];
+} pnr_model;
+
+#define PNR_OBSTACLE_NONE 0
+#define PNR_OBSTACLE_PLANE 1              /* p = point on plane, e = unit normal                        */
+#define PNR_OBSTACLE_BOX 2                /* p = centre, e = half extents (axis aligned)                */
+#define PNR_OBSTACLE_SPHERE 3             /* p = centre, e[0] = radius                                  */
+
+/* PioneerKinematicConfig (pioneer_knm_env.py:19-34) + SimulationConfig (bullet_env.py:36-44)
+ * + gym TimeLimit (pioneer_knm_train.py:27) + the knobs of this implementation. */
+typedef struct pnr_config {
+    double max_v_to_r, max_a_to_v;
+    double done_distance;
+    double award_max, award_done, award_potential_slope, penalty_step;
+    double target_lo[3], target_hi[3];
+    double timestep;                      /* 1/240                                                      */
+    int32_t frame_skip;                   /* 10                                                         */
+    double gravity;                       /* 0; acts along -z in dynamic mode                           */
+    int32_t max_episode_steps;            /* TimeLimit; 0 = no limit                                    */
+    int32_t arith;                        /* PNR_ARITH_*                                                */
+    int32_t obs_mode;                     /* PNR_OBS_*                                                  */
+    int32_t auto_reset;                   /* reset finished envs inside the step kernel                 */
+    int32_t mode;                         /* PNR_MODE_*                                                 */
+    /* dynamic mode: explicit PD position control  tau = kp*(q_des-q) - kd*qd, clamped to +-effort*torque_scale */
+    double kp, kd, torque_scale;
+    /* obstacle variant (Joint/Scene.create_body_box/plane, pioneer_knm_env.py:249-261) */
+    int32_t n_obstacles;
+    int32_t obstacle_type[PNR_MAX_OBSTACLES];
+    double obstacle_p[PNR_MAX_OBSTACLES][3];
+    double obstacle_e[PNR_MAX_OBSTACLES][3];
+    double contact_penalty;               /* reward -= contact_penalty * sum(penetration depth)         */
+} pnr_config;
+
+typedef struct pnr_handle pnr_handle;
+
+int pnr_abi_version(void);
+const char* pnr_last_error(void);
+
+/* Fill `cfg` with the reference defaults (pioneer_knm_env.py:19-34, bullet_env.py:36-44, TimeLimit 500). */
+void pnr_default_config(pnr_config* cfg);
+
+/* Replaces PioneerKinematicEnv.__init__ + BulletEnv.reset_simulator (pioneer_knm_env.py:39-74,
+ * bullet_env.py:90-99) for n_envs independent envs on CUDA device `device`.  `env_id_base` is the
+ * global id of local env 0 (multi-GPU sharding; reset randomness is keyed on the global id so results
+ * do not depend on the number of GPUs).  All envs start reset (as reset_world()). */
+int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t n_envs, int64_t env_id_base,
+               int device, uint64_t seed, pnr_handle** out);
+void pnr_destroy(pnr_handle* h);
+
+int64_t pnr_num_envs(const pnr_handle* h);
+/* derived bounds (pioneer_knm_env.py:56-58): each out pointer is HOST float[PNR_DOF] or NULL */
+int pnr_get_bounds(const pnr_handle* h, float* r_lo, float* r_hi, float* v_max, float* a_max);
+/* re-seed the reset generator (PioneerKinematicEnv.seed, pioneer_knm_env.py:107-109) */
+int pnr_seed(pnr_handle* h, uint64_t seed);
+
+/* Replaces BulletEnv.reset / reset_world(joint_positions, target_position) (bullet_env.py:187-190,
+ * pioneer_knm_env.py:76-105).  idx: DEVICE int64[n] local env indices, or NULL = all envs (then n must
+ * be n_envs).  q0: DEVICE float[n,6] or NULL = uniform in [r_lo, r_hi].  target: DEVICE float[n,3] or
+ * NULL = uniform in [target_lo, target_hi].  obs_out: DEVICE float[n,137] or NULL. */
+int pnr_reset(pnr_handle* h, const int64_t* idx, int64_t n, const float* q0, const float* target,
+              float* obs_out, void* stream);
+
+/* Replaces BulletEnv.step -> act() + observe() through gym TimeLimit (bullet_env.py:192-197,
+ * pioneer_knm_env.py:111-211) for every env in one fused kernel launch.
+ * actions DEVICE float[N,6] (stored unclipped, as pioneer_knm_env.py:144); obs DEVICE float[N,137];
+ * reward DEVICE float[N]; done DEVICE uint8[N] (PNR_DONE | PNR_TRUNCATED bits). */
+int pnr_step(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, void* stream);
+
+/* Same step with HOST buffers (pinned or pageable): H2D of actions, the kernel, D2H of
+ * obs/reward/done, pipelined in chunks on internal streams; returns after the results are on the host. */
+int pnr_step_host(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done);
+
+/* Replaces PioneerKinematicEnv.observe (pioneer_knm_env.py:184-211) on the current state.
+ * idx DEVICE int64[n] or NULL = all. */
+int pnr_observe(pnr_handle* h, const int64_t* idx, int64_t n, float* obs_out, void* stream);
+
+/* Replaces Joint.position()/velocity() and the env attributes a, v, r, potential (bullet_scene.py:115-121,
+ * pioneer_knm_env.py:63-66).  All DEVICE, any may be NULL: r,v,a float[N,6]; potential float[N];
+ * target float[N,3]; t int32[N] (steps since reset); ep_return float[N]. */
+int pnr_get_state(pnr_handle* h, float* r, float* v, float* a, float* potential, float* target,
+                  int32_t* t, float* ep_return, void* stream);
+int pnr_set_state(pnr_handle* h, const float* r, const float* v, const float* a, const float* potential,
+                  const float* target, const int32_t* t, const float* ep_return, void* stream);
+
+/* Episode statistics accumulated on the device since the last clear (the columns cli.py:32-38 prints):
+ * out HOST double[8] = {episodes, sum_return, sum_length, sum_return^2, max_return, min_return,
+ * env_steps, reached_target}.  Synchronises `stream`. */
+int pnr_stats(pnr_handle* h, double* out, int clear, void* stream);
+/* DEVICE double[8] view of the same accumulators, for an in-place NCCL all-reduce. */
+int pnr_stats_device_ptr(pnr_handle* h, double** out);
+
+/* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
+int64_t pnr_launch_count(const pnr_handle* h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif  /* PIONEER_B200_H_ */

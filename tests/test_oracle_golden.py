@@ -1,0 +1,115 @@
+"""The CPU oracle replayed against golden vectors recorded from the unmodified reference source
+(tests/golden/make_golden.py).  CPU only."""
+import numpy as np
+import pytest
+
+from oracle.reach_oracle import OracleConfig, OracleEnv, fk_pointer, philox4x32_10
+from tests._util import golden_case, load_golden, oracle_chain
+
+G = load_golden()
+CHAIN = oracle_chain()
+
+
+def replay(case, config=None):
+    env = OracleEnv(CHAIN, config, arith="np2")
+    ep = 0
+    env.reset_world(case["q0"][ep], case["target"][ep])
+    first = env.observe()
+    assert np.array_equal(first[:126], case["reset_obs"][ep][:126])
+    np.testing.assert_allclose(first[126:], case["reset_obs"][ep][126:], rtol=1e-12, atol=1e-12)
+    obs_at = {int(t): k for k, t in enumerate(case["obs_idx"])}
+    for t, action in enumerate(case["actions"]):
+        obs, reward, done, truncated = env.step(action)
+        # joint state: bit-exact (pure IEEE arithmetic)
+        assert np.array_equal(env.r, case["r"][t]), (t, env.r, case["r"][t])
+        assert np.array_equal(env.v, case["v"][t]), (t, env.v, case["v"][t])
+        assert np.array_equal(env.a, case["a"][t])
+        assert done == bool(case["done"][t]), t
+        assert truncated == bool(case["truncated"][t]), t
+        # float64 FK by two different algorithms: agreement to rounding
+        np.testing.assert_allclose(obs[126:137], case["tail"][t], rtol=1e-12, atol=1e-12)
+        np.testing.assert_allclose(reward, case["reward"][t], rtol=0, atol=1e-11)
+        if t in obs_at:
+            ref = case["obs"][obs_at[t]]
+            assert np.array_equal(obs[:126], ref[:126]), t  # float32-valued entries incl. numpy's float32 sin/cos
+        if done:
+            ep += 1
+            env.reset_world(case["q0"][ep], case["target"][ep])
+            np.testing.assert_allclose(env.observe(), case["reset_obs"][ep], rtol=1e-12, atol=1e-12)
+    return env
+
+
+@pytest.mark.parametrize("name", ["cfg1", "gentle", "bangbang", "wild", "zero", "reach", "approach"])
+def test_oracle_matches_reference_source(name):
+    replay(golden_case(G, name))
+
+
+def test_oracle_reward_knobs():
+    replay(golden_case(G, "knobs"), OracleConfig(award_potential_slope=4.0, award_done=7.5, penalty_step=0.02))
+
+
+def test_oracle_multi_env():
+    for k in range(16):
+        env = OracleEnv(CHAIN, arith="np2")
+        env.reset_world(G["multi__q0"][k], G["multi__target"][k])
+        for t in range(200):
+            obs, reward, done, truncated = env.step(G["multi__actions"][k, t])
+            assert np.array_equal(env.r, G["multi__r"][k, t]) and np.array_equal(env.v, G["multi__v"][k, t])
+            np.testing.assert_allclose(reward, G["multi__reward"][k, t], atol=1e-11)
+            assert done == bool(G["multi__done"][k, t])
+    # env 0 of the multi-env fixture is the cfg1 trajectory
+    assert np.array_equal(G["multi__r"][0], G["cfg1__r"][:200])
+
+
+def test_golden_cases_exercise_the_edges():
+    """The fixtures really contain the branches the parity claim is about."""
+    c = golden_case(G, "cfg1")
+    v_max, r_lo, r_hi = G["const_v_max"], G["const_r_lo"], G["const_r_hi"]
+    assert (np.abs(c["v"]) == v_max).any(), "velocity clamp never hit"
+    assert (c["r"] == r_hi).any() or (c["r"] == r_lo).any(), "position limit never hit"
+    assert c["truncated"].sum() == 2 and c["done"].sum() == 2  # TimeLimit at steps 500 and 1000
+    reach = golden_case(G, "reach")
+    assert (reach["done"] & ~reach["truncated"]).sum() >= 5, "distance-done never exercised"
+    assert (reach["tail"][:, 9] < 0.1).any() and (reach["tail"][:, 9] > 0.1).any()
+    assert reach["truncated"].any()
+    approach = golden_case(G, "approach")
+    hits = np.flatnonzero(approach["done"] & ~approach["truncated"])
+    assert len(hits) >= 3 and (approach["tail"][hits - 1, 9] > 0.1).all(), "done must fire mid-episode while moving"
+    wild = golden_case(G, "wild")
+    assert np.abs(wild["a"]).max() > 1e6
+
+
+def test_reference_constants():
+    env = OracleEnv(CHAIN)
+    assert np.array_equal(env.r_lo, G["const_r_lo"]) and np.array_equal(env.r_hi, G["const_r_hi"])
+    assert np.array_equal(env.v_max, G["const_v_max"]) and np.array_equal(env.a_max, G["const_a_max"])
+    assert env.dt == G["const_dt_eps"][0] and env.eps == G["const_dt_eps"][1]
+    assert tuple(G["const_obs_shape"]) == (137,) and str(G["const_obs_dtype"]) == "float64"
+    assert int(G["const_fps"]) == 24 and int(G["const_dof"]) == 6
+    np.testing.assert_allclose([env.compute_potential(d) for d in (0.0, 0.1, 5.0, 20.0)],
+                               [95.0, 94.0594059406, 63.3333333333, 31.6666666667], rtol=1e-11)
+    np.testing.assert_array_equal(G["const_potential_kat"], [env.compute_potential(d) for d in (0.0, 0.1, 5.0, 20.0)])
+
+
+def test_fk_known_answers():
+    """Hand-derived known answers, SURVEY.md section 8(c) C5."""
+    kat = {
+        (0, 0, 0, 0, 0, 0): (14.6, 1.0, 15.9),
+        (0.5, 0, 0, 0, 0, 0): (12.333279864995, 7.877195425512, 15.9),
+        (0, 0.5, 0, 0, 0, 0): (18.997294851594, 1.0, 7.321202184764),
+        (0, 0, 0.5, 0, 0, 0): (13.723613926947, 1.0, 8.667794003970),
+        (0, 0, 0, 0.5, 0, 0): (14.6, 0.089091476652, 15.667406867592),
+        (0, 0, 0, 0, 0.5, 0): (15.070205746153, 1.0, 13.941474928617),
+        (0, 0, 0, 0, 0, 0.5): (14.6, 0.089091476652, 15.667406867592),
+        (0.3, -0.4, 0.9, 1.1, -0.7, 2.0): (7.904033967723, 1.072102752440, 5.624962379045),
+    }
+    for q, p in kat.items():
+        np.testing.assert_allclose(fk_pointer(CHAIN, q), p, atol=2e-12)
+
+
+def test_philox_known_answers():
+    """Random123 known-answer vectors for philox4x32-10."""
+    assert philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
+        (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
