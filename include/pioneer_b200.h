@@ -163,8 +163,9 @@ int pnr_set_state(pnr_handle* h, const float* r, const float* v, const float* a,
  * out HOST double[8] = {episodes, sum_return, sum_length, sum_return^2, max_return, min_return,
  * env_steps, reached_target}.  Synchronises `stream`. */
 int pnr_stats(pnr_handle* h, double* out, int clear, void* stream);
-/* DEVICE double[8] view of the same accumulators, for an in-place NCCL all-reduce. */
-int pnr_stats_device_ptr(pnr_handle* h, double** out);
+/* Same 8 numbers written to a caller-owned DEVICE double[8] without synchronising, for an NCCL
+ * all-reduce on the same stream (SUM over {0,1,2,3,6,7}, MAX over {4, -5}). */
+int pnr_stats_device(pnr_handle* h, double* out_device, int clear, void* stream);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t pnr_launch_count(const pnr_handle* h);

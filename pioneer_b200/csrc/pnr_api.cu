@@ -1,0 +1,318 @@
+// C-ABI of pioneer_b200 (include/pioneer_b200.h): handle lifetime, parameter block, launches.
+// No torch types, no exceptions across the boundary, no CPU fallback.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "pnr_launch.h"
+
+static thread_local std::string g_last_error;
+
+static int pnr_fail(int code, const std::string& msg) {
+    g_last_error = msg;
+    return code;
+}
+
+#define PNR_CUDA(expr)                                                                          \
+    do {                                                                                        \
+        cudaError_t _e = (expr);                                                                \
+        if (_e != cudaSuccess)                                                                  \
+            return pnr_fail(PNR_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e)); \
+    } while (0)
+
+struct pnr_handle {
+    int device = 0;
+    int64_t n_envs = 0;
+    PnrParams params;
+    pnr_config cfg;
+    pnr_model model;
+    float4* state = nullptr;        // 6 planes of float4[n_envs]
+    PnrStats* stats = nullptr;
+    double* stats_out = nullptr;    // device double[8] snapshot
+    double* stats_host = nullptr;   // pinned
+    uint32_t tick = 0;              // keys the reset generator: one tick per reset/step call
+    double env_steps = 0.0;
+    int64_t launches = 0;
+    float a_max[PNR_DOF];
+    // host-buffer path (pnr_step_host)
+    float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
+    uint8_t* h_done = nullptr;
+    cudaStream_t host_stream = nullptr;
+};
+
+struct PnrDeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit PnrDeviceGuard(int dev) {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~PnrDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+extern "C" int pnr_abi_version(void) { return PNR_ABI_VERSION; }
+extern "C" const char* pnr_last_error(void) { return g_last_error.c_str(); }
+
+extern "C" void pnr_default_config(pnr_config* c) {
+    if (!c) return;
+    std::memset(c, 0, sizeof(*c));
+    c->max_v_to_r = 2.0; c->max_a_to_v = 10.0;                  // pioneer_knm_env.py:21-22
+    c->done_distance = 0.1;                                      // :24
+    c->award_max = 100.0; c->award_done = 5.0;                   // :26-27
+    c->award_potential_slope = 10.0; c->penalty_step = 1.0 / 100; // :28-29
+    c->target_lo[0] = 15; c->target_lo[1] = -10; c->target_lo[2] = 2;   // :31
+    c->target_hi[0] = 25; c->target_hi[1] = 10; c->target_hi[2] = 6;    // :32
+    c->timestep = 1.0 / 240; c->frame_skip = 10; c->gravity = 0.0;      // bullet_env.py:38-41
+    c->max_episode_steps = 500;                                  // pioneer_knm_train.py:27
+    c->arith = PNR_ARITH_F32;
+    c->obs_mode = PNR_OBS_TERMINAL;
+    c->auto_reset = 1;
+    c->mode = PNR_MODE_KINEMATIC;
+    c->kp = 0.0; c->kd = 0.0; c->torque_scale = 1.0;
+    c->n_obstacles = 0;
+    c->contact_penalty = 0.0;
+}
+
+static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_envs, int64_t env_id_base,
+                            uint64_t seed, PnrParams& p, float (&a_max)[PNR_DOF]) {
+    std::memset(&p, 0, sizeof(p));
+    if (m.dof != PNR_DOF) return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_model.dof must be 6 (PNR_DOF)");
+    for (int j = 0; j < PNR_DOF; ++j) {
+        double n2 = 0;
+        for (int k = 0; k < 3; ++k) n2 += m.axis[j][k] * m.axis[j][k];
+        if (std::fabs(n2 - 1.0) > 1e-9) return pnr_fail(PNR_ERR_INVALID, "pnr_model.axis must be unit vectors");
+        int code = PNR_AXIS_GENERAL;
+        float sign = 1.f;
+        for (int k = 0; k < 3; ++k)
+            if (std::fabs(std::fabs(m.axis[j][k]) - 1.0) < 1e-12) { code = k; sign = m.axis[j][k] > 0 ? 1.f : -1.f; }
+        p.axis_code[j] = code;
+        p.axis_sign[j] = sign;
+        bool has_rot = false;
+        for (int k = 0; k < 9; ++k) {
+            const double ident = (k % 4 == 0) ? 1.0 : 0.0;
+            if (std::fabs(m.origin_rot[j][k] - ident) > 1e-15) has_rot = true;
+            p.origin_rot[j][k] = (float)m.origin_rot[j][k];
+            p.origin_rot64[j][k] = m.origin_rot[j][k];
+        }
+        p.origin_has_rot[j] = has_rot ? 1 : 0;
+        for (int k = 0; k < 3; ++k) {
+            p.axis[j][k] = (float)m.axis[j][k];
+            p.axis64[j][k] = m.axis[j][k];
+            p.origin_xyz[j][k] = (float)m.origin_xyz[j][k];
+            p.origin_xyz64[j][k] = m.origin_xyz[j][k];
+        }
+        // bounds exactly as the reference derives them (pioneer_knm_env.py:56-58, 217-220):
+        // float32 limits; python scalar * float32 array stays float32
+        p.r_lo[j] = (float)m.lower[j];
+        p.r_hi[j] = (float)m.upper[j];
+        p.v_max[j] = (float)c.max_v_to_r * (p.r_hi[j] - p.r_lo[j]);
+        a_max[j] = (float)c.max_a_to_v * p.v_max[j];
+        // float32 cos/sin of float32 limits (np.cos on a float32 array); computed in double and rounded once
+        p.cos_r_lo[j] = (float)std::cos((double)p.r_lo[j]); p.sin_r_lo[j] = (float)std::sin((double)p.r_lo[j]);
+        p.cos_r_hi[j] = (float)std::cos((double)p.r_hi[j]); p.sin_r_hi[j] = (float)std::sin((double)p.r_hi[j]);
+    }
+    for (int k = 0; k < 3; ++k) {
+        p.tip_xyz[k] = (float)m.tip_xyz[k];
+        p.tip_xyz64[k] = m.tip_xyz[k];
+        p.target_lo[k] = (float)c.target_lo[k];
+        p.target_hi[k] = (float)c.target_hi[k];
+    }
+    if (!(c.timestep > 0) || c.frame_skip < 1) return pnr_fail(PNR_ERR_INVALID, "timestep/frame_skip must be positive");
+    p.dt64 = c.timestep * c.frame_skip;          // World.step_time, bullet_scene.py:277-279
+    p.eps64 = 1e-5;                              // pioneer_knm_env.py:61
+    p.dt32 = (float)p.dt64;
+    p.eps32 = (float)p.eps64;
+    p.done_distance = (float)c.done_distance;
+    p.done_distance64 = c.done_distance;
+    p.done_band = 1e-3f;                         // >> float32 FK error (~1e-5 at 30-unit reach)
+    p.pot_max = (float)(c.award_max - c.award_done);
+    p.pot_slope = (float)c.award_potential_slope;
+    p.penalty_step = (float)c.penalty_step;
+    p.award_done = (float)c.award_done;
+    p.max_episode_steps = c.max_episode_steps;
+    p.auto_reset = c.auto_reset;
+    p.seed_lo = (uint32_t)seed;
+    p.seed_hi = (uint32_t)(seed >> 32);
+    p.env_id_base = env_id_base;
+    p.n_envs = n_envs;
+    return PNR_OK;
+}
+
+extern "C" int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t n_envs, int64_t env_id_base,
+                          int device, uint64_t seed, pnr_handle** out) {
+    if (!model || !cfg || !out) return pnr_fail(PNR_ERR_INVALID, "pnr_create: null argument");
+    if (n_envs < 1) return pnr_fail(PNR_ERR_INVALID, "pnr_create: n_envs must be >= 1");
+    if (cfg->arith != PNR_ARITH_F32 && cfg->arith != PNR_ARITH_LEGACY64)
+        return pnr_fail(PNR_ERR_INVALID, "pnr_create: unknown arith");
+    if (cfg->obs_mode != PNR_OBS_TERMINAL && cfg->obs_mode != PNR_OBS_AUTORESET)
+        return pnr_fail(PNR_ERR_INVALID, "pnr_create: unknown obs_mode");
+    if (cfg->mode != PNR_MODE_KINEMATIC)
+        return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_create: only PNR_MODE_KINEMATIC is built in this version");
+    int count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&count);
+    if (ce != cudaSuccess || count == 0)
+        return pnr_fail(PNR_ERR_CUDA, std::string("pnr_create: no CUDA device (there is no CPU fallback): ") +
+                                          cudaGetErrorString(ce));
+    if (device < 0 || device >= count || device >= PNR_MAX_DEVICES)
+        return pnr_fail(PNR_ERR_INVALID, "pnr_create: bad device index");
+    pnr_handle* h = new (std::nothrow) pnr_handle();
+    if (!h) return pnr_fail(PNR_ERR_ALLOC, "pnr_create: out of host memory");
+    h->device = device;
+    h->n_envs = n_envs;
+    h->cfg = *cfg;
+    h->model = *model;
+    int rc = pnr_build_params(*model, *cfg, n_envs, env_id_base, seed, h->params, h->a_max);
+    if (rc != PNR_OK) { delete h; return rc; }
+    PnrDeviceGuard guard(device);
+    if (!guard.ok) { delete h; return pnr_fail(PNR_ERR_CUDA, "pnr_create: cudaSetDevice failed"); }
+    auto bail = [&](cudaError_t e, const char* what) {
+        std::string msg = std::string(what) + ": " + cudaGetErrorString(e);
+        pnr_destroy(h);
+        return pnr_fail(e == cudaErrorMemoryAllocation ? PNR_ERR_ALLOC : PNR_ERR_CUDA, msg);
+    };
+    cudaError_t e;
+    if ((e = cudaMalloc(&h->state, sizeof(float4) * 6 * (size_t)n_envs)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
+    if ((e = cudaMalloc(&h->stats, sizeof(PnrStats))) != cudaSuccess) return bail(e, "cudaMalloc(stats)");
+    if ((e = cudaMalloc(&h->stats_out, sizeof(double) * PNR_STATS_LEN)) != cudaSuccess) return bail(e, "cudaMalloc(stats_out)");
+    if ((e = cudaMallocHost(&h->stats_host, sizeof(double) * PNR_STATS_LEN)) != cudaSuccess) return bail(e, "cudaMallocHost");
+    // clear statistics, then reset every env (reset_world) with tick 0
+    if ((e = pnr_launch_stats_snapshot(h->stats, 0.0, h->stats_out, 1, nullptr)) != cudaSuccess) return bail(e, "stats init");
+    if ((e = pnr_launch_reset_observe(h->params, device, 0, h->state, nullptr, n_envs, nullptr, nullptr, nullptr,
+                                      h->tick, nullptr)) != cudaSuccess) return bail(e, "initial reset");
+    h->launches += 2;
+    h->tick += 1;
+    if ((e = cudaStreamSynchronize(nullptr)) != cudaSuccess) return bail(e, "pnr_create sync");
+    *out = h;
+    return PNR_OK;
+}
+
+extern "C" void pnr_destroy(pnr_handle* h) {
+    if (!h) return;
+    PnrDeviceGuard guard(h->device);
+    if (h->host_stream) { cudaStreamSynchronize(h->host_stream); cudaStreamDestroy(h->host_stream); }
+    cudaFree(h->state); cudaFree(h->stats); cudaFree(h->stats_out);
+    cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_done);
+    if (h->stats_host) cudaFreeHost(h->stats_host);
+    delete h;
+}
+
+extern "C" int64_t pnr_num_envs(const pnr_handle* h) { return h ? h->n_envs : 0; }
+extern "C" int64_t pnr_launch_count(const pnr_handle* h) { return h ? h->launches : 0; }
+
+extern "C" int pnr_get_bounds(const pnr_handle* h, float* r_lo, float* r_hi, float* v_max, float* a_max) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_get_bounds: null handle");
+    for (int j = 0; j < PNR_DOF; ++j) {
+        if (r_lo) r_lo[j] = h->params.r_lo[j];
+        if (r_hi) r_hi[j] = h->params.r_hi[j];
+        if (v_max) v_max[j] = h->params.v_max[j];
+        if (a_max) a_max[j] = h->a_max[j];
+    }
+    return PNR_OK;
+}
+
+extern "C" int pnr_seed(pnr_handle* h, uint64_t seed) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_seed: null handle");
+    h->params.seed_lo = (uint32_t)seed;
+    h->params.seed_hi = (uint32_t)(seed >> 32);
+    return PNR_OK;
+}
+
+extern "C" int pnr_reset(pnr_handle* h, const int64_t* idx, int64_t n, const float* q0, const float* target,
+                         float* obs_out, void* stream) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_reset: null handle");
+    if (n < 0 || (!idx && n != h->n_envs)) return pnr_fail(PNR_ERR_INVALID, "pnr_reset: idx == NULL requires n == n_envs");
+    PnrDeviceGuard guard(h->device);
+    PNR_CUDA(pnr_launch_reset_observe(h->params, h->device, 0, h->state, idx, n, q0, target, obs_out, h->tick,
+                                      (cudaStream_t)stream));
+    h->tick += 1;
+    h->launches += (n > 0);
+    return PNR_OK;
+}
+
+extern "C" int pnr_observe(pnr_handle* h, const int64_t* idx, int64_t n, float* obs_out, void* stream) {
+    if (!h || !obs_out) return pnr_fail(PNR_ERR_INVALID, "pnr_observe: null argument");
+    if (n < 0 || (!idx && n != h->n_envs)) return pnr_fail(PNR_ERR_INVALID, "pnr_observe: idx == NULL requires n == n_envs");
+    PnrDeviceGuard guard(h->device);
+    PNR_CUDA(pnr_launch_reset_observe(h->params, h->device, 1, h->state, idx, n, nullptr, nullptr, obs_out, h->tick,
+                                      (cudaStream_t)stream));
+    h->launches += (n > 0);
+    return PNR_OK;
+}
+
+extern "C" int pnr_step(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, void* stream) {
+    if (!h || !actions || !obs || !reward || !done) return pnr_fail(PNR_ERR_INVALID, "pnr_step: null argument");
+    if ((reinterpret_cast<uintptr_t>(obs) & 15) || (reinterpret_cast<uintptr_t>(actions) & 7))
+        return pnr_fail(PNR_ERR_INVALID, "pnr_step: obs must be 16-byte and actions 8-byte aligned");
+    PnrDeviceGuard guard(h->device);
+    PNR_CUDA(pnr_launch_step(h->params, h->device, h->cfg.arith, h->cfg.obs_mode, h->state, actions, obs, reward, done,
+                             h->stats, h->tick, (cudaStream_t)stream));
+    h->tick += 1;
+    h->env_steps += (double)h->n_envs;
+    h->launches += 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_step_host(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done) {
+    if (!h || !actions || !obs || !reward || !done) return pnr_fail(PNR_ERR_INVALID, "pnr_step_host: null argument");
+    PnrDeviceGuard guard(h->device);
+    const size_t n = (size_t)h->n_envs;
+    if (!h->host_stream) {
+        PNR_CUDA(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+        PNR_CUDA(cudaMalloc(&h->h_actions, n * PNR_DOF * sizeof(float)));
+        PNR_CUDA(cudaMalloc(&h->h_obs, n * PNR_OBS_DIM * sizeof(float)));
+        PNR_CUDA(cudaMalloc(&h->h_reward, n * sizeof(float)));
+        PNR_CUDA(cudaMalloc(&h->h_done, n));
+    }
+    cudaStream_t s = h->host_stream;
+    PNR_CUDA(cudaMemcpyAsync(h->h_actions, actions, n * PNR_DOF * sizeof(float), cudaMemcpyHostToDevice, s));
+    int rc = pnr_step(h, h->h_actions, h->h_obs, h->h_reward, h->h_done, s);
+    if (rc != PNR_OK) return rc;
+    PNR_CUDA(cudaMemcpyAsync(obs, h->h_obs, n * PNR_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PNR_CUDA(cudaMemcpyAsync(reward, h->h_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
+    PNR_CUDA(cudaMemcpyAsync(done, h->h_done, n, cudaMemcpyDeviceToHost, s));
+    PNR_CUDA(cudaStreamSynchronize(s));
+    return PNR_OK;
+}
+
+extern "C" int pnr_get_state(pnr_handle* h, float* r, float* v, float* a, float* potential, float* target,
+                             int32_t* t, float* ep_return, void* stream) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_get_state: null handle");
+    PnrDeviceGuard guard(h->device);
+    PNR_CUDA(pnr_launch_state_io(false, h->state, h->n_envs, r, v, a, potential, target, t, ep_return, (cudaStream_t)stream));
+    h->launches += 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_set_state(pnr_handle* h, const float* r, const float* v, const float* a, const float* potential,
+                             const float* target, const int32_t* t, const float* ep_return, void* stream) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_set_state: null handle");
+    PnrDeviceGuard guard(h->device);
+    PNR_CUDA(pnr_launch_state_io(true, h->state, h->n_envs, const_cast<float*>(r), const_cast<float*>(v),
+                                 const_cast<float*>(a), const_cast<float*>(potential), const_cast<float*>(target),
+                                 const_cast<int32_t*>(t), const_cast<float*>(ep_return), (cudaStream_t)stream));
+    h->launches += 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_stats_device(pnr_handle* h, double* out_device, int clear, void* stream) {
+    if (!h || !out_device) return pnr_fail(PNR_ERR_INVALID, "pnr_stats_device: null argument");
+    PnrDeviceGuard guard(h->device);
+    PNR_CUDA(pnr_launch_stats_snapshot(h->stats, h->env_steps, out_device, clear, (cudaStream_t)stream));
+    if (clear) h->env_steps = 0.0;
+    h->launches += 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_stats(pnr_handle* h, double* out, int clear, void* stream) {
+    if (!h || !out) return pnr_fail(PNR_ERR_INVALID, "pnr_stats: null argument");
+    PnrDeviceGuard guard(h->device);
+    int rc = pnr_stats_device(h, h->stats_out, clear, stream);
+    if (rc != PNR_OK) return rc;
+    PNR_CUDA(cudaMemcpyAsync(h->stats_host, h->stats_out, sizeof(double) * PNR_STATS_LEN, cudaMemcpyDeviceToHost,
+                             (cudaStream_t)stream));
+    PNR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
+    std::memcpy(out, h->stats_host, sizeof(double) * PNR_STATS_LEN);
+    return PNR_OK;
+}

@@ -1,0 +1,131 @@
+// Device-side parameter block, Philox reset generator and small math helpers shared by the kernels.
+// sm_100a only (compiled with -gencode arch=compute_100a,code=sm_100a).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "../../include/pioneer_b200.h"
+
+#define PNR_AXIS_X 0
+#define PNR_AXIS_Y 1
+#define PNR_AXIS_Z 2
+#define PNR_AXIS_GENERAL 3
+
+// Everything the kernels need besides per-env state.  Passed BY VALUE as a __grid_constant__ kernel
+// parameter: it lands in the constant bank, reads are warp-uniform, and several handles with different
+// configurations can coexist in one process (a __constant__ symbol could not).
+struct PnrParams {
+    // flattened chain, float32 copies for the hot path (pioneer_b200/urdf.py)
+    float axis[PNR_DOF][3];
+    float origin_xyz[PNR_DOF][3];
+    float origin_rot[PNR_DOF][9];
+    float tip_xyz[3];
+    int32_t axis_code[PNR_DOF];     // PNR_AXIS_*: axis-aligned joints rotate with 4 FMA instead of Rodrigues
+    float axis_sign[PNR_DOF];       // +1 / -1 for axis-aligned joints
+    int32_t origin_has_rot[PNR_DOF];
+    // float64 copies for the done-band re-evaluation (matches the reference's double-precision FK)
+    double axis64[PNR_DOF][3];
+    double origin_xyz64[PNR_DOF][3];
+    double origin_rot64[PNR_DOF][9];
+    double tip_xyz64[3];
+    // bounds (pioneer_knm_env.py:56-58), all float32 like the reference
+    float r_lo[PNR_DOF], r_hi[PNR_DOF], v_max[PNR_DOF];
+    // the constant third of the observation: cos/sin of r_lo and r_hi (pioneer_knm_env.py:196-197)
+    float cos_r_lo[PNR_DOF], sin_r_lo[PNR_DOF], cos_r_hi[PNR_DOF], sin_r_hi[PNR_DOF];
+    float dt32, eps32;
+    double dt64, eps64;
+    float done_distance, done_band;
+    float pot_max, pot_slope;       // (award_max - award_done), award_potential_slope
+    float penalty_step, award_done;
+    double done_distance64;
+    float target_lo[3], target_hi[3];
+    int32_t max_episode_steps;
+    int32_t auto_reset;
+    uint32_t seed_lo, seed_hi;
+    int64_t env_id_base;
+    int64_t n_envs;
+};
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (Salmon et al., SC'11), bit-identical to oracle/reach_oracle.py::philox4x32_10
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint4 pnr_philox4x32_10(uint4 c, uint32_t k0, uint32_t k1) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+        c = make_uint4(hi1 ^ c.y ^ k0, lo1, hi0 ^ c.w ^ k1, lo0);
+        k0 += 0x9E3779B9u;
+        k1 += 0xBB67AE85u;
+    }
+    return c;
+}
+
+__device__ __forceinline__ float pnr_u01(uint32_t x) { return __fmul_rn((float)(x >> 8), 5.9604644775390625e-08f); }
+
+// lo + (hi - lo) * u with separately rounded multiply and add (no FMA) so the CPU oracle reproduces it
+__device__ __forceinline__ float pnr_uniform(float lo, float hi, float u) {
+    return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), u));
+}
+
+// 6 joint positions then 3 target coordinates (reference draw order, pioneer_knm_env.py:80-90),
+// counter = (global env id lo, hi, tick, block), key = seed
+__device__ __forceinline__ void pnr_reset_draws(const PnrParams& p, int64_t global_env, uint32_t tick,
+                                                float (&q)[PNR_DOF], float (&tgt)[3]) {
+    const uint32_t g0 = (uint32_t)global_env, g1 = (uint32_t)((uint64_t)global_env >> 32);
+    const uint4 b0 = pnr_philox4x32_10(make_uint4(g0, g1, tick, 0u), p.seed_lo, p.seed_hi);
+    const uint4 b1 = pnr_philox4x32_10(make_uint4(g0, g1, tick, 1u), p.seed_lo, p.seed_hi);
+    const uint4 b2 = pnr_philox4x32_10(make_uint4(g0, g1, tick, 2u), p.seed_lo, p.seed_hi);
+    q[0] = pnr_uniform(p.r_lo[0], p.r_hi[0], pnr_u01(b0.x));
+    q[1] = pnr_uniform(p.r_lo[1], p.r_hi[1], pnr_u01(b0.y));
+    q[2] = pnr_uniform(p.r_lo[2], p.r_hi[2], pnr_u01(b0.z));
+    q[3] = pnr_uniform(p.r_lo[3], p.r_hi[3], pnr_u01(b0.w));
+    q[4] = pnr_uniform(p.r_lo[4], p.r_hi[4], pnr_u01(b1.x));
+    q[5] = pnr_uniform(p.r_lo[5], p.r_hi[5], pnr_u01(b1.y));
+    tgt[0] = pnr_uniform(p.target_lo[0], p.target_hi[0], pnr_u01(b1.z));
+    tgt[1] = pnr_uniform(p.target_lo[1], p.target_hi[1], pnr_u01(b1.w));
+    tgt[2] = pnr_uniform(p.target_lo[2], p.target_hi[2], pnr_u01(b2.x));
+}
+
+// np.clip for scalars: NaN propagates (comparisons are false)
+template <typename T>
+__device__ __forceinline__ T pnr_clip(T x, T lo, T hi) { return x < lo ? lo : (x > hi ? hi : x); }
+
+// ---------------------------------------------------------------------------------------------
+// streaming global accesses: state planes are re-read next step (keep in L2), observations are
+// written once and consumed by someone else (evict-first so they do not push the state out of L2)
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pnr_st_stream(float4* ptr, const float4& v) {
+    asm volatile("st.global.cs.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(ptr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void pnr_st_stream(float* ptr, float v) {
+    asm volatile("st.global.cs.f32 [%0], %1;" ::"l"(ptr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float2 pnr_ld_stream(const float2* ptr) {
+    float2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(ptr));
+    return v;
+}
+
+// orderable unsigned encoding of a float (for atomicMax/atomicMin on episode returns)
+__device__ __host__ __forceinline__ uint32_t pnr_float_to_ordered(float f) {
+#ifdef __CUDA_ARCH__
+    const uint32_t u = __float_as_uint(f);
+#else
+    uint32_t u; memcpy(&u, &f, 4);
+#endif
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __host__ __forceinline__ float pnr_ordered_to_float(uint32_t o) {
+    const uint32_t u = (o & 0x80000000u) ? (o & 0x7fffffffu) : ~o;
+#ifdef __CUDA_ARCH__
+    return __uint_as_float(u);
+#else
+    float f; memcpy(&f, &u, 4); return f;
+#endif
+}
+
+// device-side episode statistics (one per handle)
+struct PnrStats {
+    double episodes, sum_return, sum_length, sum_return_sq, reached;
+    uint32_t max_return_ord, min_return_ord;
+};

@@ -1,0 +1,227 @@
+// Device functions of the fused reach-env step: state planes, joint integrator, forward kinematics,
+// reward/done, reset, observation tile.  One thread owns one env; a warp owns a tile of 32 envs whose
+// 32 x 137 observation rows form ONE contiguous 17,536-byte span of the output, staged in shared
+// memory (row stride 137 words is odd => bank-conflict free) and streamed out as coalesced float4.
+#pragma once
+#include "pnr_device.cuh"
+
+#define PNR_TILE_ENVS 32
+#define PNR_TILE_FLOATS (PNR_TILE_ENVS * PNR_OBS_DIM)      // 4384 floats = 17,536 B = 1096 float4
+#define PNR_FULL_MASK 0xffffffffu
+
+// per-env state in registers.  HBM layout: 6 planes of float4[N] (plane-major), so every load/store of
+// a warp is one fully coalesced 512-byte transaction:
+//   plane0 = r0 r1 r2 r3 | plane1 = r4 r5 v0 v1 | plane2 = v2 v3 v4 v5
+//   plane3 = a0 a1 a2 a3 | plane4 = a4 a5 potential episode_return | plane5 = target xyz, t (int bits)
+struct PnrEnv {
+    float r[PNR_DOF], v[PNR_DOF], a[PNR_DOF];
+    float pot, ep_ret;
+    float tgt[3];
+    int32_t t;
+};
+
+__device__ __forceinline__ void pnr_load_env(const float4* __restrict__ S, int64_t N, int64_t e, PnrEnv& s) {
+    const float4 p0 = S[0 * N + e], p1 = S[1 * N + e], p2 = S[2 * N + e];
+    const float4 p3 = S[3 * N + e], p4 = S[4 * N + e], p5 = S[5 * N + e];
+    s.r[0] = p0.x; s.r[1] = p0.y; s.r[2] = p0.z; s.r[3] = p0.w; s.r[4] = p1.x; s.r[5] = p1.y;
+    s.v[0] = p1.z; s.v[1] = p1.w; s.v[2] = p2.x; s.v[3] = p2.y; s.v[4] = p2.z; s.v[5] = p2.w;
+    s.a[0] = p3.x; s.a[1] = p3.y; s.a[2] = p3.z; s.a[3] = p3.w; s.a[4] = p4.x; s.a[5] = p4.y;
+    s.pot = p4.z; s.ep_ret = p4.w;
+    s.tgt[0] = p5.x; s.tgt[1] = p5.y; s.tgt[2] = p5.z; s.t = __float_as_int(p5.w);
+}
+
+__device__ __forceinline__ void pnr_store_env(float4* __restrict__ S, int64_t N, int64_t e, const PnrEnv& s) {
+    S[0 * N + e] = make_float4(s.r[0], s.r[1], s.r[2], s.r[3]);
+    S[1 * N + e] = make_float4(s.r[4], s.r[5], s.v[0], s.v[1]);
+    S[2 * N + e] = make_float4(s.v[2], s.v[3], s.v[4], s.v[5]);
+    S[3 * N + e] = make_float4(s.a[0], s.a[1], s.a[2], s.a[3]);
+    S[4 * N + e] = make_float4(s.a[4], s.a[5], s.pot, s.ep_ret);
+    S[5 * N + e] = make_float4(s.tgt[0], s.tgt[1], s.tgt[2], __int_as_float(s.t));
+}
+
+// reset_world (pioneer_knm_env.py:92-105): a = v = 0, potential = 0; TimeLimit.reset: elapsed = 0
+__device__ __forceinline__ void pnr_reset_env(PnrEnv& s, const float (&q)[PNR_DOF], const float (&tgt)[3]) {
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) { s.r[i] = q[i]; s.v[i] = 0.f; s.a[i] = 0.f; }
+    s.tgt[0] = tgt[0]; s.tgt[1] = tgt[1]; s.tgt[2] = tgt[2];
+    s.pot = 0.f; s.ep_ret = 0.f; s.t = 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// act() integrator for one joint (pioneer_knm_env.py:120-141).  Every operation is an explicitly
+// rounded intrinsic: no FMA contraction, so r and v are BIT-EXACT against the oracle.
+//   PNR_ARITH_F32      : the reference source under NumPy >= 2 (all float32)
+//   PNR_ARITH_LEGACY64 : NumPy 1.x promotion (float64 intermediates, float32 stores)
+// ---------------------------------------------------------------------------------------------
+template <int ARITH>
+__device__ __forceinline__ void pnr_integrate_joint(const PnrParams& p, int i, float a0, float v0, float r0,
+                                                    float& v1_out, float& r1_out) {
+    const float vmax = p.v_max[i];
+    float v1, r1;
+    if (ARITH == PNR_ARITH_F32) {
+        const float dt = p.dt32;
+        v1 = __fadd_rn(v0, __fmul_rn(a0, dt));                                   // :121
+        float dt_p1 = dt, dt_p2 = 0.f;
+        const bool hi = v1 > vmax, lo = v1 < -vmax;                              // :125, :129
+        if (hi || lo) {
+            const float vsat = hi ? vmax : -vmax;
+            const float q = __fdiv_rn(__fsub_rn(vsat, v0), __fadd_rn(a0, p.eps32));  // :126, :130
+            dt_p1 = pnr_clip(q, 0.f, dt);
+            dt_p2 = __fsub_rn(dt, dt_p1);
+            v1 = vsat;
+        }
+        const float half = __fmul_rn(0.5f, __fadd_rn(v0, v1));                   // :134
+        r1 = __fadd_rn(__fadd_rn(r0, __fmul_rn(half, dt_p1)), __fmul_rn(v1, dt_p2));
+    } else {
+        const double dt = p.dt64;
+        v1 = (float)__dadd_rn((double)v0, __dmul_rn((double)a0, dt));
+        double dt_p1 = dt, dt_p2 = 0.0;
+        const bool hi = v1 > vmax, lo = v1 < -vmax;
+        if (hi || lo) {
+            const float vsat = hi ? vmax : -vmax;
+            const double q = __ddiv_rn((double)__fsub_rn(vsat, v0), __dadd_rn((double)a0, p.eps64));
+            dt_p1 = pnr_clip(q, 0.0, dt);
+            dt_p2 = __dsub_rn(dt, dt_p1);
+            v1 = vsat;
+        }
+        const double half = __dmul_rn(0.5, (double)__fadd_rn(v0, v1));
+        r1 = (float)__dadd_rn(__dadd_rn((double)r0, __dmul_rn(half, dt_p1)), __dmul_rn((double)v1, dt_p2));
+    }
+    if (r1 >= p.r_hi[i]) { r1 = p.r_hi[i]; v1 = 0.f; }                           // :135-137
+    if (r1 <= p.r_lo[i]) { r1 = p.r_lo[i]; v1 = 0.f; }                           // :139-141
+    v1_out = v1; r1_out = r1;
+}
+
+__device__ __forceinline__ void pnr_sincos(float x, float& s, float& c) { sincosf(x, &s, &c); }
+
+// ---------------------------------------------------------------------------------------------
+// Forward kinematics of the tracked tip ('robot:pointer'), evaluated tip-to-base:
+//   p <- origin_j + R_origin_j * Rot(axis_j, q_j) * p          (URDF: child = parent*T(origin)*Rot(axis,q))
+// replaces resetJointState x6 + getLinkState (pioneer_knm_env.py:148-151, bullet_scene.py:58).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pnr_fk_tip(const PnrParams& p, const float (&sn)[PNR_DOF], const float (&cs)[PNR_DOF],
+                                           float (&out)[3]) {
+    float x = p.tip_xyz[0], y = p.tip_xyz[1], z = p.tip_xyz[2];
+#pragma unroll
+    for (int j = PNR_DOF - 1; j >= 0; --j) {
+        const float c = cs[j], s = sn[j] * p.axis_sign[j];
+        const int code = p.axis_code[j];            // warp-uniform (constant bank)
+        if (code == PNR_AXIS_X) {
+            const float ny = fmaf(c, y, -s * z), nz = fmaf(s, y, c * z);
+            y = ny; z = nz;
+        } else if (code == PNR_AXIS_Y) {
+            const float nx = fmaf(c, x, s * z), nz = fmaf(-s, x, c * z);
+            x = nx; z = nz;
+        } else if (code == PNR_AXIS_Z) {
+            const float nx = fmaf(c, x, -s * y), ny = fmaf(s, x, c * y);
+            x = nx; y = ny;
+        } else {                                     // Rodrigues: p c + (k x p) s + k (k.p)(1-c)
+            const float kx = p.axis[j][0], ky = p.axis[j][1], kz = p.axis[j][2];
+            const float kp = (kx * x + ky * y + kz * z) * (1.f - c);
+            const float nx = fmaf(x, c, fmaf(ky * z - kz * y, s, kx * kp));
+            const float ny = fmaf(y, c, fmaf(kz * x - kx * z, s, ky * kp));
+            const float nz = fmaf(z, c, fmaf(kx * y - ky * x, s, kz * kp));
+            x = nx; y = ny; z = nz;
+        }
+        if (p.origin_has_rot[j]) {
+            const float* R = p.origin_rot[j];
+            const float nx = R[0] * x + R[1] * y + R[2] * z;
+            const float ny = R[3] * x + R[4] * y + R[5] * z;
+            const float nz = R[6] * x + R[7] * y + R[8] * z;
+            x = nx; y = ny; z = nz;
+        }
+        x += p.origin_xyz[j][0]; y += p.origin_xyz[j][1]; z += p.origin_xyz[j][2];
+    }
+    out[0] = x; out[1] = y; out[2] = z;
+}
+
+// float64 twin, only for envs whose float32 distance falls inside the done band: the reference
+// evaluates `distance < done_distance` in double (pioneer_knm_env.py:155-160), so the done mask is
+// decided in double exactly where float32 could flip it.  Rare => deliberately not inlined.
+__device__ __noinline__ void pnr_fk_tip_f64(const PnrParams& p, const float (&r)[PNR_DOF], const float (&tgt)[3],
+                                             float (&ptr_out)[3], float& dist_out, bool& within) {
+    double x = p.tip_xyz64[0], y = p.tip_xyz64[1], z = p.tip_xyz64[2];
+    for (int j = PNR_DOF - 1; j >= 0; --j) {
+        double s, c;
+        sincos((double)r[j], &s, &c);
+        const double kx = p.axis64[j][0], ky = p.axis64[j][1], kz = p.axis64[j][2];
+        const double kp = (kx * x + ky * y + kz * z) * (1.0 - c);
+        const double nx = x * c + (ky * z - kz * y) * s + kx * kp;
+        const double ny = y * c + (kz * x - kx * z) * s + ky * kp;
+        const double nz = z * c + (kx * y - ky * x) * s + kz * kp;
+        const double* R = p.origin_rot64[j];
+        x = R[0] * nx + R[1] * ny + R[2] * nz + p.origin_xyz64[j][0];
+        y = R[3] * nx + R[4] * ny + R[5] * nz + p.origin_xyz64[j][1];
+        z = R[6] * nx + R[7] * ny + R[8] * nz + p.origin_xyz64[j][2];
+    }
+    const double dx = (double)tgt[0] - x, dy = (double)tgt[1] - y, dz = (double)tgt[2] - z;
+    const double d = sqrt(dx * dx + dy * dy + dz * dz);
+    ptr_out[0] = (float)x; ptr_out[1] = (float)y; ptr_out[2] = (float)z;
+    dist_out = (float)d;
+    within = d < p.done_distance64;
+}
+
+// sincos of the joint angles + tip position + distance to the target for the current r
+struct PnrPose {
+    float sn[PNR_DOF], cs[PNR_DOF];
+    float ptr[3];
+    float dist;
+};
+
+__device__ __forceinline__ void pnr_pose(const PnrParams& p, const PnrEnv& s, PnrPose& o) {
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) pnr_sincos(s.r[i], o.sn[i], o.cs[i]);
+    pnr_fk_tip(p, o.sn, o.cs, o.ptr);
+    const float dx = s.tgt[0] - o.ptr[0], dy = s.tgt[1] - o.ptr[1], dz = s.tgt[2] - o.ptr[2];
+    o.dist = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+}
+
+// compute_potential (pioneer_knm_env.py:232-236)
+__device__ __forceinline__ float pnr_potential(const PnrParams& p, float dist) {
+    return __fdiv_rn(p.pot_max, __fadd_rn(__fdiv_rn(dist, p.pot_slope), 1.f));
+}
+
+// ---------------------------------------------------------------------------------------------
+// observe() (pioneer_knm_env.py:184-211): the 137-float row of one env, written into the warp's
+// shared-memory tile at row `lane`.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void pnr_pack_obs(const PnrParams& p, float* __restrict__ row, const PnrEnv& s,
+                                             const PnrPose& o, float pot) {
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) {
+        const float r = s.r[i];
+        row[0 + i] = r;            row[6 + i] = o.cs[i];         row[12 + i] = o.sn[i];
+        row[18 + i] = p.r_lo[i];   row[24 + i] = p.cos_r_lo[i];  row[30 + i] = p.sin_r_lo[i];
+        row[36 + i] = p.r_hi[i];   row[42 + i] = p.cos_r_hi[i];  row[48 + i] = p.sin_r_hi[i];
+        float sn, cs;
+        const float dlo = __fsub_rn(r, p.r_lo[i]);
+        pnr_sincos(dlo, sn, cs);
+        row[54 + i] = dlo;         row[60 + i] = cs;             row[66 + i] = sn;
+        const float dhi = __fsub_rn(p.r_hi[i], r);
+        pnr_sincos(dhi, sn, cs);
+        row[72 + i] = dhi;         row[78 + i] = cs;             row[84 + i] = sn;
+        pnr_sincos(s.v[i], sn, cs);
+        row[90 + i] = s.v[i];      row[96 + i] = cs;             row[102 + i] = sn;
+        pnr_sincos(s.a[i], sn, cs);
+        row[108 + i] = s.a[i];     row[114 + i] = cs;            row[120 + i] = sn;
+    }
+    row[126] = o.ptr[0]; row[127] = o.ptr[1]; row[128] = o.ptr[2];
+    row[129] = s.tgt[0]; row[130] = s.tgt[1]; row[131] = s.tgt[2];
+    row[132] = s.tgt[0] - o.ptr[0]; row[133] = s.tgt[1] - o.ptr[1]; row[134] = s.tgt[2] - o.ptr[2];
+    row[135] = o.dist;
+    row[136] = pot;
+}
+
+// stream the warp's tile (rows_valid x 137 floats, contiguous in `out`) with coalesced 16-byte stores
+__device__ __forceinline__ void pnr_emit_tile(const float* __restrict__ tile, float* __restrict__ out,
+                                              int rows_valid, int lane) {
+    __syncwarp();
+    const int total = rows_valid * PNR_OBS_DIM;
+    const int n4 = total >> 2;
+    const float4* t4 = reinterpret_cast<const float4*>(tile);
+    float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll 4
+    for (int i = lane; i < n4; i += 32) pnr_st_stream(o4 + i, t4[i]);
+    for (int i = (n4 << 2) + lane; i < total; i += 32) pnr_st_stream(out + i, tile[i]);
+    __syncwarp();
+}

@@ -1,0 +1,19 @@
+// Host-side launch interface between pnr_api.cu (C-ABI) and the kernel translation units.
+#pragma once
+#include <cuda_runtime.h>
+#include "pnr_device.cuh"
+
+#define PNR_STEP_WARPS 4
+#define PNR_STEP_THREADS (PNR_STEP_WARPS * 32)
+#define PNR_STEP_SMEM (PNR_STEP_WARPS * 32 * PNR_OBS_DIM * sizeof(float))   // 70,144 B: 3 CTAs / SM
+#define PNR_MAX_DEVICES 16
+
+cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions,
+                            float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick,
+                            cudaStream_t stream);
+cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, float4* state, const int64_t* idx,
+                                     int64_t n, const float* q0, const float* target, float* obs_out, uint32_t tick,
+                                     cudaStream_t stream);
+cudaError_t pnr_launch_state_io(bool set, float4* state, int64_t N, float* r, float* v, float* a, float* potential,
+                                float* target, int32_t* t, float* ep_return, cudaStream_t stream);
+cudaError_t pnr_launch_stats_snapshot(PnrStats* stats, double env_steps, double* out, int clear, cudaStream_t stream);
