@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""Benchmark of the hot path: env-steps/sec of the batched Pioneer 6-DoF reach env on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--envs-per-gpu E] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One JSON line on stdout (rank 0).  A "step" is ONE fused-kernel pass of the hot path over the whole
+batch of envs with synthetic random actions (BASELINE.json configs[2]: 65,536 envs per GPU, joint limits,
+TimeLimit 500, in-kernel auto-reset; weak scaling: every rank owns its own 65,536 envs, no data-path
+collective).  See DESIGN.md "Measurement" for what each key means and how the bytes are counted.
+
+`--impl reference` times the reference's CPU path (one env per process on all host cores).  PyBullet is
+not installable offline, so the arm runs the CPU restatement in oracle/ (the only place besides the
+`cpu_baseline` leg where this file executes oracle/ code, and never as the thing shipped).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "env-steps/sec (6-DoF reach)"
+UNIT = "env-steps/s"
+DOF, OBS_DIM = 6, 137
+# ALGORITHMIC bytes per env-step: actions 24 + obs 548 + reward 4 + done 1
+# + 23 words of state read and written (92 + 92)
+BYTES_IO = 24 + 548 + 4 + 1
+BYTES_STATE = 2 * 92
+BYTES_PER_ENV_STEP = BYTES_IO + BYTES_STATE          # 761
+FRAME_SKIP = 10
+FALLBACK_HBM_GBS = 6650.0                            # /opt/skills/guides/B200_PROFILING.md fallback
+L2_FLUSH_BYTES = 512 << 20                           # > 4x the 126 MB L2
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of pnr_step_kernel at 65,536 envs from the committed
+# `ncu --set full` capture (profiles/); None until a capture exists
+NCU_TRAFFIC_BYTES_65536 = None
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3000)
+    ap.add_argument("--warmup", type=int, default=100)
+    ap.add_argument("--envs-per-gpu", type=int, default=65536)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-sweep", action="store_true", help="skip the env-count sweep (N=1 only)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-steps-per-proc", type=int, default=0,
+                    help="reference arm: env-steps per process per bench step (0 = sized for ~20 s in total)")
+    return ap.parse_args()
+
+
+# =================================================================================================
+# reference arm / cpu_baseline: the oracle, one env per process on every host core
+# =================================================================================================
+def _host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def _cpu_worker(task):
+    """One reference-style rollout worker: TimeLimit(PioneerKinematicEnv(), 500) restated by oracle.OracleEnv,
+    random actions in [-a_max, a_max], reset on done.  Returns (env_steps, seconds) of the timed part."""
+    proc_id, warm_steps, timed_steps = task
+    import numpy as np
+    from oracle.reach_oracle import OracleChain, OracleEnv
+    from pioneer_b200.urdf import flatten_urdf      # host-side table builder only (no CUDA involved)
+    env = OracleEnv(OracleChain.from_model(flatten_urdf()), arith="np2", global_env_id=proc_id, seed=0)
+    rng = np.random.default_rng(proc_id)
+    tick = 0
+    env.reset_world(tick=tick)
+    actions = (rng.uniform(-1, 1, size=(1024, DOF)) * env.a_max).astype(np.float32)
+
+    def run(n):
+        nonlocal tick
+        for t in range(n):
+            _, _, done, _ = env.step(actions[t & 1023])
+            if done:
+                tick += 1
+                env.reset_world(tick=tick)
+                env.observe()
+
+    run(warm_steps)
+    t0 = time.perf_counter()
+    run(timed_steps)
+    return timed_steps, time.perf_counter() - t0
+
+
+def run_cpu_path(steps: int, warmup: int, per_step: int):
+    """steps x per_step env-steps on each of P processes.  Returns (value, cores, seconds, per_step)."""
+    import multiprocessing as mp
+    cores = _host_cores()
+    if per_step <= 0:
+        # ~1.6k env-steps/s per core for the Python port: aim for ~20 s of timed work per process
+        per_step = max(1, min(512, math.ceil(32000 / max(steps, 1))))
+    tasks = [(i, warmup * per_step if warmup * per_step < 2000 else 2000, steps * per_step) for i in range(cores)]
+    ctx = mp.get_context("spawn")
+    with ctx.Pool(cores) as pool:
+        res = pool.map(_cpu_worker, tasks)
+    total = sum(r[0] for r in res)
+    slowest = max(r[1] for r in res)
+    return total / slowest, cores, slowest, per_step
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    value, cores, seconds, per_step = run_cpu_path(args.steps, args.warmup, args.cpu_steps_per_proc)
+    sample = (f"{cores} processes x 1 env each (the reference's rollout-worker layout), {args.steps} steps x "
+              f"{per_step} env-steps per process, TimeLimit 500 with resets, random actions; "
+              "Python restatement of the reference env (oracle/reach_oracle.py), no PyBullet calls: an upper "
+              "bound on the real reference's speed")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * seconds / max(args.steps, 1),
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64/f32 (numpy)",
+        "data": "synthetic",
+        "config": {"workload": "one reach env per host process, random actions, TimeLimit 500",
+                   "envs": cores, "env_steps_per_step": cores * per_step},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "substeps_per_sec": value * FRAME_SKIP, "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline_subprocess(seconds_budget: float = 20.0):
+    """Run the reference arm in a fresh interpreter (this process holds a CUDA context) and parse its line."""
+    steps = 250
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--steps", str(steps), "--warmup", "3",
+           "--cpu-steps-per-proc", str(max(1, int(seconds_budget * 1600 / steps)))]
+    env = {k: v for k, v in os.environ.items() if k not in ("RANK", "LOCAL_RANK", "WORLD_SIZE")}
+    out = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=600)
+    for ln in reversed(out.stdout.strip().splitlines()):
+        if ln.startswith("{"):
+            return json.loads(ln)["cpu_baseline"]
+    raise RuntimeError("cpu baseline failed: " + out.stderr[-2000:])
+
+
+# =================================================================================================
+# clocks during the timed region
+# =================================================================================================
+_REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x10: "sync_boost", 0x20: "sw_thermal_slowdown",
+            0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake_slowdown", 0x2: "applications_clocks_setting"}
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, torch_device_index: int, period_s: float = 0.01):
+        super().__init__(daemon=True)
+        self.period = period_s
+        self.samples, self.bits, self.power = [], 0, []
+        self._stop_evt = threading.Event()
+        self.ok = False
+        self.max_mhz = None
+        try:
+            import pynvml
+            import torch
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            uuid = str(torch.cuda.get_device_properties(torch_device_index).uuid)
+            try:
+                self.h = pynvml.nvmlDeviceGetHandleByUUID(("GPU-" + uuid) if not uuid.startswith("GPU-") else uuid)
+            except Exception:  # noqa: BLE001
+                self.h = pynvml.nvmlDeviceGetHandleByIndex(torch_device_index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.ok = True
+        except Exception as exc:  # noqa: BLE001
+            self.err = repr(exc)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:  # noqa: BLE001
+                    self.bits |= int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1e3)
+            except Exception:  # noqa: BLE001
+                pass
+            time.sleep(self.period)
+
+    def finish(self):
+        self._stop_evt.set()
+        if self.is_alive():
+            self.join(timeout=2)
+        if not self.ok or not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0,
+                    "note": getattr(self, "err", "no samples")}
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2], "sm_max_mhz": self.max_mhz,
+                "reasons": [name for bit, name in _REASONS.items() if self.bits & bit], "samples": len(s),
+                "power_w_max": max(self.power) if self.power else None}
+
+
+# =================================================================================================
+# our arm
+# =================================================================================================
+def measured_hbm_peak():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (of measured)"
+    except Exception:  # noqa: BLE001
+        return FALLBACK_HBM_GBS, "B200_PROFILING.md fallback (of fallback)"
+
+
+def time_device_steps(torch, env, actions, obs_ring, reward, flags, steps, warmup, flush):
+    """K steps, each bracketed by its own CUDA-event pair on the launching stream; an untimed L2 flush
+    (512 MiB memset) runs between steps.  Returns (sum of kernel ms, list of per-step ms)."""
+    n_act, n_obs = actions.shape[0], obs_ring.shape[0]
+    for k in range(warmup):
+        if flush is not None:
+            flush.zero_()
+        env.step_tensor(actions[k % n_act], out=(obs_ring[k % n_obs], reward, flags))
+    starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
+    torch.cuda.synchronize()
+    for k in range(steps):
+        if flush is not None:
+            flush.zero_()
+        starts[k].record()
+        env.step_tensor(actions[k % n_act], out=(obs_ring[k % n_obs], reward, flags))
+        stops[k].record()
+    torch.cuda.synchronize()
+    per = [s.elapsed_time(e) for s, e in zip(starts, stops)]
+    return sum(per), per
+
+
+def time_back_to_back(torch, env, actions, obs_ring, reward, flags, steps):
+    n_act, n_obs = actions.shape[0], obs_ring.shape[0]
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for k in range(steps):
+        env.step_tensor(actions[k % n_act], out=(obs_ring[k % n_obs], reward, flags))
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e)
+
+
+def make_buffers(torch, env, n, device, seed):
+    g = torch.Generator(device=device).manual_seed(seed)
+    a_max = torch.as_tensor(env.a_max, device=device)
+    n_act = 8
+    actions = (torch.rand((n_act, n, DOF), device=device, generator=g) * 2 - 1) * a_max
+    # rollout-fragment style observation ring: consecutive steps write different slots
+    n_obs = max(2, min(8, (1 << 30) // (n * OBS_DIM * 4)))
+    obs_ring = torch.empty((n_obs, n, OBS_DIM), dtype=torch.float32, device=device)
+    reward = torch.empty(n, dtype=torch.float32, device=device)
+    flags = torch.empty(n, dtype=torch.uint8, device=device)
+    return actions, obs_ring, reward, flags
+
+
+def ours_arm(args):
+    import torch
+    import torch.distributed as dist
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    from pioneer_b200.distributed import reduce_episode_stats, summarize
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback "
+                         "(use --impl reference for the CPU arm)")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if world == 1 and args.gpus > 1:
+        raise SystemExit("bench.py: for --gpus N > 1 launch with torch.distributed.run, one rank per GPU")
+    device = torch.device("cuda", local_rank)
+    torch.cuda.set_device(device)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    n = args.envs_per_gpu
+    env = BatchedPioneerEnv(n, device=device, seed=0, env_id_base=rank * n,
+                            batch_config=BatchConfig(max_episode_steps=500, auto_reset=True, obs_mode="terminal"))
+    actions, obs_ring, reward, flags = make_buffers(torch, env, n, device, seed=rank)
+    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x: float) -> float:
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    # ---- device-resident throughput: `value` ---------------------------------------------------------
+    env.episode_stats(clear=True)
+    barrier()
+    if sampler:
+        sampler.start()
+    launches0 = env.launch_count
+    wall0 = time.perf_counter()
+    kernel_ms, per_step = time_device_steps(torch, env, actions, obs_ring, reward, flags, args.steps, args.warmup, flush)
+    launches = env.launch_count - launches0 - args.warmup
+    # the path's one collective: episode statistics, once per iteration (here: once per timed region)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    stats = reduce_episode_stats(env.episode_stats_tensor())
+    ev1.record()
+    barrier()
+    wall_s = time.perf_counter() - wall0
+    stats_ms = ev0.elapsed_time(ev1)
+    kernel_ms_max = max_over_ranks(kernel_ms)
+    total_envs = n * world
+    value = total_envs * args.steps / (kernel_ms_max / 1e3)
+    clocks = sampler.finish() if sampler else None
+
+    # ---- same loop without the L2 flush (what a rollout loop sees: state planes stay L2-resident) -------
+    barrier()
+    warm_ms = max_over_ranks(time_back_to_back(torch, env, actions, obs_ring, reward, flags, args.steps))
+    value_l2_warm = total_envs * args.steps / (warm_ms / 1e3)
+
+    # ---- end to end through the public host API: pinned host actions in, obs/reward/done out ------------
+    e2e_steps = min(args.steps, 300)
+    host_actions = [torch.empty((n, DOF), dtype=torch.float32, pin_memory=True).copy_(actions[i]) for i in range(4)]
+    for k in range(3):
+        env.step_host(host_actions[k % 4])
+    barrier()
+    t0 = time.perf_counter()
+    checksum = 0.0
+    for k in range(e2e_steps):
+        _, h_reward, _ = env.step_host(host_actions[k % 4])
+        checksum += float(h_reward[0])
+    torch.cuda.synchronize()
+    e2e_s = max_over_ranks(time.perf_counter() - t0)
+    e2e_value = total_envs * e2e_steps / e2e_s
+
+    peak, peak_src = measured_hbm_peak()
+    avg_ms = kernel_ms / args.steps                      # this rank's kernel, per launch
+    achieved = BYTES_PER_ENV_STEP * n / (avg_ms / 1e3) / 1e9
+    srt = sorted(per_step)
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": kernel_ms_max / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"BASELINE.json configs[2]: batched reach env, {n} envs per GPU, joint limits, "
+                               "TimeLimit 500, in-kernel auto-reset, uniform random actions in [-a_max, a_max]",
+                   "envs_per_gpu": n, "total_envs": total_envs, "mode": "kinematic (the reference env)",
+                   "arith": "f32", "obs": "float32[N,137] terminal observations, 8-slot rollout ring",
+                   "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB memset, untimed); each step "
+                         "timed by its own CUDA-event pair on the launching stream",
+                   "parallelism": f"env-sharded x{world}, no data-path collective; one stats all-reduce per iteration"},
+        "substeps_per_sec": value * FRAME_SKIP,
+        "value_l2_warm": value_l2_warm,
+        "ms_per_step_l2_warm": warm_ms / args.steps,
+        "step_ms_percentiles": {"p5": srt[len(srt) // 20], "p50": srt[len(srt) // 2], "p95": srt[(len(srt) * 19) // 20]},
+        "stats_allreduce_ms": stats_ms,
+        "episode_stats": summarize(stats),
+        "wall_s_timed_region_incl_flush": wall_s,
+        "gpu_launches": launches,
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * DOF * 4,
+                "d2h_bytes_per_step": n * (OBS_DIM * 4 + 4 + 1), "steps": e2e_steps,
+                "api": "BatchedPioneerEnv.step_host -> pnr_step_host (pinned host buffers, copies inside the timed region)",
+                "timer": "host perf_counter around synchronous calls, max over ranks"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": NCU_TRAFFIC_BYTES_65536 if n == 65536 else None, "kernel": "pnr_step_kernel<F32,TERMINAL>",
+                     "bytes_per_env_step": BYTES_PER_ENV_STEP, "units_per_launch": n, "peak_source": peak_src},
+    }
+    env.close()
+    del obs_ring, actions
+
+    # ---- env-count sweep (N=1 only): the metric is quoted at 4K..1M envs --------------------------------
+    if world == 1 and not args.no_sweep:
+        sweep = []
+        for m in (4096, 16384, 131072, 1048576):
+            e = BatchedPioneerEnv(m, device=device, seed=0, batch_config=BatchConfig(max_episode_steps=500))
+            a, o, r, f = make_buffers(torch, e, m, device, seed=1)
+            k_steps = min(args.steps, 1000)
+            ms, _ = time_device_steps(torch, e, a, o, r, f, k_steps, min(args.warmup, 20), flush)
+            ms_w = time_back_to_back(torch, e, a, o, r, f, k_steps)
+            gbs = BYTES_PER_ENV_STEP * m / (ms / k_steps / 1e3) / 1e9
+            sweep.append({"envs": m, "ms_per_step": ms / k_steps, "value": m * k_steps / (ms / 1e3),
+                          "value_l2_warm": m * k_steps / (ms_w / 1e3), "achieved_gbs": gbs, "frac": gbs / peak})
+            e.close()
+            del a, o, r, f
+        line["sweep"] = sweep
+
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        try:
+            line["cpu_baseline"] = cpu_baseline_subprocess()
+        except Exception as exc:  # noqa: BLE001
+            line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": _host_cores(), "kind": "port",
+                                    "sample": f"failed: {exc!r}"}
+    if rank == 0:
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        ours_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,55 @@
+"""Multi-GPU sharding of the env batch and the one collective the path has.
+
+Envs are independent: a job of ``total_envs`` is cut into contiguous ranges of global env ids, one
+per rank / GPU, with no data-path communication.  Once per training iteration the per-GPU episode
+statistics (the columns the reference CLI prints, cli.py:32-38) are reduced with NCCL over
+NVLink: SUM over the counters and MAX over (max_return, -min_return).  The reference moves the same
+numbers from its Ray rollout workers to the trainer (pioneer/launch/pioneer_knm_train.py:49).
+"""
+from __future__ import annotations
+
+from typing import Dict, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+from .batched_env import STATS_FIELDS
+
+SUM_SLOTS = (0, 1, 2, 3, 6, 7)
+MAX_SLOTS = (4, 5)
+
+
+def shard_range(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
+    """(env_id_base, n_local): contiguous split, the first ``total % world`` ranks get one more."""
+    assert 0 <= rank < world_size and total_envs >= world_size
+    q, r = divmod(total_envs, world_size)
+    n_local = q + (1 if rank < r else 0)
+    base = rank * q + min(rank, r)
+    return base, n_local
+
+
+def reduce_episode_stats(local: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-reduce the packed float64[8] statistics vector (any backend; NCCL on the GPUs).
+    Two collectives: SUM and MAX.  Returns a new tensor on the same device."""
+    assert local.dtype == torch.float64 and local.numel() == len(STATS_FIELDS)
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return local.clone()
+    sums = local[list(SUM_SLOTS)].contiguous()
+    maxs = torch.stack([local[4], -local[5]])
+    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
+    dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
+    out = torch.empty_like(local)
+    out[list(SUM_SLOTS)] = sums
+    out[4], out[5] = maxs[0], -maxs[1]
+    return out
+
+
+def summarize(stats: torch.Tensor) -> Dict[str, float]:
+    """episode_reward_max/min/mean, episode_len_mean, episodes_total (cli.py:32-38) from the packed vector."""
+    s = [float(x) for x in stats.tolist()]
+    n = s[0]
+    mean = s[1] / n if n else float("nan")
+    var = max(s[3] / n - mean * mean, 0.0) if n else float("nan")
+    return {"episodes_total": n, "episode_reward_mean": mean, "episode_reward_std": var ** 0.5 if n else float("nan"),
+            "episode_reward_max": s[4] if n else float("nan"), "episode_reward_min": s[5] if n else float("nan"),
+            "episode_len_mean": s[2] / n if n else float("nan"), "env_steps": s[6], "reached_target": s[7]}

@@ -1,0 +1,342 @@
+"""Parity of the CUDA path (through the C-ABI, include/pioneer_b200.h) against
+  * the golden vectors recorded from the unmodified reference source (tests/golden/make_golden.py), and
+  * the CPU oracle (oracle/reach_oracle.py) on the same seeded inputs.
+
+Bars:
+  * joint state r, v, a                : BIT-EXACT (explicitly rounded IEEE float32 arithmetic, no FMA)
+  * done / truncated masks             : BIT-EXACT (the distance test is re-decided in float64 inside a band)
+  * pointer xyz, distance              : |diff| <= 2e-4   (float32 FK at ~30-unit reach vs the reference's float64)
+  * potential, reward                  : |diff| <= 1e-3   (d potential / d distance <= 9.5)
+  * cos / sin observation columns      : |diff| <= 5e-7   (CUDA sincosf vs numpy float32 cos/sin, ~1 ulp each)
+  * every other observation column     : BIT-EXACT
+"""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle.reach_oracle import PNR_DONE, PNR_TRUNCATED, OracleBatch, OracleConfig
+from tests._util import golden_case, load_golden, oracle_chain
+
+pytestmark = pytest.mark.gpu
+
+POS_TOL = 2e-4
+REW_TOL = 1e-3
+TRIG_TOL = 5e-7
+
+# observation columns (pioneer_knm_env.py:194-211): value blocks and their cos / sin blocks
+VALUE_COLS = np.r_[0:6, 18:24, 36:42, 54:60, 72:78, 90:96, 108:114, 129:132]
+TRIG_COLS = np.r_[6:18, 24:36, 42:54, 60:72, 78:90, 96:108, 114:126]
+POS_COLS = np.r_[126:129, 132:136]
+
+
+def make_env(n, **kw):
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv, PioneerKinematicConfig
+    bc_keys = ("max_episode_steps", "auto_reset", "obs_mode", "arith")
+    bc = BatchConfig(**{k: kw.pop(k) for k in bc_keys if k in kw})
+    pc = kw.pop("pioneer_config", None)
+    if isinstance(pc, dict):
+        pc = PioneerKinematicConfig(**pc)
+    return BatchedPioneerEnv(n, batch_config=bc, pioneer_config=pc, **kw)
+
+
+def check_obs(obs_gpu, obs_ref, what=""):
+    obs_gpu = np.asarray(obs_gpu, np.float64)
+    obs_ref = np.asarray(obs_ref, np.float64)
+    assert np.array_equal(obs_gpu[..., VALUE_COLS], obs_ref[..., VALUE_COLS].astype(np.float32)), what
+    np.testing.assert_allclose(obs_gpu[..., TRIG_COLS], obs_ref[..., TRIG_COLS], rtol=0, atol=TRIG_TOL, err_msg=what)
+    np.testing.assert_allclose(obs_gpu[..., POS_COLS], obs_ref[..., POS_COLS], rtol=0, atol=POS_TOL, err_msg=what)
+    np.testing.assert_allclose(obs_gpu[..., 136], obs_ref[..., 136], rtol=0, atol=REW_TOL, err_msg=what)
+
+
+G = load_golden()
+
+
+def replay_golden(name, pioneer_config=None):
+    """One env driven exactly like tests/golden/make_golden.py::rollout drove the reference."""
+    case = golden_case(G, name)
+    env = make_env(1, max_episode_steps=500, auto_reset=False, pioneer_config=pioneer_config)
+    ep = 0
+    first = env.reset_world(case["q0"][ep][None], case["target"][ep][None], observe=True).cpu().numpy()[0]
+    check_obs(first, case["reset_obs"][ep], f"{name} reset obs")
+    obs_at = {int(t): k for k, t in enumerate(case["obs_idx"])}
+    actions = torch.as_tensor(case["actions"]).cuda()
+    for t in range(len(case["actions"])):
+        obs, reward, flags = env.step_tensor(actions[t:t + 1])
+        s = env.state()
+        r, v, a = (s[k].cpu().numpy()[0] for k in ("r", "v", "a"))
+        assert np.array_equal(r, case["r"][t]), (name, t, r, case["r"][t])
+        assert np.array_equal(v, case["v"][t]), (name, t, v, case["v"][t])
+        assert np.array_equal(a, case["a"][t]), (name, t)
+        f = int(flags[0])
+        assert bool(f & PNR_DONE) == bool(case["done"][t]), (name, t)
+        assert bool(f & PNR_TRUNCATED) == bool(case["truncated"][t]), (name, t)
+        o = obs.cpu().numpy()[0]
+        np.testing.assert_allclose(o[126:136], case["tail"][t][:10], rtol=0, atol=POS_TOL, err_msg=f"{name} {t}")
+        np.testing.assert_allclose(o[136], case["tail"][t][10], rtol=0, atol=REW_TOL)
+        np.testing.assert_allclose(float(reward[0]), case["reward"][t], rtol=0, atol=REW_TOL, err_msg=f"{name} {t}")
+        if t in obs_at:
+            check_obs(o, case["obs"][obs_at[t]], f"{name} obs at {t}")
+        if case["done"][t]:
+            ep += 1
+            first = env.reset_world(case["q0"][ep][None], case["target"][ep][None], observe=True).cpu().numpy()[0]
+            check_obs(first, case["reset_obs"][ep], f"{name} reset obs {ep}")
+    env.close()
+
+
+@pytest.mark.parametrize("name", ["cfg1", "gentle", "bangbang", "wild", "zero", "reach", "approach"])
+def test_golden_replay(name):
+    replay_golden(name)
+
+
+def test_golden_reward_knobs():
+    replay_golden("knobs", dict(award_potential_slope=4.0, award_done=7.5, penalty_step=0.02))
+
+
+def test_golden_multi_env_batch():
+    """16 envs x 200 steps in ONE batch (a half-filled warp tile); env 0 is the cfg1 trajectory."""
+    env = make_env(16, max_episode_steps=500, auto_reset=False)
+    env.reset_world(G["multi__q0"], G["multi__target"])
+    actions = torch.as_tensor(G["multi__actions"]).cuda()
+    for t in range(200):
+        obs, reward, flags = env.step_tensor(actions[:, t].contiguous())
+        s = env.state()
+        assert np.array_equal(s["r"].cpu().numpy(), G["multi__r"][:, t]), t
+        assert np.array_equal(s["v"].cpu().numpy(), G["multi__v"][:, t]), t
+        np.testing.assert_allclose(reward.cpu().numpy(), G["multi__reward"][:, t], rtol=0, atol=REW_TOL)
+        np.testing.assert_allclose(obs.cpu().numpy()[:, 126:136], G["multi__tail"][:, t, :10], rtol=0, atol=POS_TOL)
+        assert np.array_equal((flags.cpu().numpy() & 1).astype(bool), G["multi__done"][:, t])
+    env.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# CUDA path vs CPU oracle on the same seeded inputs: Philox resets, auto-reset, both observation
+# modes, both arithmetic modes, ragged batch sizes (not a multiple of the 32-env warp tile)
+# ---------------------------------------------------------------------------------------------
+def run_vs_oracle(n, steps, arith, obs_mode, max_episode_steps, seed, env_id_base=0, action_scale=1.0,
+                  near_targets=False):
+    chain = oracle_chain()
+    cfg = OracleConfig(max_episode_steps=max_episode_steps)
+    ob = OracleBatch(chain, n, cfg, arith={"f32": "np2", "legacy64": "legacy"}[arith], env_id_base=env_id_base,
+                     seed=seed, auto_reset=True, obs_mode=obs_mode)
+    env = make_env(n, max_episode_steps=max_episode_steps, auto_reset=True, obs_mode=obs_mode, arith=arith,
+                   seed=seed, env_id_base=env_id_base)
+    # both sides were created reset with tick 0: same Philox draws
+    s = env.state()
+    os_ = ob.state()
+    assert np.array_equal(s["r"].cpu().numpy(), os_["r"])
+    assert np.array_equal(s["target"].cpu().numpy(), os_["target"].astype(np.float32))
+    if near_targets:      # put every target within reach of the pointer so the distance-done path fires
+        rng = np.random.default_rng(seed + 5)
+        ptr = np.array([e.observe()[126:129] for e in ob.envs])
+        tgt = (ptr + rng.normal(size=(n, 3)) * 0.08).astype(np.float32)
+        q0 = os_["r"]
+        ob.reset(q0=q0, target=tgt)
+        env.reset_world(q0, tgt)
+    check_obs(env.observe().cpu().numpy(), np.array([e.observe() for e in ob.envs]), "initial obs")
+    rng = np.random.default_rng(seed + 1)
+    a_max = env.a_max
+    n_done = 0
+    for t in range(steps):
+        act = (rng.uniform(-1, 1, size=(n, 6)) * a_max * action_scale).astype(np.float32)
+        obs, reward, flags = env.step_tensor(torch.as_tensor(act).cuda())
+        o_obs, o_reward, o_flags = ob.step(act)
+        assert np.array_equal(flags.cpu().numpy(), o_flags), f"done mask differs at step {t}"
+        n_done += int((o_flags & 1).sum())
+        s, os_ = env.state(), ob.state()
+        for k in ("r", "v", "a"):
+            assert np.array_equal(s[k].cpu().numpy(), os_[k]), f"{k} differs at step {t}"
+        assert np.array_equal(s["t"].cpu().numpy(), os_["t"]), t
+        assert np.array_equal(s["target"].cpu().numpy(), os_["target"].astype(np.float32)), t
+        np.testing.assert_allclose(reward.cpu().numpy(), o_reward, rtol=0, atol=REW_TOL)
+        np.testing.assert_allclose(s["ep_return"].cpu().numpy(), os_["ep_return"], rtol=0, atol=REW_TOL * (t + 2))
+        check_obs(obs.cpu().numpy(), o_obs, f"step {t}")
+    st = env.episode_stats()
+    assert st["episodes"] == ob.stats[0] == n_done
+    assert st["env_steps"] == ob.stats[6] == n * steps
+    assert st["reached_target"] == ob.stats[7]
+    if n_done:
+        np.testing.assert_allclose(st["sum_return"], ob.stats[1], rtol=1e-5, atol=REW_TOL * steps)
+        np.testing.assert_allclose(st["sum_length"], ob.stats[2])
+        np.testing.assert_allclose([st["max_return"], st["min_return"]], ob.stats[4:6], atol=REW_TOL * steps)
+    env.close()
+    return n_done
+
+
+@pytest.mark.parametrize("arith", ["f32", "legacy64"])
+@pytest.mark.parametrize("obs_mode", ["terminal", "autoreset"])
+def test_vs_oracle_random_rollout(arith, obs_mode):
+    # TimeLimit 7 => every env auto-resets 3 times in 24 steps; 77 envs = 2 full warp tiles + a ragged one
+    n_done = run_vs_oracle(77, 24, arith, obs_mode, max_episode_steps=7, seed=1234)
+    assert n_done == 77 * 3
+
+
+def test_vs_oracle_distance_done_and_autoreset():
+    n_done = run_vs_oracle(40, 12, "f32", "terminal", max_episode_steps=500, seed=99, action_scale=0.002,
+                           near_targets=True)
+    assert n_done >= 10
+
+
+def test_vs_oracle_sharded_ids():
+    """env_id_base offsets the Philox counter: a shard starting at global id 1000 matches the oracle's."""
+    run_vs_oracle(33, 10, "f32", "terminal", max_episode_steps=4, seed=7, env_id_base=1000)
+
+
+def test_single_env_and_tiny_batches():
+    for n in (1, 2, 31, 32, 33):
+        run_vs_oracle(n, 3, "f32", "terminal", max_episode_steps=2, seed=n)
+
+
+# ---------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE.json's full sizes
+# ---------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n", [4096, 65536])
+def test_invariants_full_size(n):
+    env = make_env(n, max_episode_steps=500, auto_reset=True, seed=3)
+    obs0 = env.reset()
+    # (i) after reset: a = v = 0, potential = 0 -> obs[90:126] = {0,1,0,0,1,0} pattern, obs[136] = 0
+    o = obs0.cpu().numpy()
+    assert (o[:, 90:96] == 0).all() and (o[:, 96:102] == 1).all() and (o[:, 102:108] == 0).all()
+    assert (o[:, 108:114] == 0).all() and (o[:, 114:120] == 1).all() and (o[:, 120:126] == 0).all()
+    assert (o[:, 136] == 0).all()
+    r_lo, r_hi, v_max = (torch.as_tensor(x).cuda() for x in (env.r_lo, env.r_hi, env.v_max))
+    tlo, thi = (torch.tensor(x, dtype=torch.float32).cuda() for x in (env.config.target_lo, env.config.target_hi))
+    assert ((obs0[:, 0:6] >= r_lo) & (obs0[:, 0:6] <= r_hi)).all()
+    assert ((obs0[:, 129:132] >= tlo) & (obs0[:, 129:132] <= thi)).all()
+    g = torch.Generator(device="cuda").manual_seed(0)
+    a_max = torch.as_tensor(env.a_max).cuda()
+    prev_pot = torch.zeros(n, device="cuda")
+    prev_r = obs0[:, 0:6].clone()
+    for t in range(1, 41):
+        act = (torch.rand((n, 6), device="cuda", generator=g) * 2 - 1) * a_max
+        if t == 1:
+            act_first = act.clone()
+        obs, reward, flags = env.step_tensor(act)
+        r, v, a = obs[:, 0:6], obs[:, 90:96], obs[:, 108:114]
+        # (iv) bounds; v == 0 exactly on a limit
+        assert ((r >= r_lo) & (r <= r_hi)).all() and (v.abs() <= v_max).all()
+        on_limit = (r == r_lo) | (r == r_hi)
+        assert (v[on_limit] == 0).all()
+        # (v) the action given at step t first moves the arm at step t+1
+        if t == 1:
+            assert torch.equal(r, prev_r)
+        assert torch.equal(a, act)
+        # (vi) obs[132:135] = target - pointer, obs[135] = norm
+        diff = obs[:, 129:132] - obs[:, 126:129]
+        assert torch.allclose(obs[:, 132:135], diff, atol=1e-5)
+        assert torch.allclose(obs[:, 135], diff.double().norm(dim=1).float(), atol=1e-4)
+        # (ii) reward = potential - old potential - 0.01 (+5): no env is done by distance here
+        reached = (flags & PNR_DONE).bool() & ~(flags & PNR_TRUNCATED).bool()
+        expect = obs[:, 136] - prev_pot - 0.01 + 5.0 * reached
+        assert torch.allclose(reward, expect, atol=1e-4)
+        pot = 95.0 / (obs[:, 135].double() / 10.0 + 1.0)
+        assert torch.allclose(obs[:, 136].double(), pot, atol=1e-4)
+        prev_pot = torch.where((flags & PNR_DONE).bool(), torch.zeros_like(prev_pot), obs[:, 136])
+        # trig columns are the sin/cos of their value columns
+        assert torch.allclose(obs[:, 6:12], torch.cos(r.double()).float(), atol=1e-6)
+        assert torch.allclose(obs[:, 120:126], torch.sin(a.double()).float(), atol=1e-6)
+    assert env.episode_stats()["env_steps"] == 40 * n
+    env.close()
+
+
+def test_time_limit_and_zero_action_properties():
+    """(iii) a == 0 forever: r constant, reward == -0.01 from step 2 on; (vii) done at step 500 whatever the distance."""
+    n = 4096
+    env = make_env(n, max_episode_steps=500, auto_reset=True, seed=11)
+    obs0 = env.reset().clone()
+    zero = torch.zeros((n, 6), device="cuda")
+    for t in range(1, 501):
+        obs, reward, flags = env.step_tensor(zero)
+        if t == 2:
+            assert torch.equal(obs[:, 0:6], obs0[:, 0:6])
+            assert torch.allclose(reward, torch.full_like(reward, -0.01), atol=1e-6)
+        if t < 500:
+            assert int(flags.max()) == 0
+    assert (flags == (PNR_DONE | PNR_TRUNCATED)).all()
+    assert torch.equal(obs[:, 0:6], obs0[:, 0:6])            # terminal observation, not the reset one
+    st = env.episode_stats()
+    assert st["episodes"] == n and st["sum_length"] == 500 * n and st["reached_target"] == 0
+    after = env.state()
+    assert (after["t"] == 0).all() and not torch.equal(after["r"], obs0[:, 0:6])   # auto-reset drew new episodes
+    env.close()
+
+
+def test_sharding_is_invisible():
+    """Two handles covering global ids [0, 3000) and [3000, 6000) reproduce one handle of 6000 envs bit for bit."""
+    n = 6000
+    whole = make_env(n, max_episode_steps=5, seed=21)
+    lo = make_env(3000, max_episode_steps=5, seed=21, env_id_base=0)
+    hi = make_env(3000, max_episode_steps=5, seed=21, env_id_base=3000)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a_max = torch.as_tensor(whole.a_max).cuda()
+    for t in range(12):
+        act = (torch.rand((n, 6), device="cuda", generator=g) * 2 - 1) * a_max
+        o, r, f = whole.step_tensor(act)
+        o1, r1, f1 = lo.step_tensor(act[:3000].contiguous())
+        o2, r2, f2 = hi.step_tensor(act[3000:].contiguous())
+        assert torch.equal(o, torch.cat([o1, o2])) and torch.equal(r, torch.cat([r1, r2]))
+        assert torch.equal(f, torch.cat([f1, f2]))
+    a, b, c = whole.episode_stats(), lo.episode_stats(), hi.episode_stats()
+    assert a["episodes"] == b["episodes"] + c["episodes"] == 2 * n
+    for e in (whole, lo, hi):
+        e.close()
+
+
+def test_step_host_matches_step_tensor():
+    n = 1000
+    a_env = make_env(n, max_episode_steps=6, seed=5)
+    b_env = make_env(n, max_episode_steps=6, seed=5)
+    rng = np.random.default_rng(0)
+    for t in range(8):
+        act = (rng.uniform(-1, 1, size=(n, 6)) * a_env.a_max).astype(np.float32)
+        o, r, f = a_env.step_tensor(torch.as_tensor(act).cuda())
+        ho, hr, hf = b_env.step_host(act)
+        assert np.array_equal(o.cpu().numpy(), ho) and np.array_equal(r.cpu().numpy(), hr)
+        assert np.array_equal(f.cpu().numpy(), hf)
+    a_env.close(); b_env.close()
+
+
+def test_reset_subset_and_observe_indices():
+    n = 100
+    env = make_env(n, max_episode_steps=0, auto_reset=False, seed=2)
+    before = env.state()
+    idx = [3, 50, 99]
+    q0 = np.zeros((3, 6), np.float32)
+    tg = np.array([[20, 0, 4]] * 3, np.float32)
+    obs = env.reset_world(q0, tg, indices=idx, observe=True).cpu().numpy()
+    np.testing.assert_allclose(obs[:, 126:129], [[14.6, 1.0, 15.9]] * 3, atol=1e-5)     # FK known answer, q = 0
+    after = env.state()
+    keep = np.setdiff1d(np.arange(n), idx)
+    assert torch.equal(after["r"][keep], before["r"][keep])
+    assert (after["r"][idx] == 0).all()
+    assert np.array_equal(env.observe(indices=idx).cpu().numpy(), obs)
+    env.close()
+
+
+def test_fk_known_answers_on_device():
+    """Hand-derived known answers, SURVEY.md section 8(c) C5, through pnr_reset + pnr_observe."""
+    kat = {
+        (0, 0, 0, 0, 0, 0): (14.6, 1.0, 15.9),
+        (0.5, 0, 0, 0, 0, 0): (12.333279864995, 7.877195425512, 15.9),
+        (0, 0.5, 0, 0, 0, 0): (18.997294851594, 1.0, 7.321202184764),
+        (0, 0, 0.5, 0, 0, 0): (13.723613926947, 1.0, 8.667794003970),
+        (0, 0, 0, 0.5, 0, 0): (14.6, 0.089091476652, 15.667406867592),
+        (0, 0, 0, 0, 0.5, 0): (15.070205746153, 1.0, 13.941474928617),
+        (0, 0, 0, 0, 0, 0.5): (14.6, 0.089091476652, 15.667406867592),
+        (0.3, -0.4, 0.9, 1.1, -0.7, 2.0): (7.904033967723, 1.072102752440, 5.624962379045),
+    }
+    env = make_env(len(kat), max_episode_steps=0, auto_reset=False)
+    q = np.array(list(kat.keys()), np.float32)
+    obs = env.reset_world(q, np.zeros((len(kat), 3), np.float32), observe=True).cpu().numpy()
+    np.testing.assert_allclose(obs[:, 126:129], np.array(list(kat.values())), atol=2e-5)
+    env.close()
+
+
+def test_errors_are_loud():
+    from pioneer_b200 import _cabi
+    env = make_env(8)
+    with pytest.raises(_cabi.PioneerB200Error):
+        _cabi.check(env._lib.pnr_step(env._h, None, None, None, None, None), "pnr_step")
+    with pytest.raises(_cabi.PioneerB200Error):
+        _cabi.check(env._lib.pnr_reset(env._h, None, 3, None, None, None, None), "pnr_reset")
+    env.close()
