@@ -109,6 +109,10 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
         p.r_hi[j] = (float)m.upper[j];
         p.v_max[j] = (float)c.max_v_to_r * (p.r_hi[j] - p.r_lo[j]);
         a_max[j] = (float)c.max_a_to_v * p.v_max[j];
+        if (!(p.v_max[j] <= 1.0e5f)) p.trig_slow = 1;      // joint rates beyond the fast sincos range (pnr_trig.cuh)
+        // the step kernel evaluates sin/cos of angles inside [r_lo, r_hi] and of limit distances with the fast path
+        if (!(std::fabs(m.lower[j]) <= 1.0e4 && std::fabs(m.upper[j]) <= 1.0e4 && m.lower[j] <= m.upper[j]))
+            return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_model joint limits must satisfy -1e4 <= lower <= upper <= 1e4 rad");
         // float32 cos/sin of float32 limits (np.cos on a float32 array); computed in double and rounded once
         p.cos_r_lo[j] = (float)std::cos((double)p.r_lo[j]); p.sin_r_lo[j] = (float)std::sin((double)p.r_lo[j]);
         p.cos_r_hi[j] = (float)std::cos((double)p.r_hi[j]); p.sin_r_hi[j] = (float)std::sin((double)p.r_hi[j]);

@@ -40,6 +40,7 @@ struct PnrParams {
     float target_lo[3], target_hi[3];
     int32_t max_episode_steps;
     int32_t auto_reset;
+    int32_t trig_slow;              // v_max beyond the fast sincos range: joint-rate columns take the library path
     uint32_t seed_lo, seed_hi;
     int64_t env_id_base;
     int64_t n_envs;
@@ -105,6 +106,22 @@ __device__ __forceinline__ float2 pnr_ld_stream(const float2* ptr) {
     asm volatile("ld.global.nc.L1::no_allocate.v2.f32 {%0, %1}, [%2];" : "=f"(v.x), "=f"(v.y) : "l"(ptr));
     return v;
 }
+
+// ---------------------------------------------------------------------------------------------
+// TMA bulk store shared -> global (cp.async.bulk, sm_90+/sm_100a): one elected lane hands a whole
+// contiguous observation tile to the copy engine instead of 35 LDS.128 + STG.128 round trips per lane.
+// Protocol: every writer executes fence.proxy.async (generic-proxy smem writes -> async proxy), the warp
+// syncs, one lane issues + commits; before the tile is overwritten that lane waits for the READ of smem.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t pnr_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void pnr_fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void pnr_bulk_store(void* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;"
+                 ::"l"(gdst), "r"(pnr_smem_u32(ssrc)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pnr_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void pnr_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void pnr_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // orderable unsigned encoding of a float (for atomicMax/atomicMin on episode returns)
 __device__ __host__ __forceinline__ uint32_t pnr_float_to_ordered(float f) {

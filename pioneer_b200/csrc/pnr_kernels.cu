@@ -15,22 +15,37 @@ __global__ void __launch_bounds__(PNR_STEP_THREADS)
 pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                 PnrStats* __restrict__ stats, uint32_t tick) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = smem + warp * PNR_TILE_FLOATS;
+    float* row = tile + lane * PNR_OBS_DIM;
     const int64_t N = p.n_envs;
     const int64_t n_tiles = (N + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
+    const int64_t stride = (int64_t)gridDim.x * PNR_STEP_WARPS;
+    int64_t t_idx = (int64_t)blockIdx.x * PNR_STEP_WARPS + warp;
+    if (t_idx >= n_tiles) return;
 
-    for (int64_t t_idx = (int64_t)blockIdx.x * PNR_STEP_WARPS + warp; t_idx < n_tiles;
-         t_idx += (int64_t)gridDim.x * PNR_STEP_WARPS) {
+    pnr_pack_obs_const(p, row);                               // obs[18:54] never change: once per warp
+
+    // software pipeline: the loads of tile i+1 are in flight while tile i is computed
+    PnrRaw raw;
+    {
+        const int64_t e0 = t_idx * PNR_TILE_ENVS + lane;
+        pnr_load_raw(state, actions, N, e0 < N ? e0 : N - 1, raw);
+    }
+    bool tile_busy = false;                                   // a bulk store of this warp's tile is in flight
+    for (; t_idx < n_tiles; t_idx += stride) {
         const int64_t env_raw = t_idx * PNR_TILE_ENVS + lane;
         const bool active = env_raw < N;
         const int64_t env = active ? env_raw : N - 1;       // tail lanes shadow the last env, stores masked
 
         PnrEnv s;
-        pnr_load_env(state, N, env, s);
-        const float2* a2 = reinterpret_cast<const float2*>(actions + env * PNR_DOF);
-        const float2 act01 = pnr_ld_stream(a2), act23 = pnr_ld_stream(a2 + 1), act45 = pnr_ld_stream(a2 + 2);
+        pnr_unpack_raw(raw, s);
+        const float2 act01 = raw.a01, act23 = raw.a23, act45 = raw.a45;
+        if (t_idx + stride < n_tiles) {
+            const int64_t en = (t_idx + stride) * PNR_TILE_ENVS + lane;
+            pnr_load_raw(state, actions, N, en < N ? en : N - 1, raw);
+        }
 
         // --- act(): integrate with the PREVIOUS action (one-step actuation delay), then latch the new one
 #pragma unroll
@@ -41,9 +56,9 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         }
         s.a[0] = act01.x; s.a[1] = act01.y; s.a[2] = act23.x; s.a[3] = act23.y; s.a[4] = act45.x; s.a[5] = act45.y;
 
-        // --- pose, distance, reward, done
+        // --- pose, distance, reward, done (r is inside the joint limits after the integrator: fast sincos)
         PnrPose o;
-        pnr_pose(p, s, o);
+        pnr_pose<true>(p, s, o);
         bool reached = o.dist < p.done_distance;
         if (fabsf(o.dist - p.done_distance) < p.done_band)   // decide in float64 where float32 could flip it
             pnr_fk_tip_f64(p, s.r, s.tgt, o.ptr, o.dist, reached);
@@ -87,11 +102,11 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             }
         }
 
-        // --- observation + auto-reset
-        float* row = tile + lane * PNR_OBS_DIM;
+        // --- observation + auto-reset.  The previous tile's bulk store must have finished reading smem.
+        if (tile_busy) pnr_tile_wait(lane);
         const bool do_reset = is_done && (p.auto_reset != 0);
         if (OBS_MODE == PNR_OBS_TERMINAL) {
-            pnr_pack_obs(p, row, s, o, s.pot);                 // what BulletEnv.step returns
+            pnr_pack_obs_dyn<true>(p, row, s, o, s.pot);       // what BulletEnv.step returns
             if (do_reset) {
                 float q[PNR_DOF], tg[3];
                 pnr_reset_draws(p, p.env_id_base + env, tick, q, tg);
@@ -105,17 +120,19 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             }
             if (__any_sync(PNR_FULL_MASK, do_reset)) {         // warp-uniform; rare
                 PnrPose o2;
-                pnr_pose(p, s, o2);
+                pnr_pose<true>(p, s, o2);                      // fresh joint angles lie inside the limits
                 if (do_reset) o = o2;
             }
-            pnr_pack_obs(p, row, s, o, s.pot);                 // first observation of the next episode
+            pnr_pack_obs_dyn<true>(p, row, s, o, s.pot);       // first observation of the next episode
         }
         if (active) pnr_store_env(state, N, env, s);
 
         const int64_t rows_left = N - t_idx * PNR_TILE_ENVS;
         pnr_emit_tile(tile, obs + t_idx * (int64_t)PNR_TILE_FLOATS,
                       rows_left < PNR_TILE_ENVS ? (int)rows_left : PNR_TILE_ENVS, lane);
+        tile_busy = true;
     }
+    if (lane == 0) pnr_bulk_wait_read();                      // smem must outlive the copy engine's reads
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -126,11 +143,12 @@ __global__ void __launch_bounds__(PNR_STEP_THREADS)
 pnr_reset_observe_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                          const int64_t* __restrict__ idx, int64_t n, const float* __restrict__ q0,
                          const float* __restrict__ target, float* __restrict__ obs_out, uint32_t tick) {
-    extern __shared__ __align__(16) float smem[];
+    extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = smem + warp * PNR_TILE_FLOATS;
     const int64_t N = p.n_envs;
     const int64_t n_tiles = (n + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
+    bool tile_busy = false;
     for (int64_t t_idx = (int64_t)blockIdx.x * PNR_STEP_WARPS + warp; t_idx < n_tiles;
          t_idx += (int64_t)gridDim.x * PNR_STEP_WARPS) {
         const int64_t k_raw = t_idx * PNR_TILE_ENVS + lane;
@@ -152,16 +170,21 @@ pnr_reset_observe_kernel(const __grid_constant__ PnrParams p, float4* __restrict
             pnr_load_env(state, N, env, s);
         }
         if (obs_out) {
+            // injected joint angles may lie anywhere: library sincos for every column here (not the hot path)
             PnrPose o;
-            pnr_pose(p, s, o);
+            pnr_pose<false>(p, s, o);
             bool within;
             if (fabsf(o.dist - p.done_distance) < p.done_band) pnr_fk_tip_f64(p, s.r, s.tgt, o.ptr, o.dist, within);
-            pnr_pack_obs(p, tile + lane * PNR_OBS_DIM, s, o, s.pot);
+            if (tile_busy) pnr_tile_wait(lane);
+            pnr_pack_obs_const(p, tile + lane * PNR_OBS_DIM);
+            pnr_pack_obs_dyn<false>(p, tile + lane * PNR_OBS_DIM, s, o, s.pot);
             const int64_t rows_left = n - t_idx * PNR_TILE_ENVS;
             pnr_emit_tile(tile, obs_out + t_idx * (int64_t)PNR_TILE_FLOATS,
                           rows_left < PNR_TILE_ENVS ? (int)rows_left : PNR_TILE_ENVS, lane);
+            tile_busy = true;
         }
     }
+    if (lane == 0) pnr_bulk_wait_read();
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -1,9 +1,11 @@
 // Device functions of the fused reach-env step: state planes, joint integrator, forward kinematics,
 // reward/done, reset, observation tile.  One thread owns one env; a warp owns a tile of 32 envs whose
 // 32 x 137 observation rows form ONE contiguous 17,536-byte span of the output, staged in shared
-// memory (row stride 137 words is odd => bank-conflict free) and streamed out as coalesced float4.
+// memory (row stride 137 words is odd => bank-conflict free) and handed to the TMA copy engine as one
+// bulk store (cp.async.bulk shared -> global); ragged tail tiles fall back to coalesced float4 stores.
 #pragma once
 #include "pnr_device.cuh"
+#include "pnr_trig.cuh"
 
 #define PNR_TILE_ENVS 32
 #define PNR_TILE_FLOATS (PNR_TILE_ENVS * PNR_OBS_DIM)      // 4384 floats = 17,536 B = 1096 float4
@@ -28,6 +30,28 @@ __device__ __forceinline__ void pnr_load_env(const float4* __restrict__ S, int64
     s.a[0] = p3.x; s.a[1] = p3.y; s.a[2] = p3.z; s.a[3] = p3.w; s.a[4] = p4.x; s.a[5] = p4.y;
     s.pot = p4.z; s.ep_ret = p4.w;
     s.tgt[0] = p5.x; s.tgt[1] = p5.y; s.tgt[2] = p5.z; s.t = __float_as_int(p5.w);
+}
+
+// the 6 state planes + the action of one env exactly as they sit in HBM; loaded one tile ahead of use
+struct PnrRaw {
+    float4 p0, p1, p2, p3, p4, p5;
+    float2 a01, a23, a45;
+};
+
+__device__ __forceinline__ void pnr_load_raw(const float4* __restrict__ S, const float* __restrict__ actions,
+                                             int64_t N, int64_t e, PnrRaw& w) {
+    w.p0 = S[0 * N + e]; w.p1 = S[1 * N + e]; w.p2 = S[2 * N + e];
+    w.p3 = S[3 * N + e]; w.p4 = S[4 * N + e]; w.p5 = S[5 * N + e];
+    const float2* a2 = reinterpret_cast<const float2*>(actions + e * PNR_DOF);
+    w.a01 = pnr_ld_stream(a2); w.a23 = pnr_ld_stream(a2 + 1); w.a45 = pnr_ld_stream(a2 + 2);
+}
+
+__device__ __forceinline__ void pnr_unpack_raw(const PnrRaw& w, PnrEnv& s) {
+    s.r[0] = w.p0.x; s.r[1] = w.p0.y; s.r[2] = w.p0.z; s.r[3] = w.p0.w; s.r[4] = w.p1.x; s.r[5] = w.p1.y;
+    s.v[0] = w.p1.z; s.v[1] = w.p1.w; s.v[2] = w.p2.x; s.v[3] = w.p2.y; s.v[4] = w.p2.z; s.v[5] = w.p2.w;
+    s.a[0] = w.p3.x; s.a[1] = w.p3.y; s.a[2] = w.p3.z; s.a[3] = w.p3.w; s.a[4] = w.p4.x; s.a[5] = w.p4.y;
+    s.pot = w.p4.z; s.ep_ret = w.p4.w;
+    s.tgt[0] = w.p5.x; s.tgt[1] = w.p5.y; s.tgt[2] = w.p5.z; s.t = __float_as_int(w.p5.w);
 }
 
 __device__ __forceinline__ void pnr_store_env(float4* __restrict__ S, int64_t N, int64_t e, const PnrEnv& s) {
@@ -92,7 +116,17 @@ __device__ __forceinline__ void pnr_integrate_joint(const PnrParams& p, int i, f
     v1_out = v1; r1_out = r1;
 }
 
+// library sine/cosine, any argument (reset / observe kernels and the out-of-range fallback of the step kernel)
 __device__ __forceinline__ void pnr_sincos(float x, float& s, float& c) { sincosf(x, &s, &c); }
+
+// FAST: straight-line Cody-Waite + polynomial (pnr_trig.cuh), valid for |x| <= PNR_TRIG_FAST_LIMIT.
+// The step kernel uses it for r, r - r_lo, r_hi - r (clamped to the joint limits by the integrator) and,
+// under a per-env guard, for v and a.
+template <bool FAST>
+__device__ __forceinline__ void pnr_sincos_sel(float x, float& s, float& c) {
+    if (FAST) pnr_sincos_fast(x, s, c);
+    else sincosf(x, &s, &c);
+}
 
 // ---------------------------------------------------------------------------------------------
 // Forward kinematics of the tracked tip ('robot:pointer'), evaluated tip-to-base:
@@ -168,9 +202,10 @@ struct PnrPose {
     float dist;
 };
 
+template <bool FAST>
 __device__ __forceinline__ void pnr_pose(const PnrParams& p, const PnrEnv& s, PnrPose& o) {
 #pragma unroll
-    for (int i = 0; i < PNR_DOF; ++i) pnr_sincos(s.r[i], o.sn[i], o.cs[i]);
+    for (int i = 0; i < PNR_DOF; ++i) pnr_sincos_sel<FAST>(s.r[i], o.sn[i], o.cs[i]);
     pnr_fk_tip(p, o.sn, o.cs, o.ptr);
     const float dx = s.tgt[0] - o.ptr[0], dy = s.tgt[1] - o.ptr[1], dz = s.tgt[2] - o.ptr[2];
     o.dist = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
@@ -183,45 +218,92 @@ __device__ __forceinline__ float pnr_potential(const PnrParams& p, float dist) {
 
 // ---------------------------------------------------------------------------------------------
 // observe() (pioneer_knm_env.py:184-211): the 137-float row of one env, written into the warp's
-// shared-memory tile at row `lane`.
+// shared-memory tile at row `lane`.  The 36 columns that never change (r_lo, r_hi and their cos / sin,
+// obs[18:54]) are written once per warp per kernel; every step rewrites the other 101.
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ void pnr_pack_obs(const PnrParams& p, float* __restrict__ row, const PnrEnv& s,
-                                             const PnrPose& o, float pot) {
+__device__ __forceinline__ void pnr_pack_obs_const(const PnrParams& p, float* __restrict__ row) {
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) {
+        row[18 + i] = p.r_lo[i];   row[24 + i] = p.cos_r_lo[i];  row[30 + i] = p.sin_r_lo[i];
+        row[36 + i] = p.r_hi[i];   row[42 + i] = p.cos_r_hi[i];  row[48 + i] = p.sin_r_hi[i];
+    }
+}
+
+template <bool FAST>
+__device__ __forceinline__ void pnr_pack_obs_dyn(const PnrParams& p, float* __restrict__ row, const PnrEnv& s,
+                                                 const PnrPose& o, float pot) {
+    float sn, cs;
 #pragma unroll
     for (int i = 0; i < PNR_DOF; ++i) {
         const float r = s.r[i];
         row[0 + i] = r;            row[6 + i] = o.cs[i];         row[12 + i] = o.sn[i];
-        row[18 + i] = p.r_lo[i];   row[24 + i] = p.cos_r_lo[i];  row[30 + i] = p.sin_r_lo[i];
-        row[36 + i] = p.r_hi[i];   row[42 + i] = p.cos_r_hi[i];  row[48 + i] = p.sin_r_hi[i];
-        float sn, cs;
         const float dlo = __fsub_rn(r, p.r_lo[i]);
-        pnr_sincos(dlo, sn, cs);
+        pnr_sincos_sel<FAST>(dlo, sn, cs);
         row[54 + i] = dlo;         row[60 + i] = cs;             row[66 + i] = sn;
         const float dhi = __fsub_rn(p.r_hi[i], r);
-        pnr_sincos(dhi, sn, cs);
+        pnr_sincos_sel<FAST>(dhi, sn, cs);
         row[72 + i] = dhi;         row[78 + i] = cs;             row[84 + i] = sn;
-        pnr_sincos(s.v[i], sn, cs);
-        row[90 + i] = s.v[i];      row[96 + i] = cs;             row[102 + i] = sn;
-        pnr_sincos(s.a[i], sn, cs);
-        row[108 + i] = s.a[i];     row[114 + i] = cs;            row[120 + i] = sn;
+        row[90 + i] = s.v[i];
+        row[108 + i] = s.a[i];
     }
     row[126] = o.ptr[0]; row[127] = o.ptr[1]; row[128] = o.ptr[2];
     row[129] = s.tgt[0]; row[130] = s.tgt[1]; row[131] = s.tgt[2];
     row[132] = s.tgt[0] - o.ptr[0]; row[133] = s.tgt[1] - o.ptr[1]; row[134] = s.tgt[2] - o.ptr[2];
     row[135] = o.dist;
     row[136] = pot;
+    // cos / sin of the joint rates and of the stored (unclipped) action: straight-line code unless this env
+    // holds an argument outside the fast range, which a policy bounded by the action space never produces
+    bool fast = FAST && !p.trig_slow;
+    if (FAST) {
+        float m = 0.f;
+#pragma unroll
+        for (int i = 0; i < PNR_DOF; ++i) m = fmaxf(m, fabsf(s.a[i]));
+        fast = fast && (m <= PNR_TRIG_FAST_LIMIT);       // fmaxf drops NaN: a NaN action yields NaN on both paths
+    }
+    if (fast) {
+#pragma unroll
+        for (int i = 0; i < PNR_DOF; ++i) {
+            pnr_sincos_fast(s.v[i], sn, cs);
+            row[96 + i] = cs;      row[102 + i] = sn;
+            pnr_sincos_fast(s.a[i], sn, cs);
+            row[114 + i] = cs;     row[120 + i] = sn;
+        }
+    } else {
+#pragma unroll 1
+        for (int i = 0; i < PNR_DOF; ++i) {
+            pnr_sincos(s.v[i], sn, cs);
+            row[96 + i] = cs;      row[102 + i] = sn;
+            pnr_sincos(s.a[i], sn, cs);
+            row[114 + i] = cs;     row[120 + i] = sn;
+        }
+    }
 }
 
-// stream the warp's tile (rows_valid x 137 floats, contiguous in `out`) with coalesced 16-byte stores
+// hand the warp's tile (rows_valid x 137 floats, contiguous in `out`) to global memory.  Full tiles (and any
+// tile whose byte count is a multiple of 16) go out as ONE TMA bulk store issued by lane 0; other ragged tails
+// use coalesced 16-byte stores.  Call pnr_tile_wait() before writing the tile again.
 __device__ __forceinline__ void pnr_emit_tile(const float* __restrict__ tile, float* __restrict__ out,
                                               int rows_valid, int lane) {
+    pnr_fence_async_smem();
     __syncwarp();
-    const int total = rows_valid * PNR_OBS_DIM;
-    const int n4 = total >> 2;
-    const float4* t4 = reinterpret_cast<const float4*>(tile);
-    float4* o4 = reinterpret_cast<float4*>(out);
+    if ((rows_valid & 3) == 0) {
+        if (lane == 0) {
+            pnr_bulk_store(out, tile, (uint32_t)(rows_valid * PNR_OBS_DIM * sizeof(float)));
+            pnr_bulk_commit();
+        }
+    } else {
+        const int total = rows_valid * PNR_OBS_DIM;
+        const int n4 = total >> 2;
+        const float4* t4 = reinterpret_cast<const float4*>(tile);
+        float4* o4 = reinterpret_cast<float4*>(out);
 #pragma unroll 4
-    for (int i = lane; i < n4; i += 32) pnr_st_stream(o4 + i, t4[i]);
-    for (int i = (n4 << 2) + lane; i < total; i += 32) pnr_st_stream(out + i, tile[i]);
+        for (int i = lane; i < n4; i += 32) pnr_st_stream(o4 + i, t4[i]);
+        for (int i = (n4 << 2) + lane; i < total; i += 32) pnr_st_stream(out + i, tile[i]);
+    }
+}
+
+// the tile may be overwritten once the copy engine has finished READING it
+__device__ __forceinline__ void pnr_tile_wait(int lane) {
+    if (lane == 0) pnr_bulk_wait_read();
     __syncwarp();
 }
