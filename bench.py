@@ -53,6 +53,9 @@ def parse_args():
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-sweep", action="store_true", help="skip the env-count sweep (N=1 only)")
+    ap.add_argument("--flush", default="write", choices=["write", "write+read"],
+                    help="L2 flush between timed steps: 512 MiB memset, optionally followed by a 512 MiB read sweep "
+                         "(leaves the L2 full of CLEAN lines instead of dirty ones)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps-per-proc", type=int, default=0,
                     help="reference arm: env-steps per process per bench step (0 = sized for ~20 s in total)")
@@ -226,14 +229,14 @@ def time_device_steps(torch, env, actions, obs_ring, reward, flags, steps, warmu
     n_act, n_obs = actions.shape[0], obs_ring.shape[0]
     for k in range(warmup):
         if flush is not None:
-            flush.zero_()
+            flush()
         env.step_tensor(actions[k % n_act], out=(obs_ring[k % n_obs], reward, flags))
     starts = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     stops = [torch.cuda.Event(enable_timing=True) for _ in range(steps)]
     torch.cuda.synchronize()
     for k in range(steps):
         if flush is not None:
-            flush.zero_()
+            flush()
         starts[k].record()
         env.step_tensor(actions[k % n_act], out=(obs_ring[k % n_obs], reward, flags))
         stops[k].record()
@@ -291,7 +294,16 @@ def ours_arm(args):
     env = BatchedPioneerEnv(n, device=device, seed=0, env_id_base=rank * n,
                             batch_config=BatchConfig(max_episode_steps=500, auto_reset=True, obs_mode="terminal"))
     actions, obs_ring, reward, flags = make_buffers(torch, env, n, device, seed=rank)
-    flush = torch.empty(L2_FLUSH_BYTES, dtype=torch.uint8, device=device)
+    flush_buf = torch.empty(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
+    if args.flush == "write":
+        def flush():
+            flush_buf.zero_()
+    else:
+        flush_src = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
+
+        def flush():
+            flush_buf.zero_()
+            flush_src.sum()
 
     def barrier():
         if world > 1:
@@ -360,7 +372,8 @@ def ours_arm(args):
                                "TimeLimit 500, in-kernel auto-reset, uniform random actions in [-a_max, a_max]",
                    "envs_per_gpu": n, "total_envs": total_envs, "mode": "kinematic (the reference env)",
                    "arith": "f32", "obs": "float32[N,137] terminal observations, 8-slot rollout ring",
-                   "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB memset, untimed); each step "
+                   "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB memset"
+                         + (" then a 512 MiB read sweep" if args.flush != "write" else "") + ", untimed); each step "
                          "timed by its own CUDA-event pair on the launching stream",
                    "parallelism": f"env-sharded x{world}, no data-path collective; one stats all-reduce per iteration"},
         "substeps_per_sec": value * FRAME_SKIP,

@@ -31,19 +31,29 @@ def _stale() -> bool:
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
-    if not force and not _stale():
+TRACE_LIB_PATH = os.path.join(LIB_DIR, "libpioneer_b200_trace.so")
+
+
+def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
+    """trace=True: developer build with per-CTA phase timestamps (-DPNR_TRACE) next to the product library;
+    select it with PIONEER_B200_LIB=<path>."""
+    out = TRACE_LIB_PATH if trace else LIB_PATH
+    if not trace and not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + _sources() + ["-o", LIB_PATH]
+    extra = os.environ.get("PNR_EXTRA_NVCC_FLAGS", "").split()     # developer experiments (e.g. -DPNR_STEP_MIN_CTAS=6)
+    if extra:
+        out = os.environ.get("PNR_LIB_OUT", out)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-DPNR_TRACE"] if trace else []) + (["-Xptxas", "-v"] if verbose else []) \
+        + _sources() + ["-o", out]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
     if verbose:
         print(proc.stdout + proc.stderr)
-    return LIB_PATH
+    return out
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv, trace="--trace" in sys.argv))

@@ -120,7 +120,10 @@ __device__ __forceinline__ void pnr_bulk_store(void* gdst, const void* ssrc, uin
                  ::"l"(gdst), "r"(pnr_smem_u32(ssrc)), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void pnr_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void pnr_bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+template <int PENDING>
+__device__ __forceinline__ void pnr_bulk_wait_read() {      // returns once at most PENDING groups still read smem
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
+}
 __device__ __forceinline__ void pnr_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // orderable unsigned encoding of a float (for atomicMax/atomicMin on episode returns)

@@ -4,135 +4,247 @@
 #include "pnr_launch.h"
 
 // ---------------------------------------------------------------------------------------------
-// K1: the fused env step.  Per env: load 6 state planes + the action, integrate the 6 joints
-// (act(), pioneer_knm_env.py:111-146), forward kinematics, reward / done / TimeLimit
-// (:151-165, gym TimeLimit), episode statistics, in-kernel auto-reset (reset_world, :76-105),
-// observation (observe(), :184-211) staged per warp in shared memory and streamed out.
-// Grid-stride over warp tiles; grid = resident CTAs of the whole GPU (multiple of the SM count).
+// K1: the fused env step.  One CTA of 4 warps owns a tile of 32 envs (lane = env); the work of ONE env is
+// split across the 4 warps so that its dependent instruction chain is ~4x shorter and 4x more warps are
+// resident per byte of shared memory than with one thread per env:
+//   warps 0..2 ("joint warps") : joints 2k, 2k+1 -- act() integrator (pioneer_knm_env.py:111-146), their
+//                                21 + 21 observation columns incl. 10 (sin, cos) pairs, state planes RV_k, A_k
+//   warp 3     ("task warp")   : forward kinematics of the pointer from the joint warps' sin/cos (read back
+//                                from the tile), reward / done / TimeLimit (:151-165), episode statistics,
+//                                auto-reset (reset_world, :76-105), observation tail, planes X0, X1,
+//                                reward / done outputs, and the TMA bulk store of the finished tile
+// Three CTA barriers per tile: B0 tile free (previous bulk store has read it), B1 joint angles and their
+// sin/cos are in the tile, B2 tile complete.  Each warp prefetches its own planes of the CTA's next tile.
+// Grid = min(tiles, resident CTAs of the whole GPU); grid-stride over tiles.
 // ---------------------------------------------------------------------------------------------
+// In-kernel auto-reset of ONE env by the task warp after the tile is complete: new joint angles and target from
+// the Philox stream, a = v = 0, potential = 0, elapsed = 0 written over all eight planes of the env; in
+// PNR_OBS_AUTORESET mode the env's observation row is replaced by the first observation of the new episode.
+// Rare (once per episode), so deliberately not inlined: keeps registers and code out of the hot loop.
+template <int OBS_MODE>
+__device__ __noinline__ void pnr_auto_reset(const PnrParams& p, float4* __restrict__ state, int64_t env, uint32_t tick,
+                                            float* __restrict__ row) {
+    const int64_t N = p.n_envs;
+    PnrEnv s;
+    float q[PNR_DOF], tg[3];
+    pnr_reset_draws(p, p.env_id_base + env, tick, q, tg);
+    pnr_reset_env(s, q, tg);
+    pnr_store_env(state, N, env, s);
+    if (OBS_MODE == PNR_OBS_AUTORESET) {
+        PnrPose o;
+        pnr_pose<true>(p, s, o);                              // fresh joint angles lie inside the limits
+        pnr_pack_obs_dyn<true>(p, row, s, o, s.pot);
+    }
+}
+
+#ifdef PNR_TRACE
+// developer instrumentation (python -m pioneer_b200.build --trace): per-CTA phase timestamps of the first tile
+#define PNR_TRACE_SLOTS 12
+#define PNR_TRACE_CTAS 2048
+#define PNR_TRACE_ITERS 4
+__device__ unsigned long long pnr_trace_buf[PNR_TRACE_CTAS][2][PNR_TRACE_ITERS][PNR_TRACE_SLOTS];
+__device__ __forceinline__ void pnr_trace_mark(int part, int lane, int slot, int iter) {
+    if (lane == 0 && (part == 0 || part == 3) && blockIdx.x < PNR_TRACE_CTAS && iter < PNR_TRACE_ITERS) {
+        unsigned long long t;
+        if (slot == 0) asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); else t = clock64();
+        pnr_trace_buf[blockIdx.x][part == 3][iter][slot] = t;
+    }
+}
+extern "C" int pnr_debug_trace(unsigned long long* out_host) {
+    return (int)cudaMemcpyFromSymbol(out_host, pnr_trace_buf, sizeof(pnr_trace_buf));
+}
+#define PNR_MARK(slot) pnr_trace_mark(part, lane, slot, trace_iter)
+#define PNR_TRACE_NEXT() (++trace_iter)
+#else
+#define PNR_MARK(slot)
+#define PNR_TRACE_NEXT()
+#endif
+
 template <int ARITH, int OBS_MODE>
-__global__ void __launch_bounds__(PNR_STEP_THREADS)
+__global__ void __launch_bounds__(PNR_STEP_THREADS, PNR_STEP_MIN_CTAS)
 pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                 PnrStats* __restrict__ stats, uint32_t tick) {
-    extern __shared__ __align__(128) float smem[];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    float* tile = smem + warp * PNR_TILE_FLOATS;
+    extern __shared__ __align__(128) float tiles[];           // PNR_STEP_BUFS tiles: the bulk store of one drains
+    const int lane = threadIdx.x & 31;                        // while the next is being filled
+    const int part = threadIdx.x >> 5;                        // warp-uniform role
+    float* tile = tiles;
     float* row = tile + lane * PNR_OBS_DIM;
     const int64_t N = p.n_envs;
     const int64_t n_tiles = (N + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
-    const int64_t stride = (int64_t)gridDim.x * PNR_STEP_WARPS;
-    int64_t t_idx = (int64_t)blockIdx.x * PNR_STEP_WARPS + warp;
-    if (t_idx >= n_tiles) return;
+    const int64_t stride = gridDim.x;
+    int64_t t_idx = blockIdx.x;
+    if (t_idx >= n_tiles) return;                             // CTA-uniform
 
-    pnr_pack_obs_const(p, row);                               // obs[18:54] never change: once per warp
+#ifdef PNR_TRACE
+    int trace_iter = 0;
+#endif
+    PNR_MARK(0); PNR_MARK(1);
+    const int j0 = part < 3 ? 2 * part : 0;                   // first joint of a joint warp
+    float* rowj = row + j0;
+    // loop-invariant limits of this warp's two joints, read once from the constant bank
+    const float vmax0 = p.v_max[j0], vmax1 = p.v_max[j0 + 1];
+    const float rlo0 = p.r_lo[j0], rlo1 = p.r_lo[j0 + 1], rhi0 = p.r_hi[j0], rhi1 = p.r_hi[j0 + 1];
+    float4* const rv_plane = pnr_plane_rv(state, N, part < 3 ? part : 0);
+    float2* const a_plane = pnr_plane_a(state, N, part < 3 ? part : 0);
+    float4* const x0_plane = pnr_plane_x0(state, N);
+    float2* const x1_plane = pnr_plane_x1(state, N);
 
-    // software pipeline: the loads of tile i+1 are in flight while tile i is computed
-    PnrRaw raw;
-    {
-        const int64_t e0 = t_idx * PNR_TILE_ENVS + lane;
-        pnr_load_raw(state, actions, N, e0 < N ? e0 : N - 1, raw);
+    // obs[18:54] never change: written once per CTA (into every tile buffer)
+    if (part < 3) {
+#pragma unroll
+        for (int b = 0; b < PNR_STEP_BUFS; ++b) {
+            pnr_pack_joint_const(p, row + b * PNR_TILE_FLOATS, j0);
+            pnr_pack_joint_const(p, row + b * PNR_TILE_FLOATS, j0 + 1);
+        }
     }
-    bool tile_busy = false;                                   // a bulk store of this warp's tile is in flight
+
+    // software pipeline: every warp loads its own planes of the NEXT tile while it works on the current one
+    float4 ld4; float2 ld2, ld_act = make_float2(0.f, 0.f);
+    auto issue_loads = [&](int64_t tile_idx) {
+        const int64_t e_raw = tile_idx * PNR_TILE_ENVS + lane;
+        const int64_t e = e_raw < N ? e_raw : N - 1;
+        if (part < 3) {
+            ld4 = rv_plane[e];
+            ld2 = a_plane[e];
+            ld_act = pnr_ld_stream(reinterpret_cast<const float2*>(actions + e * PNR_DOF) + part);
+        } else {
+            ld4 = x0_plane[e];
+            ld2 = x1_plane[e];
+        }
+    };
+    issue_loads(t_idx);
+    PNR_MARK(2);
+    int stores_in_flight = 0;                                 // bulk stores committed by the task warp's lane 0
+    int buf = 0;
+
     for (; t_idx < n_tiles; t_idx += stride) {
         const int64_t env_raw = t_idx * PNR_TILE_ENVS + lane;
         const bool active = env_raw < N;
         const int64_t env = active ? env_raw : N - 1;       // tail lanes shadow the last env, stores masked
+        const int64_t rows_left = N - t_idx * PNR_TILE_ENVS;
+        const int rows_valid = rows_left < PNR_TILE_ENVS ? (int)rows_left : PNR_TILE_ENVS;
+        const float4 c4 = ld4;
+        const float2 c2 = ld2, c_act = ld_act;
+        if (t_idx + stride < n_tiles) issue_loads(t_idx + stride);
 
-        PnrEnv s;
-        pnr_unpack_raw(raw, s);
-        const float2 act01 = raw.a01, act23 = raw.a23, act45 = raw.a45;
-        if (t_idx + stride < n_tiles) {
-            const int64_t en = (t_idx + stride) * PNR_TILE_ENVS + lane;
-            pnr_load_raw(state, actions, N, en < N ? en : N - 1, raw);
+        float r1[2], v1[2], sn[2], cs[2];
+        if (part < 3) {
+            // --- act(): integrate with the PREVIOUS action (one-step actuation delay); registers only
+            pnr_integrate_joint<ARITH>(p, vmax0, rlo0, rhi0, c2.x, c4.z, c4.x, v1[0], r1[0]);
+            pnr_integrate_joint<ARITH>(p, vmax1, rlo1, rhi1, c2.y, c4.w, c4.y, v1[1], r1[1]);
+            pnr_sincos_fast(r1[0], sn[0], cs[0]);             // r is inside the joint limits: fast path
+            pnr_sincos_fast(r1[1], sn[1], cs[1]);
+        } else if (lane == 0 && stores_in_flight >= PNR_STEP_BUFS) {
+            // the copy engine must have finished READING this buffer (the store issued PNR_STEP_BUFS tiles ago)
+            if (PNR_STEP_BUFS == 1) pnr_bulk_wait_read<0>(); else pnr_bulk_wait_read<PNR_STEP_BUFS - 1>();
         }
+        PNR_MARK(3);
+        __syncthreads();                                      // B0: the tile may be written
+        PNR_MARK(4);
 
-        // --- act(): integrate with the PREVIOUS action (one-step actuation delay), then latch the new one
-#pragma unroll
-        for (int i = 0; i < PNR_DOF; ++i) {
-            float v1, r1;
-            pnr_integrate_joint<ARITH>(p, i, s.a[i], s.v[i], s.r[i], v1, r1);
-            s.v[i] = v1; s.r[i] = r1;
+        if (part < 3) {
+            pnr_pack_joint_head(rowj, r1[0], sn[0], cs[0]);
+            pnr_pack_joint_head(rowj + 1, r1[1], sn[1], cs[1]);
         }
-        s.a[0] = act01.x; s.a[1] = act01.y; s.a[2] = act23.x; s.a[3] = act23.y; s.a[4] = act45.x; s.a[5] = act45.y;
+        __syncthreads();                                      // B1: r, cos r, sin r of all six joints are in the tile
+        PNR_MARK(5);
 
-        // --- pose, distance, reward, done (r is inside the joint limits after the integrator: fast sincos)
-        PnrPose o;
-        pnr_pose<true>(p, s, o);
-        bool reached = o.dist < p.done_distance;
-        if (fabsf(o.dist - p.done_distance) < p.done_band)   // decide in float64 where float32 could flip it
-            pnr_fk_tip_f64(p, s.r, s.tgt, o.ptr, o.dist, reached);
-        const float pot_new = pnr_potential(p, o.dist);
-        // (potential - old_potential) + (-penalty_step) + (award_done | 0), pioneer_knm_env.py:162-165
-        const float rew = __fadd_rn(__fadd_rn(__fsub_rn(pot_new, s.pot), -p.penalty_step), reached ? p.award_done : 0.f);
-        s.pot = pot_new;
-        s.t += 1;
-        s.ep_ret = __fadd_rn(s.ep_ret, rew);
-        const bool timeout = p.max_episode_steps > 0 && s.t >= p.max_episode_steps;
-        const bool is_done = reached || timeout;
-        const uint8_t flags = (is_done ? PNR_DONE : 0) | ((timeout && !reached) ? PNR_TRUNCATED : 0);
-        if (active) {
-            reward[env] = rew;
-            done[env] = flags;
-        }
-
-        // --- episode statistics: one set of atomics per warp that saw an episode end
-        const unsigned done_mask = __ballot_sync(PNR_FULL_MASK, is_done && active);
-        if (done_mask) {
-            const bool mine = (done_mask >> lane) & 1u;
-            float ret = mine ? s.ep_ret : 0.f, ret2 = ret * ret, len = mine ? (float)s.t : 0.f;
-            float mx = mine ? s.ep_ret : -INFINITY, mn = mine ? s.ep_ret : INFINITY;
-#pragma unroll
-            for (int ofs = 16; ofs > 0; ofs >>= 1) {
-                ret += __shfl_xor_sync(PNR_FULL_MASK, ret, ofs);
-                ret2 += __shfl_xor_sync(PNR_FULL_MASK, ret2, ofs);
-                len += __shfl_xor_sync(PNR_FULL_MASK, len, ofs);
-                mx = fmaxf(mx, __shfl_xor_sync(PNR_FULL_MASK, mx, ofs));
-                mn = fminf(mn, __shfl_xor_sync(PNR_FULL_MASK, mn, ofs));
-            }
-            const unsigned reach_mask = __ballot_sync(PNR_FULL_MASK, reached && active);
-            if (lane == 0) {
-                atomicAdd(&stats->episodes, (double)__popc(done_mask));
-                atomicAdd(&stats->sum_return, (double)ret);
-                atomicAdd(&stats->sum_length, (double)len);
-                atomicAdd(&stats->sum_return_sq, (double)ret2);
-                atomicAdd(&stats->reached, (double)__popc(reach_mask));
-                atomicMax(&stats->max_return_ord, pnr_float_to_ordered(mx));
-                atomicMin(&stats->min_return_ord, pnr_float_to_ordered(mn));
-            }
-        }
-
-        // --- observation + auto-reset.  The previous tile's bulk store must have finished reading smem.
-        if (tile_busy) pnr_tile_wait(lane);
-        const bool do_reset = is_done && (p.auto_reset != 0);
-        if (OBS_MODE == PNR_OBS_TERMINAL) {
-            pnr_pack_obs_dyn<true>(p, row, s, o, s.pot);       // what BulletEnv.step returns
-            if (do_reset) {
-                float q[PNR_DOF], tg[3];
-                pnr_reset_draws(p, p.env_id_base + env, tick, q, tg);
-                pnr_reset_env(s, q, tg);
+        bool do_reset = false;
+        if (part < 3) {
+            // --- the other 15 dynamic columns of each joint; latch the new action (stored unclipped, :144)
+            const bool fast = !p.trig_slow && fmaxf(fabsf(c_act.x), fabsf(c_act.y)) <= PNR_TRIG_FAST_LIMIT;
+            pnr_pack_joint_rest(rowj, rlo0, rhi0, r1[0], v1[0], c_act.x, fast);
+            pnr_pack_joint_rest(rowj + 1, rlo1, rhi1, r1[1], v1[1], c_act.y, fast);
+            if (active) {
+                rv_plane[env] = make_float4(r1[0], r1[1], v1[0], v1[1]);
+                a_plane[env] = c_act;
             }
         } else {
-            if (do_reset) {
-                float q[PNR_DOF], tg[3];
-                pnr_reset_draws(p, p.env_id_base + env, tick, q, tg);
-                pnr_reset_env(s, q, tg);
+            // --- pose from the joint warps' sin/cos, distance, reward, done
+            PnrPose o;
+#pragma unroll
+            for (int i = 0; i < PNR_DOF; ++i) { o.cs[i] = row[6 + i]; o.sn[i] = row[12 + i]; }
+            float tgt[3] = {c4.x, c4.y, c4.z};
+            int32_t t = __float_as_int(c4.w);
+            const float pot_old = c2.x;
+            float ep_ret = c2.y;
+            pnr_fk_tip(p, o.sn, o.cs, o.ptr);
+            const float dx = tgt[0] - o.ptr[0], dy = tgt[1] - o.ptr[1], dz = tgt[2] - o.ptr[2];
+            o.dist = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
+            bool reached = o.dist < p.done_distance;
+            if (fabsf(o.dist - p.done_distance) < p.done_band) {   // decide in float64 where float32 could flip it
+                float rr[PNR_DOF];
+#pragma unroll
+                for (int i = 0; i < PNR_DOF; ++i) rr[i] = row[i];
+                pnr_fk_tip_f64(p, rr, tgt, o.ptr, o.dist, reached);
             }
-            if (__any_sync(PNR_FULL_MASK, do_reset)) {         // warp-uniform; rare
-                PnrPose o2;
-                pnr_pose<true>(p, s, o2);                      // fresh joint angles lie inside the limits
-                if (do_reset) o = o2;
+            const float pot_new = pnr_potential(p, o.dist);
+            // (potential - old_potential) + (-penalty_step) + (award_done | 0), pioneer_knm_env.py:162-165
+            const float rew = __fadd_rn(__fadd_rn(__fsub_rn(pot_new, pot_old), -p.penalty_step),
+                                        reached ? p.award_done : 0.f);
+            t += 1;
+            ep_ret = __fadd_rn(ep_ret, rew);
+            const bool timeout = p.max_episode_steps > 0 && t >= p.max_episode_steps;
+            const bool is_done = reached || timeout;
+            const uint8_t flags = (is_done ? PNR_DONE : 0) | ((timeout && !reached) ? PNR_TRUNCATED : 0);
+            if (active) {
+                reward[env] = rew;
+                done[env] = flags;
             }
-            pnr_pack_obs_dyn<true>(p, row, s, o, s.pot);       // first observation of the next episode
-        }
-        if (active) pnr_store_env(state, N, env, s);
+            pnr_episode_stats(stats, is_done && active, reached && active, ep_ret, t, lane);
 
-        const int64_t rows_left = N - t_idx * PNR_TILE_ENVS;
-        pnr_emit_tile(tile, obs + t_idx * (int64_t)PNR_TILE_FLOATS,
-                      rows_left < PNR_TILE_ENVS ? (int)rows_left : PNR_TILE_ENVS, lane);
-        tile_busy = true;
+            // observation tail: pointer, target, difference, distance, potential (terminal values)
+            row[126] = o.ptr[0]; row[127] = o.ptr[1]; row[128] = o.ptr[2];
+            row[129] = tgt[0]; row[130] = tgt[1]; row[131] = tgt[2];
+            row[132] = tgt[0] - o.ptr[0]; row[133] = tgt[1] - o.ptr[1]; row[134] = tgt[2] - o.ptr[2];
+            row[135] = o.dist;
+            row[136] = pot_new;
+
+            if (active) {
+                x0_plane[env] = make_float4(tgt[0], tgt[1], tgt[2], __int_as_float(t));
+                x1_plane[env] = make_float2(pot_new, ep_ret);
+            }
+            do_reset = is_done && active && (p.auto_reset != 0);   // handled after B2 (rare)
+        }
+        PNR_MARK(6);
+        pnr_fence_async_smem();                               // generic-proxy tile writes -> async proxy
+        __syncthreads();                                      // B2: tile complete, joint planes stored
+        PNR_MARK(7);
+
+        const bool bulk = pnr_tile_is_bulk(rows_valid);       // CTA-uniform
+        if (part == 3) {
+            if (__any_sync(PNR_FULL_MASK, do_reset)) {         // rare: auto-reset (reset_world, :76-105)
+                if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, tick, row);
+                pnr_fence_async_smem();
+                __syncwarp();
+            }
+            if (bulk && lane == 0) {
+                pnr_bulk_store(obs + t_idx * (int64_t)PNR_TILE_FLOATS, tile,
+                               (uint32_t)(rows_valid * PNR_OBS_DIM * sizeof(float)));
+                pnr_bulk_commit();
+            }
+        }
+        PNR_MARK(8);
+        PNR_TRACE_NEXT();
+        if (bulk) {
+            ++stores_in_flight;
+        } else {                                              // ragged last tile: all 128 threads stream it out
+            __syncthreads();
+            pnr_emit_tile_manual(tile, obs + t_idx * (int64_t)PNR_TILE_FLOATS, rows_valid, threadIdx.x, PNR_STEP_THREADS);
+        }
+        if (PNR_STEP_BUFS > 1) {                              // next tile goes into the other buffer
+            buf = (buf + 1) % PNR_STEP_BUFS;
+            tile = tiles + buf * PNR_TILE_FLOATS;
+            row = tile + lane * PNR_OBS_DIM;
+            rowj = row + j0;
+        }
     }
-    if (lane == 0) pnr_bulk_wait_read();                      // smem must outlive the copy engine's reads
+    if (part == 3 && lane == 0 && stores_in_flight) pnr_bulk_wait_read<0>();   // smem must outlive the copy engine's reads
+#ifdef PNR_TRACE
+    trace_iter = 0;
+#endif
+    PNR_MARK(9);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -184,7 +296,7 @@ pnr_reset_observe_kernel(const __grid_constant__ PnrParams p, float4* __restrict
             tile_busy = true;
         }
     }
-    if (lane == 0) pnr_bulk_wait_read();
+    if (lane == 0) pnr_bulk_wait_read<0>();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -240,15 +352,16 @@ static int pnr_resident_grid(const void* fn, size_t smem) {
 }
 
 template <typename K>
-static cudaError_t pnr_prepare(K kernel, int* grid_out) {
-    cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PNR_STEP_SMEM);
+static cudaError_t pnr_prepare(K kernel, size_t smem, int* grid_out) {
+    cudaError_t e = cudaFuncSetAttribute((const void*)kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
-    *grid_out = pnr_resident_grid((const void*)kernel, PNR_STEP_SMEM);
+    *grid_out = pnr_resident_grid((const void*)kernel, smem);
     return cudaSuccess;
 }
 
-static int64_t pnr_grid_for(int64_t n_units, int resident) {
-    const int64_t blocks = (n_units + PNR_TILE_ENVS * PNR_STEP_WARPS - 1) / (PNR_TILE_ENVS * PNR_STEP_WARPS);
+// grid = min(CTAs needed, CTAs resident on the whole GPU): a multiple of the SM count once the batch is large
+static int64_t pnr_grid_for(int64_t n_envs, int envs_per_cta, int resident) {
+    const int64_t blocks = (n_envs + envs_per_cta - 1) / envs_per_cta;
     return blocks < resident ? (blocks > 0 ? blocks : 1) : resident;
 }
 
@@ -262,10 +375,10 @@ cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_m
     Kern k = kernels[arith][obs_mode];
     int& resident = grids[device % PNR_MAX_DEVICES][arith][obs_mode];
     if (resident == 0) {
-        cudaError_t e = pnr_prepare(k, &resident);
+        cudaError_t e = pnr_prepare(k, PNR_STEP_SMEM, &resident);
         if (e != cudaSuccess) return e;
     }
-    const int64_t grid = pnr_grid_for(p.n_envs, resident);
+    const int64_t grid = pnr_grid_for(p.n_envs, PNR_TILE_ENVS, resident);
     k<<<(unsigned)grid, PNR_STEP_THREADS, PNR_STEP_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick);
     return cudaGetLastError();
 }
@@ -278,12 +391,12 @@ cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, f
     static int grids[PNR_MAX_DEVICES][2] = {};
     int& resident = grids[device % PNR_MAX_DEVICES][mode];
     if (resident == 0) {
-        cudaError_t e = pnr_prepare(kernels[mode], &resident);
+        cudaError_t e = pnr_prepare(kernels[mode], PNR_RO_SMEM, &resident);
         if (e != cudaSuccess) return e;
     }
     if (n <= 0) return cudaSuccess;
-    const int64_t grid = pnr_grid_for(n, resident);
-    kernels[mode]<<<(unsigned)grid, PNR_STEP_THREADS, PNR_STEP_SMEM, stream>>>(p, state, idx, n, q0, target, obs_out, tick);
+    const int64_t grid = pnr_grid_for(n, PNR_TILE_ENVS * PNR_STEP_WARPS, resident);
+    kernels[mode]<<<(unsigned)grid, PNR_STEP_THREADS, PNR_RO_SMEM, stream>>>(p, state, idx, n, q0, target, obs_out, tick);
     return cudaGetLastError();
 }
 

@@ -1,8 +1,8 @@
 // Device functions of the fused reach-env step: state planes, joint integrator, forward kinematics,
-// reward/done, reset, observation tile.  One thread owns one env; a warp owns a tile of 32 envs whose
-// 32 x 137 observation rows form ONE contiguous 17,536-byte span of the output, staged in shared
-// memory (row stride 137 words is odd => bank-conflict free) and handed to the TMA copy engine as one
-// bulk store (cp.async.bulk shared -> global); ragged tail tiles fall back to coalesced float4 stores.
+// reward/done, reset, observation tile.  A tile is 32 envs whose 32 x 137 observation rows form ONE
+// contiguous 17,536-byte span of the output, staged in shared memory (row stride 137 words is odd =>
+// bank-conflict free) and handed to the TMA copy engine as one bulk store (cp.async.bulk shared -> global);
+// ragged tail tiles fall back to coalesced float4 stores.
 #pragma once
 #include "pnr_device.cuh"
 #include "pnr_trig.cuh"
@@ -11,10 +11,12 @@
 #define PNR_TILE_FLOATS (PNR_TILE_ENVS * PNR_OBS_DIM)      // 4384 floats = 17,536 B = 1096 float4
 #define PNR_FULL_MASK 0xffffffffu
 
-// per-env state in registers.  HBM layout: 6 planes of float4[N] (plane-major), so every load/store of
-// a warp is one fully coalesced 512-byte transaction:
-//   plane0 = r0 r1 r2 r3 | plane1 = r4 r5 v0 v1 | plane2 = v2 v3 v4 v5
-//   plane3 = a0 a1 a2 a3 | plane4 = a4 a5 potential episode_return | plane5 = target xyz, t (int bits)
+// per-env state.  HBM layout (96 B / env, plane-major so every warp access is one coalesced span), cut along
+// the work split of the step kernel: warp k of a CTA owns joints 2k and 2k+1, the fourth warp owns the task.
+//   RV_k  float4[N], k = 0..2 : r[2k] r[2k+1] v[2k] v[2k+1]          at S + k N
+//   X0    float4[N]           : target x y z, t (int bits)            at S + 3 N
+//   A_k   float2[N], k = 0..2 : a[2k] a[2k+1] (last action applied)   at (float2*)(S + 4 N) + k N
+//   X1    float2[N]           : potential, episode return             at (float2*)(S + 4 N) + 3 N
 struct PnrEnv {
     float r[PNR_DOF], v[PNR_DOF], a[PNR_DOF];
     float pot, ep_ret;
@@ -22,45 +24,35 @@ struct PnrEnv {
     int32_t t;
 };
 
-__device__ __forceinline__ void pnr_load_env(const float4* __restrict__ S, int64_t N, int64_t e, PnrEnv& s) {
-    const float4 p0 = S[0 * N + e], p1 = S[1 * N + e], p2 = S[2 * N + e];
-    const float4 p3 = S[3 * N + e], p4 = S[4 * N + e], p5 = S[5 * N + e];
-    s.r[0] = p0.x; s.r[1] = p0.y; s.r[2] = p0.z; s.r[3] = p0.w; s.r[4] = p1.x; s.r[5] = p1.y;
-    s.v[0] = p1.z; s.v[1] = p1.w; s.v[2] = p2.x; s.v[3] = p2.y; s.v[4] = p2.z; s.v[5] = p2.w;
-    s.a[0] = p3.x; s.a[1] = p3.y; s.a[2] = p3.z; s.a[3] = p3.w; s.a[4] = p4.x; s.a[5] = p4.y;
-    s.pot = p4.z; s.ep_ret = p4.w;
-    s.tgt[0] = p5.x; s.tgt[1] = p5.y; s.tgt[2] = p5.z; s.t = __float_as_int(p5.w);
+__device__ __forceinline__ float4* pnr_plane_rv(float4* S, int64_t N, int k) { return S + (int64_t)k * N; }
+__device__ __forceinline__ float4* pnr_plane_x0(float4* S, int64_t N) { return S + 3 * N; }
+__device__ __forceinline__ float2* pnr_plane_a(float4* S, int64_t N, int k) {
+    return reinterpret_cast<float2*>(S + 4 * N) + (int64_t)k * N;
 }
+__device__ __forceinline__ float2* pnr_plane_x1(float4* S, int64_t N) { return reinterpret_cast<float2*>(S + 4 * N) + 3 * N; }
 
-// the 6 state planes + the action of one env exactly as they sit in HBM; loaded one tile ahead of use
-struct PnrRaw {
-    float4 p0, p1, p2, p3, p4, p5;
-    float2 a01, a23, a45;
-};
-
-__device__ __forceinline__ void pnr_load_raw(const float4* __restrict__ S, const float* __restrict__ actions,
-                                             int64_t N, int64_t e, PnrRaw& w) {
-    w.p0 = S[0 * N + e]; w.p1 = S[1 * N + e]; w.p2 = S[2 * N + e];
-    w.p3 = S[3 * N + e]; w.p4 = S[4 * N + e]; w.p5 = S[5 * N + e];
-    const float2* a2 = reinterpret_cast<const float2*>(actions + e * PNR_DOF);
-    w.a01 = pnr_ld_stream(a2); w.a23 = pnr_ld_stream(a2 + 1); w.a45 = pnr_ld_stream(a2 + 2);
-}
-
-__device__ __forceinline__ void pnr_unpack_raw(const PnrRaw& w, PnrEnv& s) {
-    s.r[0] = w.p0.x; s.r[1] = w.p0.y; s.r[2] = w.p0.z; s.r[3] = w.p0.w; s.r[4] = w.p1.x; s.r[5] = w.p1.y;
-    s.v[0] = w.p1.z; s.v[1] = w.p1.w; s.v[2] = w.p2.x; s.v[3] = w.p2.y; s.v[4] = w.p2.z; s.v[5] = w.p2.w;
-    s.a[0] = w.p3.x; s.a[1] = w.p3.y; s.a[2] = w.p3.z; s.a[3] = w.p3.w; s.a[4] = w.p4.x; s.a[5] = w.p4.y;
-    s.pot = w.p4.z; s.ep_ret = w.p4.w;
-    s.tgt[0] = w.p5.x; s.tgt[1] = w.p5.y; s.tgt[2] = w.p5.z; s.t = __float_as_int(w.p5.w);
+__device__ __forceinline__ void pnr_load_env(float4* __restrict__ S, int64_t N, int64_t e, PnrEnv& s) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 rv = pnr_plane_rv(S, N, k)[e];
+        const float2 a = pnr_plane_a(S, N, k)[e];
+        s.r[2 * k] = rv.x; s.r[2 * k + 1] = rv.y; s.v[2 * k] = rv.z; s.v[2 * k + 1] = rv.w;
+        s.a[2 * k] = a.x; s.a[2 * k + 1] = a.y;
+    }
+    const float4 x0 = pnr_plane_x0(S, N)[e];
+    const float2 x1 = pnr_plane_x1(S, N)[e];
+    s.tgt[0] = x0.x; s.tgt[1] = x0.y; s.tgt[2] = x0.z; s.t = __float_as_int(x0.w);
+    s.pot = x1.x; s.ep_ret = x1.y;
 }
 
 __device__ __forceinline__ void pnr_store_env(float4* __restrict__ S, int64_t N, int64_t e, const PnrEnv& s) {
-    S[0 * N + e] = make_float4(s.r[0], s.r[1], s.r[2], s.r[3]);
-    S[1 * N + e] = make_float4(s.r[4], s.r[5], s.v[0], s.v[1]);
-    S[2 * N + e] = make_float4(s.v[2], s.v[3], s.v[4], s.v[5]);
-    S[3 * N + e] = make_float4(s.a[0], s.a[1], s.a[2], s.a[3]);
-    S[4 * N + e] = make_float4(s.a[4], s.a[5], s.pot, s.ep_ret);
-    S[5 * N + e] = make_float4(s.tgt[0], s.tgt[1], s.tgt[2], __int_as_float(s.t));
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        pnr_plane_rv(S, N, k)[e] = make_float4(s.r[2 * k], s.r[2 * k + 1], s.v[2 * k], s.v[2 * k + 1]);
+        pnr_plane_a(S, N, k)[e] = make_float2(s.a[2 * k], s.a[2 * k + 1]);
+    }
+    pnr_plane_x0(S, N)[e] = make_float4(s.tgt[0], s.tgt[1], s.tgt[2], __int_as_float(s.t));
+    pnr_plane_x1(S, N)[e] = make_float2(s.pot, s.ep_ret);
 }
 
 // reset_world (pioneer_knm_env.py:92-105): a = v = 0, potential = 0; TimeLimit.reset: elapsed = 0
@@ -77,10 +69,19 @@ __device__ __forceinline__ void pnr_reset_env(PnrEnv& s, const float (&q)[PNR_DO
 //   PNR_ARITH_F32      : the reference source under NumPy >= 2 (all float32)
 //   PNR_ARITH_LEGACY64 : NumPy 1.x promotion (float64 intermediates, float32 stores)
 // ---------------------------------------------------------------------------------------------
+// exact float32 quotient num / den.  A velocity that is ALREADY saturated gives num == +0 on every following
+// step; the hardware's fast division path rejects zero numerators and falls into a ~40-instruction subroutine,
+// so that (very common) case is answered directly with the IEEE result: +-0, or NaN for a zero / NaN divisor.
+__device__ __forceinline__ float pnr_div_exact(float num, float den) {
+    const bool zero = num == 0.f;
+    const float q = __fdiv_rn(zero ? 1.f : num, den);
+    const float q0 = (den != 0.f && den == den) ? copysignf(0.f, den) : __int_as_float(0x7fc00000);
+    return zero ? q0 : q;
+}
+
 template <int ARITH>
-__device__ __forceinline__ void pnr_integrate_joint(const PnrParams& p, int i, float a0, float v0, float r0,
-                                                    float& v1_out, float& r1_out) {
-    const float vmax = p.v_max[i];
+__device__ __forceinline__ void pnr_integrate_joint(const PnrParams& p, float vmax, float r_lo, float r_hi, float a0,
+                                                    float v0, float r0, float& v1_out, float& r1_out) {
     float v1, r1;
     if (ARITH == PNR_ARITH_F32) {
         const float dt = p.dt32;
@@ -89,7 +90,7 @@ __device__ __forceinline__ void pnr_integrate_joint(const PnrParams& p, int i, f
         const bool hi = v1 > vmax, lo = v1 < -vmax;                              // :125, :129
         if (hi || lo) {
             const float vsat = hi ? vmax : -vmax;
-            const float q = __fdiv_rn(__fsub_rn(vsat, v0), __fadd_rn(a0, p.eps32));  // :126, :130
+            const float q = pnr_div_exact(__fsub_rn(vsat, v0), __fadd_rn(a0, p.eps32));  // :126, :130
             dt_p1 = pnr_clip(q, 0.f, dt);
             dt_p2 = __fsub_rn(dt, dt_p1);
             v1 = vsat;
@@ -111,8 +112,8 @@ __device__ __forceinline__ void pnr_integrate_joint(const PnrParams& p, int i, f
         const double half = __dmul_rn(0.5, (double)__fadd_rn(v0, v1));
         r1 = (float)__dadd_rn(__dadd_rn((double)r0, __dmul_rn(half, dt_p1)), __dmul_rn((double)v1, dt_p2));
     }
-    if (r1 >= p.r_hi[i]) { r1 = p.r_hi[i]; v1 = 0.f; }                           // :135-137
-    if (r1 <= p.r_lo[i]) { r1 = p.r_lo[i]; v1 = 0.f; }                           // :139-141
+    if (r1 >= r_hi) { r1 = r_hi; v1 = 0.f; }                                     // :135-137
+    if (r1 <= r_lo) { r1 = r_lo; v1 = 0.f; }                                     // :139-141
     v1_out = v1; r1_out = r1;
 }
 
@@ -279,31 +280,105 @@ __device__ __forceinline__ void pnr_pack_obs_dyn(const PnrParams& p, float* __re
     }
 }
 
+// ---- per-joint column groups for the step kernel's joint warps (joint j owns columns j, 6+j, ..., 120+j) ----
+__device__ __forceinline__ void pnr_pack_joint_const(const PnrParams& p, float* __restrict__ row, int j) {
+    row[18 + j] = p.r_lo[j];   row[24 + j] = p.cos_r_lo[j];  row[30 + j] = p.sin_r_lo[j];
+    row[36 + j] = p.r_hi[j];   row[42 + j] = p.cos_r_hi[j];  row[48 + j] = p.sin_r_hi[j];
+}
+
+// `rowj` = row + j: every store below has an immediate offset from one base register
+__device__ __forceinline__ void pnr_pack_joint_head(float* __restrict__ rowj, float r, float sn, float cs) {
+    rowj[0] = r;               rowj[6] = cs;                 rowj[12] = sn;
+}
+
+// r - r_lo, r_hi - r, v, a and their cos / sin.  `fast_va`: v and a are inside the fast sincos range
+__device__ __forceinline__ void pnr_pack_joint_rest(float* __restrict__ rowj, float r_lo, float r_hi, float r,
+                                                    float v, float a, bool fast_va) {
+    float sn, cs;
+    const float dlo = __fsub_rn(r, r_lo);
+    pnr_sincos_fast(dlo, sn, cs);
+    rowj[54] = dlo;            rowj[60] = cs;                rowj[66] = sn;
+    const float dhi = __fsub_rn(r_hi, r);
+    pnr_sincos_fast(dhi, sn, cs);
+    rowj[72] = dhi;            rowj[78] = cs;                rowj[84] = sn;
+    rowj[90] = v;
+    rowj[108] = a;
+    if (fast_va) {
+        pnr_sincos_fast(v, sn, cs);
+        rowj[96] = cs;         rowj[102] = sn;
+        pnr_sincos_fast(a, sn, cs);
+        rowj[114] = cs;        rowj[120] = sn;
+    } else {
+        pnr_sincos(v, sn, cs);
+        rowj[96] = cs;         rowj[102] = sn;
+        pnr_sincos(a, sn, cs);
+        rowj[114] = cs;        rowj[120] = sn;
+    }
+}
+
+// episode statistics of one warp (= one tile): one set of atomics per warp that saw an episode end
+__device__ __forceinline__ void pnr_episode_stats(PnrStats* __restrict__ stats, bool ended, bool reached, float ep_ret,
+                                                  int32_t t, int lane) {
+    const unsigned done_mask = __ballot_sync(PNR_FULL_MASK, ended);
+    if (done_mask) {
+        const bool mine = (done_mask >> lane) & 1u;
+        float ret = mine ? ep_ret : 0.f, ret2 = ret * ret, len = mine ? (float)t : 0.f;
+        float mx = mine ? ep_ret : -INFINITY, mn = mine ? ep_ret : INFINITY;
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) {
+            ret += __shfl_xor_sync(PNR_FULL_MASK, ret, ofs);
+            ret2 += __shfl_xor_sync(PNR_FULL_MASK, ret2, ofs);
+            len += __shfl_xor_sync(PNR_FULL_MASK, len, ofs);
+            mx = fmaxf(mx, __shfl_xor_sync(PNR_FULL_MASK, mx, ofs));
+            mn = fminf(mn, __shfl_xor_sync(PNR_FULL_MASK, mn, ofs));
+        }
+        const unsigned reach_mask = __ballot_sync(PNR_FULL_MASK, reached);
+        if (lane == 0) {
+            atomicAdd(&stats->episodes, (double)__popc(done_mask));
+            atomicAdd(&stats->sum_return, (double)ret);
+            atomicAdd(&stats->sum_length, (double)len);
+            atomicAdd(&stats->sum_return_sq, (double)ret2);
+            atomicAdd(&stats->reached, (double)__popc(reach_mask));
+            atomicMax(&stats->max_return_ord, pnr_float_to_ordered(mx));
+            atomicMin(&stats->min_return_ord, pnr_float_to_ordered(mn));
+        }
+    }
+}
+
 // hand the warp's tile (rows_valid x 137 floats, contiguous in `out`) to global memory.  Full tiles (and any
 // tile whose byte count is a multiple of 16) go out as ONE TMA bulk store issued by lane 0; other ragged tails
 // use coalesced 16-byte stores.  Call pnr_tile_wait() before writing the tile again.
+__device__ __forceinline__ bool pnr_tile_is_bulk(int rows_valid) { return (rows_valid & 3) == 0; }
+
+// ragged tail: `n_threads` threads (tid = 0 .. n_threads-1) stream the tile with coalesced 16-byte stores
+__device__ __forceinline__ void pnr_emit_tile_manual(const float* __restrict__ tile, float* __restrict__ out,
+                                                     int rows_valid, int tid, int n_threads) {
+    const int total = rows_valid * PNR_OBS_DIM;
+    const int n4 = total >> 2;
+    const float4* t4 = reinterpret_cast<const float4*>(tile);
+    float4* o4 = reinterpret_cast<float4*>(out);
+#pragma unroll 4
+    for (int i = tid; i < n4; i += n_threads) pnr_st_stream(o4 + i, t4[i]);
+    for (int i = (n4 << 2) + tid; i < total; i += n_threads) pnr_st_stream(out + i, tile[i]);
+}
+
+// one warp owns the tile (reset / observe kernels)
 __device__ __forceinline__ void pnr_emit_tile(const float* __restrict__ tile, float* __restrict__ out,
                                               int rows_valid, int lane) {
     pnr_fence_async_smem();
     __syncwarp();
-    if ((rows_valid & 3) == 0) {
+    if (pnr_tile_is_bulk(rows_valid)) {
         if (lane == 0) {
             pnr_bulk_store(out, tile, (uint32_t)(rows_valid * PNR_OBS_DIM * sizeof(float)));
             pnr_bulk_commit();
         }
     } else {
-        const int total = rows_valid * PNR_OBS_DIM;
-        const int n4 = total >> 2;
-        const float4* t4 = reinterpret_cast<const float4*>(tile);
-        float4* o4 = reinterpret_cast<float4*>(out);
-#pragma unroll 4
-        for (int i = lane; i < n4; i += 32) pnr_st_stream(o4 + i, t4[i]);
-        for (int i = (n4 << 2) + lane; i < total; i += 32) pnr_st_stream(out + i, tile[i]);
+        pnr_emit_tile_manual(tile, out, rows_valid, lane, 32);
     }
 }
 
 // the tile may be overwritten once the copy engine has finished READING it
 __device__ __forceinline__ void pnr_tile_wait(int lane) {
-    if (lane == 0) pnr_bulk_wait_read();
+    if (lane == 0) pnr_bulk_wait_read<0>();
     __syncwarp();
 }

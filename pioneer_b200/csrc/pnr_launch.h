@@ -5,7 +5,14 @@
 
 #define PNR_STEP_WARPS 4
 #define PNR_STEP_THREADS (PNR_STEP_WARPS * 32)
-#define PNR_STEP_SMEM (PNR_STEP_WARPS * 32 * PNR_OBS_DIM * sizeof(float))   // 70,144 B: 3 CTAs / SM
+#ifndef PNR_STEP_MIN_CTAS
+#define PNR_STEP_MIN_CTAS 6                                                  // 24 warps / SM, <= 85 registers: no spills (8 CTAs spill)
+#endif
+#ifndef PNR_STEP_BUFS
+#define PNR_STEP_BUFS 1                                                      // observation tiles per CTA (2 = double buffering: measured no gain)
+#endif
+#define PNR_STEP_SMEM (PNR_STEP_BUFS * 32 * PNR_OBS_DIM * sizeof(float))     // step kernel: 17,536 B per tile buffer
+#define PNR_RO_SMEM (PNR_STEP_WARPS * 32 * PNR_OBS_DIM * sizeof(float))      // reset/observe: one tile per warp
 #define PNR_MAX_DEVICES 16
 
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions,
