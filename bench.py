@@ -257,6 +257,41 @@ def time_back_to_back(torch, env, actions, obs_ring, reward, flags, steps):
     return s.elapsed_time(e)
 
 
+def time_graph(torch, env, actions, obs_ring, steps):
+    """Same back-to-back loop replayed from a CUDA graph of len(obs_ring) steps: no host launch cost per step."""
+    T = obs_ring.shape[0]
+    n = obs_ring.shape[1]
+    rew = torch.empty((T, n), dtype=torch.float32, device=obs_ring.device)
+    flg = torch.empty((T, n), dtype=torch.uint8, device=obs_ring.device)
+    graph = env.capture_rollout(actions[:T].contiguous(), obs_ring, rew, flg)
+    reps = max(1, steps // T)
+    graph.replay()
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    s.record()
+    for _ in range(reps):
+        graph.replay()
+    e.record()
+    torch.cuda.synchronize()
+    return s.elapsed_time(e), reps * T
+
+
+def timing_floor(torch, env, flush, reps=200):
+    """What the per-step event-pair method reads for an (almost) empty kernel after the same flush: the part of
+    ms_per_step that no kernel work can remove.  Uses the library's 1-thread statistics snapshot kernel."""
+    out = []
+    for _ in range(reps):
+        flush()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        env.episode_stats_tensor()
+        b.record()
+        out.append((a, b))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in out)
+    return ts[len(ts) // 2]
+
+
 def make_buffers(torch, env, n, device, seed):
     g = torch.Generator(device=device).manual_seed(seed)
     a_max = torch.as_tensor(env.a_max, device=device)
@@ -345,6 +380,11 @@ def ours_arm(args):
     warm_ms = max_over_ranks(time_back_to_back(torch, env, actions, obs_ring, reward, flags, args.steps))
     value_l2_warm = total_envs * args.steps / (warm_ms / 1e3)
 
+    graph_ms, graph_steps = time_graph(torch, env, actions, obs_ring, args.steps)
+    graph_ms = max_over_ranks(graph_ms)
+    value_graph = total_envs * graph_steps / (graph_ms / 1e3)
+    floor_ms = timing_floor(torch, env, flush)
+
     # ---- end to end through the public host API: pinned host actions in, obs/reward/done out ------------
     e2e_steps = min(args.steps, 300)
     host_actions = [torch.empty((n, DOF), dtype=torch.float32, pin_memory=True).copy_(actions[i]) for i in range(4)]
@@ -377,8 +417,11 @@ def ours_arm(args):
                          "timed by its own CUDA-event pair on the launching stream",
                    "parallelism": f"env-sharded x{world}, no data-path collective; one stats all-reduce per iteration"},
         "substeps_per_sec": value * FRAME_SKIP,
+        "timing_floor_ms": floor_ms,
         "value_l2_warm": value_l2_warm,
         "ms_per_step_l2_warm": warm_ms / args.steps,
+        "value_l2_warm_cuda_graph": value_graph,
+        "ms_per_step_l2_warm_cuda_graph": graph_ms / graph_steps,
         "step_ms_percentiles": {"p5": srt[len(srt) // 20], "p50": srt[len(srt) // 2], "p95": srt[(len(srt) * 19) // 20]},
         "stats_allreduce_ms": stats_ms,
         "episode_stats": summarize(stats),

@@ -197,6 +197,28 @@ class BatchedPioneerEnv:
         self.step_index += 1
         return obs, reward, flags
 
+    def capture_rollout(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, flags: torch.Tensor):
+        """Capture T consecutive steps into ONE CUDA graph: ``actions`` [T,N,6] -> ``obs`` [T,N,137], ``reward`` [T,N],
+        ``flags`` [T,N] (caller-owned device tensors, re-read / re-written on every replay).  Replaying the graph
+        costs one launch for T fused kernels, which removes the host's per-step launch cost from a rollout
+        fragment whose actions are produced on the device.  Returns the torch.cuda.CUDAGraph; ``graph.replay()``
+        advances every env by T steps.  Note: the reset generator's call counter is frozen into the graph, so
+        replays re-use the same T reset ticks (episodes still differ: draws are keyed on the env id as well)."""
+        T = actions.shape[0]
+        assert actions.shape == (T, self.n_envs, DOF) and obs.shape == (T, self.n_envs, OBS_DIM)
+        assert reward.shape == (T, self.n_envs) and flags.shape == (T, self.n_envs)
+        for t_ in (actions, obs, reward, flags):
+            assert t_.is_contiguous() and t_.device == self.device
+        assert actions.dtype == torch.float32 and obs.dtype == torch.float32 and flags.dtype == torch.uint8
+        with torch.cuda.device(self.device):
+            self.step_tensor(actions[0], out=(obs[0], reward[0], flags[0]))     # one-time kernel attribute setup
+            torch.cuda.synchronize(self.device)
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                for t in range(T):
+                    self.step_tensor(actions[t], out=(obs[t], reward[t], flags[t]))
+        return graph
+
     def step(self, actions):
         """BulletEnv.step through gym TimeLimit (bullet_env.py:192-197, pioneer_knm_train.py:27) for every env:
         (obs, reward, done, info) with tensors; info['TimeLimit.truncated'] is a bool tensor."""
