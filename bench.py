@@ -323,6 +323,7 @@ def ours_arm(args):
     torch.cuda.set_device(device)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ["NCCL_DEBUG"] = os.environ.get("PNR_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     n = args.envs_per_gpu
@@ -352,6 +353,7 @@ def ours_arm(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
+    reduce_episode_stats(env.episode_stats_tensor())          # communicator set-up happens outside the timed region
     sampler = ClockSampler(local_rank) if rank == 0 else None
     # ---- device-resident throughput: `value` ---------------------------------------------------------
     env.episode_stats(clear=True)

@@ -1,0 +1,154 @@
+"""The reference-facing Python surface on the GPU: the single-env facade with the reference's constructor and
+gym.Env contract (pioneer/envs/pioneer/pioneer_knm_env.py:38-242), the launcher's env factories
+(pioneer/launch/pioneer_knm_train.py:20-29), the RLlib-style VectorEnv adapter and the CUDA-graph rollout."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from tests._util import golden_case, load_golden
+
+pytestmark = pytest.mark.gpu
+G = load_golden()
+
+
+def test_facade_has_the_reference_surface():
+    from pioneer_b200.envs.pioneer import PioneerKinematicConfig, PioneerKinematicEnv
+    env = PioneerKinematicEnv(headless=True, pioneer_config=PioneerKinematicConfig(), simulation_config=None,
+                              render_config=None)
+    assert env.dof == 6 and env.metadata["video.frames_per_second"] == 24
+    assert np.array_equal(env.r_lo, G["const_r_lo"]) and np.array_equal(env.r_hi, G["const_r_hi"])
+    assert np.array_equal(env.v_max, G["const_v_max"]) and np.array_equal(env.a_max, G["const_a_max"])
+    assert env.dt == G["const_dt_eps"][0] and env.eps == G["const_dt_eps"][1]
+    assert np.array_equal(env.action_space.low, G["const_action_low"])
+    assert np.array_equal(env.action_space.high, G["const_action_high"])
+    assert env.observation_space.shape == (137,) and str(env.observation_space.dtype) == "float64"
+    assert [j.name for j in env.scene.joints] == list(G["const_joint_names"])
+    assert set(G["const_item_names"]) <= set(env.scene.items_by_name)
+    lo, hi = env.joint_limits()
+    assert lo.dtype == np.float32 and np.array_equal(lo, G["const_r_lo"]) and np.array_equal(hi, G["const_r_hi"])
+    np.testing.assert_allclose([env.compute_potential(d) for d in (0.0, 0.1, 5.0, 20.0)], G["const_potential_kat"])
+    obs = env.reset()
+    assert obs.shape == (137,) and obs.dtype == np.float64
+    assert env.potential == 0 and (env.a == 0).all() and (env.v == 0).all()
+    obs2, reward, done, info = env.step(env.action_space.sample())
+    assert obs2.shape == (137,) and isinstance(reward, float) and isinstance(done, bool)
+    assert set(info) == {"r_pot", "r_step", "r_done", "rw", "dist", "pot", "a", "v", "r"}      # pioneer_knm_env.py:167-179
+    assert all(isinstance(v, str) for v in info.values())
+    with pytest.raises(NotImplementedError):
+        env.render()
+    env.close()
+
+
+def test_facade_under_timelimit_replays_the_reference_trajectory():
+    """TimeLimit(PioneerKinematicEnv(cfg), 500) exactly as the reference launcher builds it, driven with the cfg1
+    actions: joint state bit-exact, rewards/pointer within float32 tolerance, truncation at step 500."""
+    from pioneer_b200.launch import prepare_env
+    case = golden_case(G, "cfg1")
+    tl = prepare_env({"award_potential_slope": 10.0, "award_done": 5.0, "penalty_step": 1 / 100})
+    assert tl._max_episode_steps == 500
+    env = tl.env
+    tl.reset()
+    env.reset_world(joint_positions=case["q0"][0], target_position=tuple(case["target"][0]))
+    for t in range(510):
+        obs, reward, done, info = tl.step(case["actions"][t])
+        assert np.array_equal(env.r, case["r"][t]) and np.array_equal(env.v, case["v"][t]), t
+        np.testing.assert_allclose(reward, case["reward"][t], atol=1e-3)
+        np.testing.assert_allclose(obs[126:136], case["tail"][t][:10], atol=2e-4)
+        assert done == bool(case["done"][t])
+        assert bool(info.get("TimeLimit.truncated", False)) == bool(case["truncated"][t])
+        if done:
+            tl.reset()
+            env.reset_world(joint_positions=case["q0"][1], target_position=tuple(case["target"][1]))
+    tl.close()
+
+
+def test_facade_seed_reproduces_the_reference_draw_order():
+    """reset_world() draws 6 joint angles then 3 target coordinates from the env's RandomState (pioneer_knm_env.py:80-90)."""
+    from pioneer_b200.envs.pioneer import PioneerKinematicEnv
+    env = PioneerKinematicEnv()
+    env.seed(123)
+    obs = env.reset()
+    rs = np.random.RandomState(123)
+    q = rs.uniform(env.r_lo, env.r_hi)
+    tgt = rs.uniform(np.array(env.config.target_lo), np.array(env.config.target_hi))
+    assert np.array_equal(obs[0:6], q.astype(np.float32).astype(np.float64))
+    assert np.array_equal(obs[129:132], tgt.astype(np.float32).astype(np.float64))
+    env.close()
+
+
+def test_vector_env_rllib_contract():
+    from pioneer_b200 import PioneerVectorEnv
+    n = 48
+    venv = PioneerVectorEnv(n, max_episode_steps=3, seed=9)
+    obs = venv.vector_reset()
+    assert isinstance(obs, list) and len(obs) == n and obs[0].shape == (137,)
+    assert len(venv.get_unwrapped()) == n
+    rng = np.random.default_rng(0)
+    for t in range(1, 8):
+        actions = [(rng.uniform(-1, 1, size=6) * venv.batch.a_max).astype(np.float32) for _ in range(n)]
+        obs, rewards, dones, infos = venv.vector_step(actions)
+        assert len(obs) == len(rewards) == len(dones) == len(infos) == n
+        assert isinstance(rewards[0], float) and isinstance(dones[0], bool)
+        if t % 3 == 0:
+            assert all(dones) and all(i["TimeLimit.truncated"] for i in infos)
+            terminal_r = np.array([o[0:6] for o in obs])
+            # RLlib now calls reset_at(i): the kernel already started the next episode, its first observation comes back
+            fresh = np.array([venv.reset_at(i) for i in range(n)])
+            assert (fresh[:, 136] == 0).all() and (fresh[:, 90:96] == 0).all()
+            assert not np.array_equal(fresh[:, 0:6], terminal_r)
+            state_r = venv.batch.state()["r"].cpu().numpy()
+            assert np.array_equal(fresh[:, 0:6], state_r)
+        else:
+            assert not any(dones) and all(i == {} for i in infos)
+    # an explicit reset_at of an env that is NOT done starts a new episode for that env only
+    before = venv.batch.state()["t"].cpu().numpy().copy()
+    first = venv.reset_at(5)
+    after = venv.batch.state()["t"].cpu().numpy()
+    assert after[5] == 0 and first[136] == 0 and np.array_equal(np.delete(after, 5), np.delete(before, 5))
+    venv.close()
+
+
+def test_prepare_vector_env_factory():
+    from pioneer_b200.launch import prepare_vector_env
+    venv = prepare_vector_env({"award_potential_slope": 4.0, "award_done": 7.5, "penalty_step": 0.02, "num_envs": 64,
+                               "seed": 1, "worker_index": 2})
+    assert venv.num_envs == 64 and venv.batch.env_id_base == 128
+    assert venv.batch.config.award_done == 7.5 and venv.batch.batch_config.max_episode_steps == 500
+    venv.close()
+
+
+def test_cuda_graph_rollout_equals_stepping():
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    n, T = 3000, 6
+    a = BatchedPioneerEnv(n, seed=4, batch_config=BatchConfig(max_episode_steps=4))
+    b = BatchedPioneerEnv(n, seed=4, batch_config=BatchConfig(max_episode_steps=4))
+    g = torch.Generator(device="cuda").manual_seed(0)
+    actions = (torch.rand((T, n, 6), device="cuda", generator=g) * 2 - 1) * torch.as_tensor(a.a_max).cuda()
+    obs = torch.zeros((T, n, 137), device="cuda")
+    rew = torch.zeros((T, n), device="cuda")
+    flg = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+    # capture_rollout runs one eager step first (kernel attribute set-up); mirror it on the twin
+    graph = a.capture_rollout(actions, obs, rew, flg)
+    b.step_tensor(actions[0])
+    graph.replay()
+    torch.cuda.synchronize()
+    for t in range(T):
+        o, r, f = b.step_tensor(actions[t])
+        assert torch.equal(r, rew[t]) and torch.equal(f, flg[t]), t
+        # reset draws are keyed on the call counter, which the graph froze at capture time: compare non-reset rows
+        keep = ~(f & 1).bool()
+        assert torch.equal(o[keep], obs[t][keep])
+    a.close(); b.close()
+
+
+def test_scene_mirrors_answer_from_device_state():
+    from pioneer_b200.envs.pioneer import PioneerKinematicEnv
+    env = PioneerKinematicEnv()
+    env.reset_world(joint_positions=np.zeros(6, np.float32), target_position=(20.0, 0.0, 4.0))
+    np.testing.assert_allclose(env.scene.items_by_name["robot:pointer"].pose().xyz, (14.6, 1.0, 15.9), atol=1e-5)
+    np.testing.assert_allclose(env.scene.items_by_name["target"].pose().xyz, (20.0, 0.0, 4.0))
+    assert [j.position() for j in env.scene.joints] == [0.0] * 6 and env.scene.joints[0].velocity() == 0.0
+    env.scene.joints[1].reset_state(0.5)
+    np.testing.assert_allclose(env.joint_positions(), [0, 0.5, 0, 0, 0, 0])
+    env.close()

@@ -340,3 +340,41 @@ def test_errors_are_loud():
     with pytest.raises(_cabi.PioneerB200Error):
         _cabi.check(env._lib.pnr_reset(env._h, None, 3, None, None, None, None), "pnr_reset")
     env.close()
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[1]: 4,096 envs on one B200, 1,000 steps, same seeds/actions as the CPU oracle (the C
+# restatement, oracle/reach_oracle.c): per-step q / qdot / pointer diff, done/reset masks bit-exact.
+# ---------------------------------------------------------------------------------------------
+def test_cfg2_4096_envs_1000_steps_vs_c_oracle():
+    from oracle.c_oracle import COracleBatch
+    n, steps, seed = 4096, 1000, 2026
+    chain = oracle_chain()
+    cc = COracleBatch(chain, n, OracleConfig(max_episode_steps=500), arith="np2", seed=seed, obs_mode="terminal")
+    env = make_env(n, max_episode_steps=500, auto_reset=True, obs_mode="terminal", seed=seed)
+    rng = np.random.default_rng(7)
+    worst = dict(pos=0.0, rew=0.0, trig=0.0)
+    n_done = 0
+    for t in range(steps):
+        # mostly in-range random actions; every 50th step a burst far outside the action space (stored unclipped)
+        scale = 40.0 if t % 50 == 49 else 1.0
+        act = (rng.uniform(-1, 1, size=(n, 6)) * env.a_max * scale).astype(np.float32)
+        obs, reward, flags = env.step_tensor(torch.as_tensor(act).cuda())
+        o_obs, o_reward, o_flags = cc.step(act)
+        assert np.array_equal(flags.cpu().numpy(), o_flags), f"done/reset mask differs at step {t}"
+        n_done += int((o_flags & 1).sum())
+        o = obs.cpu().numpy().astype(np.float64)
+        assert np.array_equal(o[:, VALUE_COLS], o_obs[:, VALUE_COLS]), f"q / qdot / a / target differ at step {t}"
+        worst["pos"] = max(worst["pos"], float(np.abs(o[:, POS_COLS] - o_obs[:, POS_COLS]).max()))
+        worst["trig"] = max(worst["trig"], float(np.abs(o[:, TRIG_COLS] - o_obs[:, TRIG_COLS]).max()))
+        worst["rew"] = max(worst["rew"], float(np.abs(reward.cpu().numpy() - o_reward).max()))
+        if t % 100 == 99 or t == steps - 1:      # the internal state after auto-resets as well
+            s, os_ = env.state(), cc.state()
+            for k in ("r", "v", "a", "t"):
+                assert np.array_equal(s[k].cpu().numpy(), os_[k]), (k, t)
+    assert n_done == 2 * n                       # TimeLimit at steps 500 and 1000, Philox auto-resets in between
+    assert worst["pos"] <= POS_TOL and worst["rew"] <= REW_TOL and worst["trig"] <= TRIG_TOL, worst
+    st = env.episode_stats()
+    assert st["episodes"] == cc.stats[0] and st["env_steps"] == n * steps
+    np.testing.assert_allclose(st["sum_return"], cc.stats[1], rtol=1e-5)
+    env.close()
