@@ -40,9 +40,10 @@ BYTES_PER_ENV_STEP = BYTES_IO + BYTES_STATE          # 761
 FRAME_SKIP = 10
 FALLBACK_HBM_GBS = 6650.0                            # /opt/skills/guides/B200_PROFILING.md fallback
 L2_FLUSH_BYTES = 512 << 20                           # > 4x the 126 MB L2
-# dram__bytes_read.sum + dram__bytes_write.sum per launch of pnr_step_kernel at 65,536 envs from the committed
-# `ncu --set full` capture (profiles/); None until a capture exists
-NCU_TRAFFIC_BYTES_65536 = None
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of pnr_step_kernel from the committed `ncu --set full`
+# captures (profiles/r01_v3_step_65536.md, profiles/r01_v3_step_1m.md).  At 65,536 envs most of the 36 MB of
+# observations is still dirty in the 126 MB L2 when the kernel ends, so DRAM writes read far below the algorithmic bytes.
+NCU_TRAFFIC_BYTES = {65536: 7.91e6 + 0.75e6, 1048576: 126.1e6 + 625.7e6}
 
 
 def parse_args():
@@ -100,6 +101,34 @@ def _cpu_worker(task):
     return timed_steps, time.perf_counter() - t0
 
 
+def _c_port_worker(task):
+    """The compiled restatement (oracle/reach_oracle.c): 256 envs per process, observations included."""
+    proc_id, seconds = task
+    import numpy as np
+    from oracle.c_oracle import COracleBatch
+    from oracle.reach_oracle import OracleChain
+    from pioneer_b200.urdf import flatten_urdf
+    n = 256
+    b = COracleBatch(OracleChain.from_model(flatten_urdf()), n, env_id_base=proc_id * n, seed=0)
+    act = (np.random.default_rng(proc_id).uniform(-1, 1, size=(n, DOF)) * b.a_max).astype(np.float32)
+    for _ in range(20):
+        b.step(act)
+    t0, k = time.perf_counter(), 0
+    while time.perf_counter() - t0 < seconds:
+        for _ in range(20):
+            b.step(act)
+        k += 20
+    return k * n, time.perf_counter() - t0
+
+
+def run_c_port(seconds: float = 3.0):
+    import multiprocessing as mp
+    cores = _host_cores()
+    with mp.get_context("spawn").Pool(cores) as pool:
+        res = pool.map(_c_port_worker, [(i, seconds) for i in range(cores)])
+    return sum(r[0] for r in res) / max(r[1] for r in res), cores
+
+
 def run_cpu_path(steps: int, warmup: int, per_step: int):
     """steps x per_step env-steps on each of P processes.  Returns (value, cores, seconds, per_step)."""
     import multiprocessing as mp
@@ -121,6 +150,12 @@ def reference_arm(args):
     if rank != 0:
         return
     value, cores, seconds, per_step = run_cpu_path(args.steps, args.warmup, args.cpu_steps_per_proc)
+    try:     # context only: how fast a COMPILED single-thread-per-core port of the same env runs on these cores
+        c_value, c_cores = run_c_port()
+        c_port = {"value": c_value, "unit": UNIT, "cores": c_cores,
+                  "sample": "oracle/reach_oracle.c, 256 envs per process x all cores, ~3 s, observations included"}
+    except Exception as exc:  # noqa: BLE001
+        c_port = {"value": None, "note": repr(exc)}
     sample = (f"{cores} processes x 1 env each (the reference's rollout-worker layout), {args.steps} steps x "
               f"{per_step} env-steps per process, TimeLimit 500 with resets, random actions; "
               "Python restatement of the reference env (oracle/reach_oracle.py), no PyBullet calls: an upper "
@@ -132,7 +167,8 @@ def reference_arm(args):
         "data": "synthetic",
         "config": {"workload": "one reach env per host process, random actions, TimeLimit 500",
                    "envs": cores, "env_steps_per_step": cores * per_step},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
+                         "c_port": c_port},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "substeps_per_sec": value * FRAME_SKIP, "gpu_launches": 0,
     }
@@ -435,7 +471,7 @@ def ours_arm(args):
                 "api": "BatchedPioneerEnv.step_host -> pnr_step_host (pinned host buffers, copies inside the timed region)",
                 "timer": "host perf_counter around synchronous calls, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": NCU_TRAFFIC_BYTES_65536 if n == 65536 else None, "kernel": "pnr_step_kernel<F32,TERMINAL>",
+                     "traffic": NCU_TRAFFIC_BYTES.get(n), "kernel": "pnr_step_kernel<F32,TERMINAL>",
                      "bytes_per_env_step": BYTES_PER_ENV_STEP, "units_per_launch": n, "peak_source": peak_src},
     }
     env.close()
