@@ -493,6 +493,25 @@ def ours_arm(args):
             del a, o, r, f
         line["sweep"] = sweep
 
+    # ---- Tier-B dynamic mode (ABA + PD control, 10 substeps per env step), reported separately ---------------
+    if world == 1 and not args.no_sweep:
+        from pioneer_b200 import SimulationConfig
+        m = args.envs_per_gpu
+        e = BatchedPioneerEnv(m, device=device, seed=0, simulation_config=SimulationConfig(gravity=9.81),
+                              batch_config=BatchConfig(mode="dynamic", kp=2000.0, kd=500.0, torque_scale=1e5,
+                                                       max_episode_steps=500))
+        a, o, r, f = make_buffers(torch, e, m, device, seed=2)
+        lo, hi = torch.as_tensor(e.r_lo, device=device), torch.as_tensor(e.r_hi, device=device)
+        a = (a / torch.as_tensor(e.a_max, device=device)) * 0.5 * (hi - lo) + 0.5 * (hi + lo)   # desired joint positions
+        k_steps = min(args.steps, 300)
+        ms, _ = time_device_steps(torch, e, a.contiguous(), o, r, f, k_steps, 10, flush)
+        line["dynamic_mode"] = {
+            "workload": f"{m} envs, gravity 9.81, PD position control (kp 2000, kd 500), {FRAME_SKIP} ABA substeps per env step",
+            "ms_per_step": ms / k_steps, "value": m * k_steps / (ms / 1e3), "unit": UNIT,
+            "substeps_per_sec": FRAME_SKIP * m * k_steps / (ms / 1e3), "parity": "float64 oracle, unpinned vs PyBullet"}
+        e.close()
+        del a, o, r, f
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline_subprocess()

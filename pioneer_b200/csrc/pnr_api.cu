@@ -124,6 +124,29 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
         p.target_hi[k] = (float)c.target_hi[k];
     }
     if (!(c.timestep > 0) || c.frame_skip < 1) return pnr_fail(PNR_ERR_INVALID, "timestep/frame_skip must be positive");
+    // dynamic mode: composite bodies about their frame origins (parallel-axis shift of the URDF inertials)
+    for (int j = 0; j < PNR_DOF; ++j) {
+        const double m_ = m.body_mass[j];
+        const double* c_ = m.body_com[j];
+        const double* I_ = m.body_inertia[j];
+        const double cc = c_[0] * c_[0] + c_[1] * c_[1] + c_[2] * c_[2];
+        const int idx[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+        for (int k = 0; k < 6; ++k) {
+            const int a = idx[k][0], b = idx[k][1];
+            p.dyn_io[j][k] = (float)(I_[3 * a + b] + m_ * ((a == b ? cc : 0.0) - c_[a] * c_[b]));
+        }
+        for (int k = 0; k < 3; ++k) p.dyn_mc[j][k] = (float)(m_ * c_[k]);
+        p.dyn_mass[j] = (float)m_;
+        p.dyn_tau_max[j] = (float)(m.effort[j] * c.torque_scale);
+        p.dyn_damping[j] = (float)m.damping[j];
+        if (c.mode == PNR_MODE_DYNAMIC && !(m_ > 0.0))
+            return pnr_fail(PNR_ERR_INVALID, "dynamic mode needs a positive composite mass on every moving frame");
+    }
+    p.dyn_kp = (float)c.kp; p.dyn_kd = (float)c.kd;
+    p.dyn_use_pd = (c.kp != 0.0 || c.kd != 0.0) ? 1 : 0;
+    p.dyn_dt = (float)c.timestep;
+    p.dyn_gravity = (float)c.gravity;
+    p.dyn_frame_skip = c.frame_skip;
     p.dt64 = c.timestep * c.frame_skip;          // World.step_time, bullet_scene.py:277-279
     p.eps64 = 1e-5;                              // pioneer_knm_env.py:61
     p.dt32 = (float)p.dt64;
@@ -152,8 +175,12 @@ extern "C" int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t
         return pnr_fail(PNR_ERR_INVALID, "pnr_create: unknown arith");
     if (cfg->obs_mode != PNR_OBS_TERMINAL && cfg->obs_mode != PNR_OBS_AUTORESET)
         return pnr_fail(PNR_ERR_INVALID, "pnr_create: unknown obs_mode");
-    if (cfg->mode != PNR_MODE_KINEMATIC)
-        return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_create: only PNR_MODE_KINEMATIC is built in this version");
+    if (cfg->mode != PNR_MODE_KINEMATIC && cfg->mode != PNR_MODE_DYNAMIC)
+        return pnr_fail(PNR_ERR_INVALID, "pnr_create: unknown mode");
+    if (cfg->mode == PNR_MODE_DYNAMIC && cfg->arith != PNR_ARITH_F32)
+        return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_create: the dynamic mode computes in float32 (arith must be PNR_ARITH_F32)");
+    if (cfg->n_obstacles != 0 || cfg->contact_penalty != 0.0)
+        return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_create: the obstacle contact penalty is not built in this version");
     int count = 0;
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count == 0)
@@ -250,8 +277,12 @@ extern "C" int pnr_step(pnr_handle* h, const float* actions, float* obs, float* 
     if ((reinterpret_cast<uintptr_t>(obs) & 15) || (reinterpret_cast<uintptr_t>(actions) & 7))
         return pnr_fail(PNR_ERR_INVALID, "pnr_step: obs must be 16-byte and actions 8-byte aligned");
     PnrDeviceGuard guard(h->device);
-    PNR_CUDA(pnr_launch_step(h->params, h->device, h->cfg.arith, h->cfg.obs_mode, h->state, actions, obs, reward, done,
-                             h->stats, h->tick, (cudaStream_t)stream));
+    if (h->cfg.mode == PNR_MODE_DYNAMIC)
+        PNR_CUDA(pnr_launch_step_dynamic(h->params, h->device, h->cfg.obs_mode, h->state, actions, obs, reward, done,
+                                         h->stats, h->tick, (cudaStream_t)stream));
+    else
+        PNR_CUDA(pnr_launch_step(h->params, h->device, h->cfg.arith, h->cfg.obs_mode, h->state, actions, obs, reward, done,
+                                 h->stats, h->tick, (cudaStream_t)stream));
     h->tick += 1;
     h->env_steps += (double)h->n_envs;
     h->launches += 1;

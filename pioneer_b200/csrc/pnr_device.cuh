@@ -41,6 +41,14 @@ struct PnrParams {
     int32_t max_episode_steps;
     int32_t auto_reset;
     int32_t trig_slow;              // v_max beyond the fast sincos range: joint-rate columns take the library path
+    // dynamic (Tier-B) mode: composite rigid body of each moving frame about the frame origin, control, stepping
+    float dyn_io[PNR_DOF][6];       // rotational inertia about the frame origin: xx xy xz yy yz zz
+    float dyn_mc[PNR_DOF][3];       // mass * centre of mass
+    float dyn_mass[PNR_DOF];
+    float dyn_tau_max[PNR_DOF];     // effort * torque_scale
+    float dyn_damping[PNR_DOF];
+    float dyn_kp, dyn_kd, dyn_dt, dyn_gravity;
+    int32_t dyn_frame_skip, dyn_use_pd;
     uint32_t seed_lo, seed_hi;
     int64_t env_id_base;
     int64_t n_envs;

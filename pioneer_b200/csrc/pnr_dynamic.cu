@@ -1,0 +1,111 @@
+// K2: the fused env step of the dynamic (Tier-B) mode.  One thread per env: frame_skip substeps of
+// [PD / torque control -> Featherstone ABA -> semi-implicit Euler -> limit stops] with the joint state in
+// registers, then the same task code as the kinematic env (pioneer_knm_env.py:151-211): forward kinematics of
+// the pointer, reward, done, TimeLimit, statistics, auto-reset, 137-float observation staged per warp in shared
+// memory and stored with one TMA bulk copy.  Bound: FP32 pipe (10 x ~2 kflop per env-step against 761 B).
+#include "pnr_dynamics.cuh"
+#include "pnr_launch.h"
+
+template <int OBS_MODE>
+__global__ void __launch_bounds__(PNR_STEP_THREADS)
+pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
+                        float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
+                        PnrStats* __restrict__ stats, uint32_t tick) {
+    extern __shared__ __align__(128) float smem[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float* tile = smem + warp * PNR_TILE_FLOATS;
+    float* row = tile + lane * PNR_OBS_DIM;
+    const int64_t N = p.n_envs;
+    const int64_t n_tiles = (N + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
+    bool tile_busy = false;
+    pnr_pack_obs_const(p, row);
+    for (int64_t t_idx = (int64_t)blockIdx.x * PNR_STEP_WARPS + warp; t_idx < n_tiles;
+         t_idx += (int64_t)gridDim.x * PNR_STEP_WARPS) {
+        const int64_t env_raw = t_idx * PNR_TILE_ENVS + lane;
+        const bool active = env_raw < N;
+        const int64_t env = active ? env_raw : N - 1;
+
+        PnrEnv s;
+        pnr_load_env(state, N, env, s);
+        const float2* a2 = reinterpret_cast<const float2*>(actions + env * PNR_DOF);
+        const float2 act01 = pnr_ld_stream(a2), act23 = pnr_ld_stream(a2 + 1), act45 = pnr_ld_stream(a2 + 2);
+        // the action drives THIS step's substeps (a motor target, not the kinematic env's delayed acceleration)
+        s.a[0] = act01.x; s.a[1] = act01.y; s.a[2] = act23.x; s.a[3] = act23.y; s.a[4] = act45.x; s.a[5] = act45.y;
+        pnr_dynamic_substeps(p, s.r, s.v, s.a);
+
+        PnrPose o;
+        pnr_pose<true>(p, s, o);                               // q is inside the joint limits
+        bool reached = o.dist < p.done_distance;
+        if (fabsf(o.dist - p.done_distance) < p.done_band)
+            pnr_fk_tip_f64(p, s.r, s.tgt, o.ptr, o.dist, reached);
+        const float pot_new = pnr_potential(p, o.dist);
+        const float rew = __fadd_rn(__fadd_rn(__fsub_rn(pot_new, s.pot), -p.penalty_step), reached ? p.award_done : 0.f);
+        s.pot = pot_new;
+        s.t += 1;
+        s.ep_ret = __fadd_rn(s.ep_ret, rew);
+        const bool timeout = p.max_episode_steps > 0 && s.t >= p.max_episode_steps;
+        const bool is_done = reached || timeout;
+        const uint8_t flags = (is_done ? PNR_DONE : 0) | ((timeout && !reached) ? PNR_TRUNCATED : 0);
+        if (active) {
+            reward[env] = rew;
+            done[env] = flags;
+        }
+        pnr_episode_stats(stats, is_done && active, reached && active, s.ep_ret, s.t, lane);
+
+        if (tile_busy) pnr_tile_wait(lane);
+        float vmax_abs = 0.f;                                  // joint rates are not bounded by construction here
+#pragma unroll
+        for (int i = 0; i < PNR_DOF; ++i) vmax_abs = fmaxf(vmax_abs, fabsf(s.v[i]));
+        const bool slow = !(vmax_abs <= PNR_TRIG_FAST_LIMIT);
+        const bool do_reset = is_done && (p.auto_reset != 0);
+        if (OBS_MODE == PNR_OBS_TERMINAL) pnr_pack_obs_dyn<true>(p, row, s, o, s.pot, slow);
+        if (do_reset) {
+            float q[PNR_DOF], tg[3];
+            pnr_reset_draws(p, p.env_id_base + env, tick, q, tg);
+            pnr_reset_env(s, q, tg);
+        }
+        if (OBS_MODE == PNR_OBS_AUTORESET) {
+            if (__any_sync(PNR_FULL_MASK, do_reset)) {
+                PnrPose o2;
+                pnr_pose<true>(p, s, o2);
+                if (do_reset) o = o2;
+            }
+            pnr_pack_obs_dyn<true>(p, row, s, o, s.pot, slow && !do_reset);
+        }
+        if (active) pnr_store_env(state, N, env, s);
+        const int64_t rows_left = N - t_idx * PNR_TILE_ENVS;
+        pnr_emit_tile(tile, obs + t_idx * (int64_t)PNR_TILE_FLOATS,
+                      rows_left < PNR_TILE_ENVS ? (int)rows_left : PNR_TILE_ENVS, lane);
+        tile_busy = true;
+    }
+    if (lane == 0) pnr_bulk_wait_read<0>();
+}
+
+static int pnr_dyn_resident(const void* fn) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, PNR_STEP_THREADS, PNR_RO_SMEM);
+    return sms * (per_sm < 1 ? 1 : per_sm);
+}
+
+cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode, float4* state, const float* actions,
+                                    float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick,
+                                    cudaStream_t stream) {
+    typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t);
+    static Kern kernels[2] = {pnr_step_dynamic_kernel<PNR_OBS_TERMINAL>, pnr_step_dynamic_kernel<PNR_OBS_AUTORESET>};
+    static int grids[PNR_MAX_DEVICES][2] = {};
+    int& resident = grids[device % PNR_MAX_DEVICES][obs_mode];
+    if (resident == 0) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)kernels[obs_mode], cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)PNR_RO_SMEM);
+        if (e != cudaSuccess) return e;
+        resident = pnr_dyn_resident((const void*)kernels[obs_mode]);
+    }
+    const int64_t per_cta = PNR_TILE_ENVS * PNR_STEP_WARPS;
+    int64_t grid = (p.n_envs + per_cta - 1) / per_cta;
+    if (grid > resident) grid = resident;
+    if (grid < 1) grid = 1;
+    kernels[obs_mode]<<<(unsigned)grid, PNR_STEP_THREADS, PNR_RO_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick);
+    return cudaGetLastError();
+}

@@ -173,7 +173,7 @@ __device__ __forceinline__ void pnr_fk_tip(const PnrParams& p, const float (&sn)
 // float64 twin, only for envs whose float32 distance falls inside the done band: the reference
 // evaluates `distance < done_distance` in double (pioneer_knm_env.py:155-160), so the done mask is
 // decided in double exactly where float32 could flip it.  Rare => deliberately not inlined.
-__device__ __noinline__ void pnr_fk_tip_f64(const PnrParams& p, const float (&r)[PNR_DOF], const float (&tgt)[3],
+static __device__ __noinline__ void pnr_fk_tip_f64(const PnrParams& p, const float (&r)[PNR_DOF], const float (&tgt)[3],
                                              float (&ptr_out)[3], float& dist_out, bool& within) {
     double x = p.tip_xyz64[0], y = p.tip_xyz64[1], z = p.tip_xyz64[2];
     for (int j = PNR_DOF - 1; j >= 0; --j) {
@@ -232,7 +232,7 @@ __device__ __forceinline__ void pnr_pack_obs_const(const PnrParams& p, float* __
 
 template <bool FAST>
 __device__ __forceinline__ void pnr_pack_obs_dyn(const PnrParams& p, float* __restrict__ row, const PnrEnv& s,
-                                                 const PnrPose& o, float pot) {
+                                                 const PnrPose& o, float pot, bool force_slow = false) {
     float sn, cs;
 #pragma unroll
     for (int i = 0; i < PNR_DOF; ++i) {
@@ -254,7 +254,7 @@ __device__ __forceinline__ void pnr_pack_obs_dyn(const PnrParams& p, float* __re
     row[136] = pot;
     // cos / sin of the joint rates and of the stored (unclipped) action: straight-line code unless this env
     // holds an argument outside the fast range, which a policy bounded by the action space never produces
-    bool fast = FAST && !p.trig_slow;
+    bool fast = FAST && !p.trig_slow && !force_slow;
     if (FAST) {
         float m = 0.f;
 #pragma unroll
