@@ -119,7 +119,11 @@ void pnr_default_config(pnr_config* cfg);
 /* Replaces PioneerKinematicEnv.__init__ + BulletEnv.reset_simulator (pioneer_knm_env.py:39-74,
  * bullet_env.py:90-99) for n_envs independent envs on CUDA device `device`.  `env_id_base` is the
  * global id of local env 0 (multi-GPU sharding; reset randomness is keyed on the global id so results
- * do not depend on the number of GPUs).  All envs start reset (as reset_world()). */
+ * do not depend on the number of GPUs).  All envs start reset (as reset_world()).
+ * cfg->mode = PNR_MODE_DYNAMIC selects the ABA + PD/torque kernel (World.step / Joint.control_position,
+ * bullet_scene.py:123-155, 273-275); cfg->n_obstacles > 0 with a non-zero contact_penalty selects the obstacle
+ * variant (Scene.create_body_box / create_body_plane, bullet_scene.py:206-259).  Both are defined in DESIGN.md
+ * sections 8-9 and are unpinned by the reference. */
 int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t n_envs, int64_t env_id_base,
                int device, uint64_t seed, pnr_handle** out);
 void pnr_destroy(pnr_handle* h);

@@ -105,6 +105,11 @@ class OracleConfig:
     gravity: float = 0
     # gym TimeLimit, pioneer_knm_train.py:27
     max_episode_steps: int = 500
+    # obstacle variant (this repo's extension; the reference only ever instantiates a box and a
+    # plane in its GUI demo, pioneer_knm_env.py:249-261): list of (kind, position, extent), kind in plane/box/sphere
+    obstacles: Tuple = ()
+    contact_penalty: float = 0.0
+    box_samples: int = 8
 
 
 @dataclass
@@ -117,11 +122,13 @@ class OracleChain:
     tip_xyz: np.ndarray
     lower: np.ndarray
     upper: np.ndarray
+    capsules: Tuple = ()          # (body, radius, p0, p1) in the moving frame of `body`
 
     @staticmethod
     def from_model(m) -> "OracleChain":
+        caps = tuple((int(b), float(r), np.array(p0, f64), np.array(p1, f64)) for b, r, p0, p1 in getattr(m, "capsules", ()))
         return OracleChain(np.array(m.axis, f64), np.array(m.origin_xyz, f64), np.array(m.origin_rot, f64),
-                           np.array(m.tip_xyz, f64), np.array(m.lower, f64), np.array(m.upper, f64))
+                           np.array(m.tip_xyz, f64), np.array(m.lower, f64), np.array(m.upper, f64), caps)
 
 
 def fk_pointer(chain: OracleChain, q) -> np.ndarray:
@@ -136,6 +143,45 @@ def fk_pointer(chain: OracleChain, q) -> np.ndarray:
         p = p * c + np.cross(k, p) * s + k * (float(k @ p) * (1.0 - c))
         p = chain.origin_xyz[j] + chain.origin_rot[j] @ p
     return p
+
+
+def fk_point(chain: OracleChain, q, body: int, point) -> np.ndarray:
+    """World position of a point fixed in the moving frame of ``body`` (same recursion as fk_pointer)."""
+    p = np.array(point, f64)
+    for j in range(body, -1, -1):
+        k = chain.axis[j]
+        c, s = math.cos(float(q[j])), math.sin(float(q[j]))
+        p = p * c + np.cross(k, p) * s + k * (float(k @ p) * (1.0 - c))
+        p = chain.origin_xyz[j] + chain.origin_rot[j] @ p
+    return p
+
+
+def contact_depth(chain: OracleChain, q, obstacles, box_samples: int = 8) -> float:
+    """Sum over (link capsule, obstacle) pairs of the penetration depth max(0, radius - distance(segment, obstacle)).
+    plane : exact (signed distance is linear along the segment: the nearer end point decides)
+    sphere: exact (closest point of the segment to the centre)
+    box   : axis-aligned signed-distance function sampled at ``box_samples`` equally spaced points of the segment"""
+    total = 0.0
+    for body, radius, p0, p1 in chain.capsules:
+        a, b = fk_point(chain, q, body, p0), fk_point(chain, q, body, p1)
+        for kind, pos, ext in obstacles:
+            pos, ext = np.array(pos, f64), np.array(ext, f64)
+            if kind == "plane":
+                d = min(float((a - pos) @ ext), float((b - pos) @ ext))
+            elif kind == "sphere":
+                ab = b - a
+                t = min(max(float((pos - a) @ ab) / max(float(ab @ ab), 1e-30), 0.0), 1.0)
+                d = float(np.linalg.norm(a + t * ab - pos)) - float(ext[0])
+            elif kind == "box":
+                d = math.inf
+                for k in range(box_samples):
+                    x = a + (b - a) * (k / (box_samples - 1))
+                    qv = np.abs(x - pos) - ext
+                    d = min(d, float(np.linalg.norm(np.maximum(qv, 0.0))) + min(float(qv.max()), 0.0))
+            else:
+                raise ValueError(kind)
+            total += max(0.0, radius - d)
+    return total
 
 
 class OracleEnv:
@@ -254,6 +300,9 @@ class OracleEnv:
         done = distance < self.config.done_distance                                    # :160
         reward = (self.potential - old_potential) + (-self.config.penalty_step) \
             + (self.config.award_done if done else 0)                                  # :162-165
+        if self.config.obstacles and self.config.contact_penalty:
+            self.last_contact_depth = contact_depth(self.chain, self.r, self.config.obstacles, self.config.box_samples)
+            reward -= self.config.contact_penalty * self.last_contact_depth
         # world.step(): frame_skip x stepSimulation with g = 0, qdot = 0, tau = 0 leaves q unchanged (:181)
         return float(reward), bool(done)
 

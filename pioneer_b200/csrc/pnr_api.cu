@@ -142,6 +142,24 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
         if (c.mode == PNR_MODE_DYNAMIC && !(m_ > 0.0))
             return pnr_fail(PNR_ERR_INVALID, "dynamic mode needs a positive composite mass on every moving frame");
     }
+    // obstacle variant; without a penalty weight there is nothing to compute
+    p.contact_penalty = (float)c.contact_penalty;
+    p.n_obstacles = (c.contact_penalty != 0.0) ? c.n_obstacles : 0;
+    p.n_capsules = m.n_capsules;
+    for (int i = 0; i < m.n_capsules; ++i) {
+        if (m.capsule_body[i] < 0 || m.capsule_body[i] >= PNR_DOF)
+            return pnr_fail(PNR_ERR_INVALID, "pnr_model.capsule_body out of range");
+        p.capsule_body[i] = m.capsule_body[i];
+        p.capsule_radius[i] = (float)m.capsule_radius[i];
+        for (int k = 0; k < 3; ++k) { p.capsule_p0[i][k] = (float)m.capsule_p0[i][k]; p.capsule_p1[i][k] = (float)m.capsule_p1[i][k]; }
+    }
+    for (int i = 0; i < c.n_obstacles; ++i) {
+        const int t = c.obstacle_type[i];
+        if (t != PNR_OBSTACLE_PLANE && t != PNR_OBSTACLE_BOX && t != PNR_OBSTACLE_SPHERE)
+            return pnr_fail(PNR_ERR_INVALID, "pnr_config.obstacle_type must be plane, box or sphere");
+        p.obstacle_type[i] = t;
+        for (int k = 0; k < 3; ++k) { p.obstacle_p[i][k] = (float)c.obstacle_p[i][k]; p.obstacle_e[i][k] = (float)c.obstacle_e[i][k]; }
+    }
     p.dyn_kp = (float)c.kp; p.dyn_kd = (float)c.kd;
     p.dyn_use_pd = (c.kp != 0.0 || c.kd != 0.0) ? 1 : 0;
     p.dyn_dt = (float)c.timestep;
@@ -179,8 +197,9 @@ extern "C" int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t
         return pnr_fail(PNR_ERR_INVALID, "pnr_create: unknown mode");
     if (cfg->mode == PNR_MODE_DYNAMIC && cfg->arith != PNR_ARITH_F32)
         return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_create: the dynamic mode computes in float32 (arith must be PNR_ARITH_F32)");
-    if (cfg->n_obstacles != 0 || cfg->contact_penalty != 0.0)
-        return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_create: the obstacle contact penalty is not built in this version");
+    if (cfg->n_obstacles < 0 || cfg->n_obstacles > PNR_MAX_OBSTACLES || model->n_capsules < 0 ||
+        model->n_capsules > PNR_MAX_CAPSULES)
+        return pnr_fail(PNR_ERR_INVALID, "pnr_create: too many obstacles / capsules");
     int count = 0;
     cudaError_t ce = cudaGetDeviceCount(&count);
     if (ce != cudaSuccess || count == 0)

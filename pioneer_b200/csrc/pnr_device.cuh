@@ -49,6 +49,14 @@ struct PnrParams {
     float dyn_damping[PNR_DOF];
     float dyn_kp, dyn_kd, dyn_dt, dyn_gravity;
     int32_t dyn_frame_skip, dyn_use_pd;
+    // obstacle variant: link capsules (moving-frame coordinates) against static plane / box / sphere obstacles
+    int32_t n_capsules, n_obstacles;
+    int32_t capsule_body[PNR_MAX_CAPSULES];
+    float capsule_radius[PNR_MAX_CAPSULES];
+    float capsule_p0[PNR_MAX_CAPSULES][3], capsule_p1[PNR_MAX_CAPSULES][3];
+    int32_t obstacle_type[PNR_MAX_OBSTACLES];
+    float obstacle_p[PNR_MAX_OBSTACLES][3], obstacle_e[PNR_MAX_OBSTACLES][3];
+    float contact_penalty;
     uint32_t seed_lo, seed_hi;
     int64_t env_id_base;
     int64_t n_envs;

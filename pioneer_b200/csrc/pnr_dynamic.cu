@@ -6,7 +6,7 @@
 #include "pnr_dynamics.cuh"
 #include "pnr_launch.h"
 
-template <int OBS_MODE>
+template <int OBS_MODE, bool OBSTACLES>
 __global__ void __launch_bounds__(PNR_STEP_THREADS)
 pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                         float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
@@ -39,7 +39,13 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         if (fabsf(o.dist - p.done_distance) < p.done_band)
             pnr_fk_tip_f64(p, s.r, s.tgt, o.ptr, o.dist, reached);
         const float pot_new = pnr_potential(p, o.dist);
-        const float rew = __fadd_rn(__fadd_rn(__fsub_rn(pot_new, s.pot), -p.penalty_step), reached ? p.award_done : 0.f);
+        float rew = __fadd_rn(__fadd_rn(__fsub_rn(pot_new, s.pot), -p.penalty_step), reached ? p.award_done : 0.f);
+        if (OBSTACLES) {
+            PnrSinCos sc;
+#pragma unroll
+            for (int i = 0; i < PNR_DOF; ++i) { sc.sn[i] = o.sn[i]; sc.cs[i] = o.cs[i]; }
+            rew = __fsub_rn(rew, __fmul_rn(p.contact_penalty, pnr_contact_depth(p, sc)));
+        }
         s.pot = pot_new;
         s.t += 1;
         s.ep_ret = __fadd_rn(s.ep_ret, rew);
@@ -93,19 +99,22 @@ cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode
                                     float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick,
                                     cudaStream_t stream) {
     typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t);
-    static Kern kernels[2] = {pnr_step_dynamic_kernel<PNR_OBS_TERMINAL>, pnr_step_dynamic_kernel<PNR_OBS_AUTORESET>};
-    static int grids[PNR_MAX_DEVICES][2] = {};
-    int& resident = grids[device % PNR_MAX_DEVICES][obs_mode];
+    static Kern kernels[2][2] = {
+        {pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, false>, pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, true>},
+        {pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, false>, pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, true>}};
+    static int grids[PNR_MAX_DEVICES][2][2] = {};
+    const int obst = p.n_obstacles > 0 ? 1 : 0;
+    Kern kern = kernels[obs_mode][obst];
+    int& resident = grids[device % PNR_MAX_DEVICES][obs_mode][obst];
     if (resident == 0) {
-        cudaError_t e = cudaFuncSetAttribute((const void*)kernels[obs_mode], cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)PNR_RO_SMEM);
+        cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PNR_RO_SMEM);
         if (e != cudaSuccess) return e;
-        resident = pnr_dyn_resident((const void*)kernels[obs_mode]);
+        resident = pnr_dyn_resident((const void*)kern);
     }
     const int64_t per_cta = PNR_TILE_ENVS * PNR_STEP_WARPS;
     int64_t grid = (p.n_envs + per_cta - 1) / per_cta;
     if (grid > resident) grid = resident;
     if (grid < 1) grid = 1;
-    kernels[obs_mode]<<<(unsigned)grid, PNR_STEP_THREADS, PNR_RO_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick);
+    kern<<<(unsigned)grid, PNR_STEP_THREADS, PNR_RO_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick);
     return cudaGetLastError();
 }

@@ -60,7 +60,7 @@ extern "C" int pnr_debug_trace(unsigned long long* out_host) {
 #define PNR_TRACE_NEXT()
 #endif
 
-template <int ARITH, int OBS_MODE>
+template <int ARITH, int OBS_MODE, bool OBSTACLES>
 __global__ void __launch_bounds__(PNR_STEP_THREADS, PNR_STEP_MIN_CTAS)
 pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
@@ -181,8 +181,14 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             }
             const float pot_new = pnr_potential(p, o.dist);
             // (potential - old_potential) + (-penalty_step) + (award_done | 0), pioneer_knm_env.py:162-165
-            const float rew = __fadd_rn(__fadd_rn(__fsub_rn(pot_new, pot_old), -p.penalty_step),
-                                        reached ? p.award_done : 0.f);
+            float rew = __fadd_rn(__fadd_rn(__fsub_rn(pot_new, pot_old), -p.penalty_step),
+                                  reached ? p.award_done : 0.f);
+            if (OBSTACLES) {                                   // obstacle variant: capsule penetration penalty
+                PnrSinCos sc;
+#pragma unroll
+                for (int i = 0; i < PNR_DOF; ++i) { sc.sn[i] = o.sn[i]; sc.cs[i] = o.cs[i]; }
+                rew = __fsub_rn(rew, __fmul_rn(p.contact_penalty, pnr_contact_depth(p, sc)));
+            }
             t += 1;
             ep_ret = __fadd_rn(ep_ret, rew);
             const bool timeout = p.max_episode_steps > 0 && t >= p.max_episode_steps;
@@ -368,12 +374,17 @@ static int64_t pnr_grid_for(int64_t n_envs, int envs_per_cta, int resident) {
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions, float* obs,
                             float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, cudaStream_t stream) {
     typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t);
-    static Kern kernels[2][2] = {
-        {pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_TERMINAL>, pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_AUTORESET>},
-        {pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_TERMINAL>, pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_AUTORESET>}};
-    static int grids[PNR_MAX_DEVICES][2][2] = {};     // cudaFuncSetAttribute is per device
-    Kern k = kernels[arith][obs_mode];
-    int& resident = grids[device % PNR_MAX_DEVICES][arith][obs_mode];
+    // the obstacle variant is a separate instantiation: the plain kernel carries no trace of it (a call site alone
+    // cost 40 % at 1M envs through caller-saved register spills)
+    static Kern kernels[2][2][2] = {
+        {{pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_TERMINAL, false>, pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_TERMINAL, true>},
+         {pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_AUTORESET, false>, pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_AUTORESET, true>}},
+        {{pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_TERMINAL, false>, pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_TERMINAL, true>},
+         {pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_AUTORESET, false>, pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_AUTORESET, true>}}};
+    static int grids[PNR_MAX_DEVICES][2][2][2] = {};  // cudaFuncSetAttribute is per device
+    const int obst = p.n_obstacles > 0 ? 1 : 0;
+    Kern k = kernels[arith][obs_mode][obst];
+    int& resident = grids[device % PNR_MAX_DEVICES][arith][obs_mode][obst];
     if (resident == 0) {
         cudaError_t e = pnr_prepare(k, PNR_STEP_SMEM, &resident);
         if (e != cudaSuccess) return e;

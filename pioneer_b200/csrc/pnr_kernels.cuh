@@ -134,40 +134,100 @@ __device__ __forceinline__ void pnr_sincos_sel(float x, float& s, float& c) {
 //   p <- origin_j + R_origin_j * Rot(axis_j, q_j) * p          (URDF: child = parent*T(origin)*Rot(axis,q))
 // replaces resetJointState x6 + getLinkState (pioneer_knm_env.py:148-151, bullet_scene.py:58).
 // ---------------------------------------------------------------------------------------------
+// one stage of the chain: v <- origin_j + R_origin_j * Rot(axis_j, q_j) * v
+__device__ __forceinline__ void pnr_fk_stage(const PnrParams& p, int j, float sn, float c, float& x, float& y, float& z) {
+    const float s = sn * p.axis_sign[j];
+    const int code = p.axis_code[j];            // warp-uniform (constant bank)
+    if (code == PNR_AXIS_X) {
+        const float ny = fmaf(c, y, -s * z), nz = fmaf(s, y, c * z);
+        y = ny; z = nz;
+    } else if (code == PNR_AXIS_Y) {
+        const float nx = fmaf(c, x, s * z), nz = fmaf(-s, x, c * z);
+        x = nx; z = nz;
+    } else if (code == PNR_AXIS_Z) {
+        const float nx = fmaf(c, x, -s * y), ny = fmaf(s, x, c * y);
+        x = nx; y = ny;
+    } else {                                     // Rodrigues: p c + (k x p) s + k (k.p)(1-c)
+        const float kx = p.axis[j][0], ky = p.axis[j][1], kz = p.axis[j][2];
+        const float kp = (kx * x + ky * y + kz * z) * (1.f - c);
+        const float nx = fmaf(x, c, fmaf(ky * z - kz * y, s, kx * kp));
+        const float ny = fmaf(y, c, fmaf(kz * x - kx * z, s, ky * kp));
+        const float nz = fmaf(z, c, fmaf(kx * y - ky * x, s, kz * kp));
+        x = nx; y = ny; z = nz;
+    }
+    if (p.origin_has_rot[j]) {
+        const float* R = p.origin_rot[j];
+        const float nx = R[0] * x + R[1] * y + R[2] * z;
+        const float ny = R[3] * x + R[4] * y + R[5] * z;
+        const float nz = R[6] * x + R[7] * y + R[8] * z;
+        x = nx; y = ny; z = nz;
+    }
+    x += p.origin_xyz[j][0]; y += p.origin_xyz[j][1]; z += p.origin_xyz[j][2];
+}
+
 __device__ __forceinline__ void pnr_fk_tip(const PnrParams& p, const float (&sn)[PNR_DOF], const float (&cs)[PNR_DOF],
                                            float (&out)[3]) {
     float x = p.tip_xyz[0], y = p.tip_xyz[1], z = p.tip_xyz[2];
 #pragma unroll
-    for (int j = PNR_DOF - 1; j >= 0; --j) {
-        const float c = cs[j], s = sn[j] * p.axis_sign[j];
-        const int code = p.axis_code[j];            // warp-uniform (constant bank)
-        if (code == PNR_AXIS_X) {
-            const float ny = fmaf(c, y, -s * z), nz = fmaf(s, y, c * z);
-            y = ny; z = nz;
-        } else if (code == PNR_AXIS_Y) {
-            const float nx = fmaf(c, x, s * z), nz = fmaf(-s, x, c * z);
-            x = nx; z = nz;
-        } else if (code == PNR_AXIS_Z) {
-            const float nx = fmaf(c, x, -s * y), ny = fmaf(s, x, c * y);
-            x = nx; y = ny;
-        } else {                                     // Rodrigues: p c + (k x p) s + k (k.p)(1-c)
-            const float kx = p.axis[j][0], ky = p.axis[j][1], kz = p.axis[j][2];
-            const float kp = (kx * x + ky * y + kz * z) * (1.f - c);
-            const float nx = fmaf(x, c, fmaf(ky * z - kz * y, s, kx * kp));
-            const float ny = fmaf(y, c, fmaf(kz * x - kx * z, s, ky * kp));
-            const float nz = fmaf(z, c, fmaf(kx * y - ky * x, s, kz * kp));
-            x = nx; y = ny; z = nz;
-        }
-        if (p.origin_has_rot[j]) {
-            const float* R = p.origin_rot[j];
-            const float nx = R[0] * x + R[1] * y + R[2] * z;
-            const float ny = R[3] * x + R[4] * y + R[5] * z;
-            const float nz = R[6] * x + R[7] * y + R[8] * z;
-            x = nx; y = ny; z = nz;
-        }
-        x += p.origin_xyz[j][0]; y += p.origin_xyz[j][1]; z += p.origin_xyz[j][2];
-    }
+    for (int j = PNR_DOF - 1; j >= 0; --j) pnr_fk_stage(p, j, sn[j], cs[j], x, y, z);
     out[0] = x; out[1] = y; out[2] = z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Obstacle variant (this repo's extension; the reference instantiates a box and a plane only in its GUI demo,
+// pioneer_knm_env.py:249-261): sum over (link capsule, obstacle) pairs of max(0, radius - distance(segment, obstacle)).
+// plane: exact (nearer end point); sphere: exact (closest point of the segment); axis-aligned box: signed-distance
+// function sampled at PNR_BOX_SAMPLES points of the segment.  Same definition as oracle/reach_oracle.py::contact_depth.
+// Rare configuration => not inlined; the sin/cos travel by value so the caller's arrays stay in registers.
+// ---------------------------------------------------------------------------------------------
+#define PNR_BOX_SAMPLES 8
+struct PnrSinCos { float sn[PNR_DOF], cs[PNR_DOF]; };
+
+static __device__ __noinline__ float pnr_contact_depth(const PnrParams& p, PnrSinCos sc) {
+    float total = 0.f;
+    for (int c = 0; c < p.n_capsules; ++c) {
+        const int body = p.capsule_body[c];
+        float ax = p.capsule_p0[c][0], ay = p.capsule_p0[c][1], az = p.capsule_p0[c][2];
+        float bx = p.capsule_p1[c][0], by = p.capsule_p1[c][1], bz = p.capsule_p1[c][2];
+#pragma unroll
+        for (int j = PNR_DOF - 1; j >= 0; --j) {
+            if (j <= body) {
+                pnr_fk_stage(p, j, sc.sn[j], sc.cs[j], ax, ay, az);
+                pnr_fk_stage(p, j, sc.sn[j], sc.cs[j], bx, by, bz);
+            }
+        }
+        const float radius = p.capsule_radius[c];
+        const float dx = bx - ax, dy = by - ay, dz = bz - az;
+        for (int o = 0; o < p.n_obstacles; ++o) {
+            const float px = p.obstacle_p[o][0], py = p.obstacle_p[o][1], pz = p.obstacle_p[o][2];
+            const float ex = p.obstacle_e[o][0], ey = p.obstacle_e[o][1], ez = p.obstacle_e[o][2];
+            float d;
+            if (p.obstacle_type[o] == PNR_OBSTACLE_PLANE) {
+                const float da = (ax - px) * ex + (ay - py) * ey + (az - pz) * ez;
+                const float db = (bx - px) * ex + (by - py) * ey + (bz - pz) * ez;
+                d = fminf(da, db);
+            } else if (p.obstacle_type[o] == PNR_OBSTACLE_SPHERE) {
+                const float len2 = fmaxf(dx * dx + dy * dy + dz * dz, 1e-30f);
+                float t = ((px - ax) * dx + (py - ay) * dy + (pz - az) * dz) / len2;
+                t = fminf(fmaxf(t, 0.f), 1.f);
+                const float cx = fmaf(t, dx, ax) - px, cy = fmaf(t, dy, ay) - py, cz = fmaf(t, dz, az) - pz;
+                d = sqrtf(cx * cx + cy * cy + cz * cz) - ex;
+            } else {
+                d = INFINITY;
+#pragma unroll
+                for (int k = 0; k < PNR_BOX_SAMPLES; ++k) {
+                    const float t = (float)k / (float)(PNR_BOX_SAMPLES - 1);
+                    const float qx = fabsf(fmaf(t, dx, ax) - px) - ex, qy = fabsf(fmaf(t, dy, ay) - py) - ey,
+                                qz = fabsf(fmaf(t, dz, az) - pz) - ez;
+                    const float ox = fmaxf(qx, 0.f), oy = fmaxf(qy, 0.f), oz = fmaxf(qz, 0.f);
+                    const float sdf = sqrtf(ox * ox + oy * oy + oz * oz) + fminf(fmaxf(qx, fmaxf(qy, qz)), 0.f);
+                    d = fminf(d, sdf);
+                }
+            }
+            total += fmaxf(0.f, radius - d);
+        }
+    }
+    return total;
 }
 
 // float64 twin, only for envs whose float32 distance falls inside the done band: the reference
