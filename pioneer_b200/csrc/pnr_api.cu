@@ -160,6 +160,13 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
         p.obstacle_type[i] = t;
         for (int k = 0; k < 3; ++k) { p.obstacle_p[i][k] = (float)c.obstacle_p[i][k]; p.obstacle_e[i][k] = (float)c.obstacle_e[i][k]; }
     }
+    {   // the shipped robot's axis pattern gets the specialised dynamics kernel (pnr_dynamics.cuh, PNR_CHAIN_PIONEER)
+        const int pattern[PNR_DOF] = {PNR_AXIS_Z, PNR_AXIS_Y, PNR_AXIS_Y, PNR_AXIS_X, PNR_AXIS_Y, PNR_AXIS_X};
+        bool match = true;
+        for (int j = 0; j < PNR_DOF; ++j)
+            match = match && p.axis_code[j] == pattern[j] && p.axis_sign[j] > 0.f && !p.origin_has_rot[j];
+        p.chain_kind = match ? 1 : 0;
+    }
     p.dyn_kp = (float)c.kp; p.dyn_kd = (float)c.kd;
     p.dyn_use_pd = (c.kp != 0.0 || c.kd != 0.0) ? 1 : 0;
     p.dyn_dt = (float)c.timestep;

@@ -6,7 +6,7 @@
 #include "pnr_dynamics.cuh"
 #include "pnr_launch.h"
 
-template <int OBS_MODE, bool OBSTACLES>
+template <int OBS_MODE, bool OBSTACLES, int CHAIN>
 __global__ void __launch_bounds__(PNR_STEP_THREADS)
 pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                         float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
@@ -31,7 +31,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         const float2 act01 = pnr_ld_stream(a2), act23 = pnr_ld_stream(a2 + 1), act45 = pnr_ld_stream(a2 + 2);
         // the action drives THIS step's substeps (a motor target, not the kinematic env's delayed acceleration)
         s.a[0] = act01.x; s.a[1] = act01.y; s.a[2] = act23.x; s.a[3] = act23.y; s.a[4] = act45.x; s.a[5] = act45.y;
-        pnr_dynamic_substeps(p, s.r, s.v, s.a);
+        pnr_dynamic_substeps<CHAIN>(p, s.r, s.v, s.a);
 
         PnrPose o;
         pnr_pose<true>(p, s, o);                               // q is inside the joint limits
@@ -99,13 +99,15 @@ cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode
                                     float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick,
                                     cudaStream_t stream) {
     typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t);
-    static Kern kernels[2][2] = {
-        {pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, false>, pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, true>},
-        {pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, false>, pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, true>}};
-    static int grids[PNR_MAX_DEVICES][2][2] = {};
+#define PNR_DYN_ROW(CH) \
+    {{pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, false, CH>, pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, true, CH>}, \
+     {pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, false, CH>, pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, true, CH>}}
+    static Kern kernels[2][2][2] = {PNR_DYN_ROW(PNR_CHAIN_GENERIC), PNR_DYN_ROW(PNR_CHAIN_PIONEER)};
+    static int grids[PNR_MAX_DEVICES][2][2][2] = {};
     const int obst = p.n_obstacles > 0 ? 1 : 0;
-    Kern kern = kernels[obs_mode][obst];
-    int& resident = grids[device % PNR_MAX_DEVICES][obs_mode][obst];
+    const int chain = p.chain_kind == PNR_CHAIN_PIONEER ? 1 : 0;
+    Kern kern = kernels[chain][obs_mode][obst];
+    int& resident = grids[device % PNR_MAX_DEVICES][chain][obs_mode][obst];
     if (resident == 0) {
         cudaError_t e = cudaFuncSetAttribute((const void*)kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PNR_RO_SMEM);
         if (e != cudaSuccess) return e;

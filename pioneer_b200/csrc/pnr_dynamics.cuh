@@ -36,11 +36,79 @@ __device__ __forceinline__ V3 matTmul(const Mat3& a, V3 v) {
               fmaf(a.m[2], v.x, fmaf(a.m[5], v.y, a.m[8] * v.z)));
 }
 
+// CHAIN selects how the joint axes are known.  PNR_CHAIN_GENERIC reads axis codes / origin rotations from the
+// constant bank (warp-uniform branches, any serial 6-revolute chain).  PNR_CHAIN_PIONEER bakes in the shipped
+// robot (axes Z Y Y X Y X, all positive, no origin rotation; assets/pioneer_reach_6dof.urdf = the reference's
+// pioneer_knm_6dof.urdf:204-275): inside the fully unrolled joint loops every code is a compile-time constant, the
+// branches and zero terms fold away and the substep body shrinks from ~12,000 to ~3,000 SASS instructions -- the
+// generic body does not fit the instruction cache (71 % of warp stalls were instruction fetch, profiles/r01_dyn_v1).
+#define PNR_CHAIN_GENERIC 0
+#define PNR_CHAIN_PIONEER 1
+
+template <int CHAIN>
+__device__ __forceinline__ int pnr_code(const PnrParams& p, int j) {
+    if (CHAIN == PNR_CHAIN_PIONEER) return j == 0 ? PNR_AXIS_Z : ((j == 3 || j == 5) ? PNR_AXIS_X : PNR_AXIS_Y);
+    return p.axis_code[j];
+}
+template <int CHAIN>
+__device__ __forceinline__ V3 pnr_axis(const PnrParams& p, int j) {
+    if (CHAIN == PNR_CHAIN_PIONEER) {
+        const int c = pnr_code<CHAIN>(p, j);
+        return v3(c == PNR_AXIS_X ? 1.f : 0.f, c == PNR_AXIS_Y ? 1.f : 0.f, c == PNR_AXIS_Z ? 1.f : 0.f);
+    }
+    return v3(p.axis[j][0], p.axis[j][1], p.axis[j][2]);
+}
+// axis . v,  axis * s,  v x (axis * s),  I axis (a column),  H^T axis (a row): single components when the axis is known
+template <int CHAIN>
+__device__ __forceinline__ float pnr_axis_dot(const PnrParams& p, int j, V3 v) {
+    if (CHAIN == PNR_CHAIN_PIONEER) {
+        const int c = pnr_code<CHAIN>(p, j);
+        return c == PNR_AXIS_X ? v.x : (c == PNR_AXIS_Y ? v.y : v.z);
+    }
+    return dot(pnr_axis<CHAIN>(p, j), v);
+}
+template <int CHAIN>
+__device__ __forceinline__ V3 pnr_axis_scaled(const PnrParams& p, int j, float s) {
+    if (CHAIN == PNR_CHAIN_PIONEER) {
+        const int c = pnr_code<CHAIN>(p, j);
+        return v3(c == PNR_AXIS_X ? s : 0.f, c == PNR_AXIS_Y ? s : 0.f, c == PNR_AXIS_Z ? s : 0.f);
+    }
+    return pnr_axis<CHAIN>(p, j) * s;
+}
+template <int CHAIN>
+__device__ __forceinline__ V3 pnr_cross_axis(const PnrParams& p, int j, V3 a, float s) {     // a x (axis * s)
+    if (CHAIN == PNR_CHAIN_PIONEER) {
+        const int c = pnr_code<CHAIN>(p, j);
+        if (c == PNR_AXIS_X) return v3(0.f, a.z * s, -a.y * s);
+        if (c == PNR_AXIS_Y) return v3(-a.z * s, 0.f, a.x * s);
+        return v3(a.y * s, -a.x * s, 0.f);
+    }
+    return cross(a, pnr_axis<CHAIN>(p, j) * s);
+}
+template <int CHAIN>
+__device__ __forceinline__ V3 pnr_sym_axis(const PnrParams& p, int j, const Sym3& m) {        // m * axis
+    if (CHAIN == PNR_CHAIN_PIONEER) {
+        const int c = pnr_code<CHAIN>(p, j);
+        if (c == PNR_AXIS_X) return v3(m.xx, m.xy, m.xz);
+        if (c == PNR_AXIS_Y) return v3(m.xy, m.yy, m.yz);
+        return v3(m.xz, m.yz, m.zz);
+    }
+    return symmul(m, pnr_axis<CHAIN>(p, j));
+}
+template <int CHAIN>
+__device__ __forceinline__ V3 pnr_matT_axis(const PnrParams& p, int j, const Mat3& a) {       // a^T * axis
+    if (CHAIN == PNR_CHAIN_PIONEER) {
+        const int c = pnr_code<CHAIN>(p, j);
+        return v3(a.m[3 * c + 0], a.m[3 * c + 1], a.m[3 * c + 2]);
+    }
+    return matTmul(a, pnr_axis<CHAIN>(p, j));
+}
+
 // rotation about joint j's axis by the angle whose (sin, cos) are given; axis-aligned axes cost 4 FMA.
-// `code` / `sign` / general axis come from the constant bank, so the branch is warp-uniform.
+template <int CHAIN>
 __device__ __forceinline__ V3 pnr_axis_rot(const PnrParams& p, int j, float s, float c, V3 v) {
-    const int code = p.axis_code[j];
-    s *= p.axis_sign[j];
+    const int code = pnr_code<CHAIN>(p, j);
+    if (CHAIN != PNR_CHAIN_PIONEER) s *= p.axis_sign[j];
     if (code == PNR_AXIS_X) return v3(v.x, fmaf(c, v.y, -s * v.z), fmaf(s, v.y, c * v.z));
     if (code == PNR_AXIS_Y) return v3(fmaf(c, v.x, s * v.z), v.y, fmaf(-s, v.x, c * v.z));
     if (code == PNR_AXIS_Z) return v3(fmaf(c, v.x, -s * v.y), fmaf(s, v.x, c * v.y), v.z);
@@ -52,9 +120,10 @@ __device__ __forceinline__ V3 pnr_axis_rot(const PnrParams& p, int j, float s, f
 }
 
 // child -> parent coordinates: R_j v = O_j Rot(axis_j, q_j) v
+template <int CHAIN>
 __device__ __forceinline__ V3 pnr_rot(const PnrParams& p, int j, float s, float c, V3 v) {
-    V3 r = pnr_axis_rot(p, j, s, c, v);
-    if (p.origin_has_rot[j]) {
+    V3 r = pnr_axis_rot<CHAIN>(p, j, s, c, v);
+    if (CHAIN != PNR_CHAIN_PIONEER && p.origin_has_rot[j]) {
         const float* O = p.origin_rot[j];
         r = v3(O[0] * r.x + O[1] * r.y + O[2] * r.z, O[3] * r.x + O[4] * r.y + O[5] * r.z, O[6] * r.x + O[7] * r.y + O[8] * r.z);
     }
@@ -62,23 +131,25 @@ __device__ __forceinline__ V3 pnr_rot(const PnrParams& p, int j, float s, float 
 }
 
 // parent -> child coordinates: R_j^T v
+template <int CHAIN>
 __device__ __forceinline__ V3 pnr_rot_t(const PnrParams& p, int j, float s, float c, V3 v) {
-    if (p.origin_has_rot[j]) {
+    if (CHAIN != PNR_CHAIN_PIONEER && p.origin_has_rot[j]) {
         const float* O = p.origin_rot[j];
         v = v3(O[0] * v.x + O[3] * v.y + O[6] * v.z, O[1] * v.x + O[4] * v.y + O[7] * v.z, O[2] * v.x + O[5] * v.y + O[8] * v.z);
     }
-    return pnr_axis_rot(p, j, -s, c, v);
+    return pnr_axis_rot<CHAIN>(p, j, -s, c, v);
 }
 
 // B' = R B R^T for a general 3x3 block: rotate the columns, then the rows
+template <int CHAIN>
 __device__ __forceinline__ Mat3 pnr_rot_block(const PnrParams& p, int j, float s, float c, const Mat3& b) {
-    const V3 c0 = pnr_rot(p, j, s, c, v3(b.m[0], b.m[3], b.m[6]));
-    const V3 c1 = pnr_rot(p, j, s, c, v3(b.m[1], b.m[4], b.m[7]));
-    const V3 c2 = pnr_rot(p, j, s, c, v3(b.m[2], b.m[5], b.m[8]));
+    const V3 c0 = pnr_rot<CHAIN>(p, j, s, c, v3(b.m[0], b.m[3], b.m[6]));
+    const V3 c1 = pnr_rot<CHAIN>(p, j, s, c, v3(b.m[1], b.m[4], b.m[7]));
+    const V3 c2 = pnr_rot<CHAIN>(p, j, s, c, v3(b.m[2], b.m[5], b.m[8]));
     // rows of C = R B are (c0.x c1.x c2.x), ...; row i of B' = R * (row i of C)
-    const V3 r0 = pnr_rot(p, j, s, c, v3(c0.x, c1.x, c2.x));
-    const V3 r1 = pnr_rot(p, j, s, c, v3(c0.y, c1.y, c2.y));
-    const V3 r2 = pnr_rot(p, j, s, c, v3(c0.z, c1.z, c2.z));
+    const V3 r0 = pnr_rot<CHAIN>(p, j, s, c, v3(c0.x, c1.x, c2.x));
+    const V3 r1 = pnr_rot<CHAIN>(p, j, s, c, v3(c0.y, c1.y, c2.y));
+    const V3 r2 = pnr_rot<CHAIN>(p, j, s, c, v3(c0.z, c1.z, c2.z));
     Mat3 o = {{r0.x, r0.y, r0.z, r1.x, r1.y, r1.z, r2.x, r2.y, r2.z}};
     return o;
 }
@@ -101,6 +172,7 @@ struct PnrDynWork {                 // per-joint quantities kept between the thr
 };
 
 // qdd = ABA(q, qd, tau); gravity acts along -z of the base frame
+template <int CHAIN>
 __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR_DOF], const float (&qd)[PNR_DOF],
                                         const float (&tau)[PNR_DOF], float (&qdd)[PNR_DOF]) {
     PnrDynWork w;
@@ -110,14 +182,12 @@ __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR
     for (int i = 0; i < PNR_DOF; ++i) {
         pnr_sincos_fast(q[i], w.sn[i], w.cs[i]);                       // q is inside the joint limits
         const V3 pi = v3(p.origin_xyz[i][0], p.origin_xyz[i][1], p.origin_xyz[i][2]);
-        const V3 ax = v3(p.axis[i][0], p.axis[i][1], p.axis[i][2]);
         const V3 t = vl - cross(pi, om);
-        om = pnr_rot_t(p, i, w.sn[i], w.cs[i], om);
-        vl = pnr_rot_t(p, i, w.sn[i], w.cs[i], t);
-        const V3 sq = ax * qd[i];
-        om = om + sq;
-        w.c_ang[i] = cross(om, sq);
-        w.c_lin[i] = cross(vl, sq);
+        om = pnr_rot_t<CHAIN>(p, i, w.sn[i], w.cs[i], om);
+        vl = pnr_rot_t<CHAIN>(p, i, w.sn[i], w.cs[i], t);
+        om = om + pnr_axis_scaled<CHAIN>(p, i, qd[i]);
+        w.c_ang[i] = pnr_cross_axis<CHAIN>(p, i, om, qd[i]);
+        w.c_lin[i] = pnr_cross_axis<CHAIN>(p, i, vl, qd[i]);
         const Sym3 Io = {p.dyn_io[i][0], p.dyn_io[i][1], p.dyn_io[i][2], p.dyn_io[i][3], p.dyn_io[i][4], p.dyn_io[i][5]};
         const V3 mc = v3(p.dyn_mc[i][0], p.dyn_mc[i][1], p.dyn_mc[i][2]);
         const V3 n = symmul(Io, om) + cross(mc, vl);
@@ -149,10 +219,9 @@ __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR
             pa_ang = pa_ang + w.p_ang[i];
             pa_lin = pa_lin + w.p_lin[i];
         }
-        const V3 ax = v3(p.axis[i][0], p.axis[i][1], p.axis[i][2]);
-        const V3 Ua = symmul(I, ax), Ul = matTmul(H, ax);
-        const float dinv = 1.f / dot(ax, Ua);
-        const float u = tau[i] - dot(ax, pa_ang);
+        const V3 Ua = pnr_sym_axis<CHAIN>(p, i, I), Ul = pnr_matT_axis<CHAIN>(p, i, H);
+        const float dinv = 1.f / pnr_axis_dot<CHAIN>(p, i, Ua);
+        const float u = tau[i] - pnr_axis_dot<CHAIN>(p, i, pa_ang);
         w.u_ang[i] = Ua; w.u_lin[i] = Ul; w.dinv[i] = dinv; w.u[i] = u;
         if (i > 0) {
             // I^a = I^A - U U^T / d
@@ -170,9 +239,9 @@ __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR
             pa_lin = pa_lin + matTmul(H, w.c_ang[i]) + symmul(M, w.c_lin[i]) + Ul * ud;
             // hand I^a, p^a up to the parent: rotate by R_i, then move the reference point by p_i
             const float s = w.sn[i], c = w.cs[i];
-            const Mat3 Ir = pnr_rot_block(p, i, s, c, sym_to_mat(I));
-            const Mat3 Hr = pnr_rot_block(p, i, s, c, H);
-            const Mat3 Mr = pnr_rot_block(p, i, s, c, sym_to_mat(M));
+            const Mat3 Ir = pnr_rot_block<CHAIN>(p, i, s, c, sym_to_mat(I));
+            const Mat3 Hr = pnr_rot_block<CHAIN>(p, i, s, c, H);
+            const Mat3 Mr = pnr_rot_block<CHAIN>(p, i, s, c, sym_to_mat(M));
             const V3 pi = v3(p.origin_xyz[i][0], p.origin_xyz[i][1], p.origin_xyz[i][2]);
             // A = p x M' (column-wise); H'' = H' + A
             const V3 a0 = cross(pi, v3(Mr.m[0], Mr.m[3], Mr.m[6]));
@@ -201,8 +270,8 @@ __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR
 #pragma unroll
             for (int k = 0; k < 9; ++k) H.m[k] = Hr.m[k] + A.m[k];
             M = mat_to_sym(Mr);
-            const V3 fp = pnr_rot(p, i, s, c, pa_lin);
-            pa_ang = pnr_rot(p, i, s, c, pa_ang) + cross(pi, fp);
+            const V3 fp = pnr_rot<CHAIN>(p, i, s, c, pa_lin);
+            pa_ang = pnr_rot<CHAIN>(p, i, s, c, pa_ang) + cross(pi, fp);
             pa_lin = fp;
         }
     }
@@ -211,12 +280,11 @@ __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR
 #pragma unroll
     for (int i = 0; i < PNR_DOF; ++i) {
         const V3 pi = v3(p.origin_xyz[i][0], p.origin_xyz[i][1], p.origin_xyz[i][2]);
-        const V3 ax = v3(p.axis[i][0], p.axis[i][1], p.axis[i][2]);
         const V3 t = al - cross(pi, aa);
-        aa = pnr_rot_t(p, i, w.sn[i], w.cs[i], aa) + w.c_ang[i];
-        al = pnr_rot_t(p, i, w.sn[i], w.cs[i], t) + w.c_lin[i];
+        aa = pnr_rot_t<CHAIN>(p, i, w.sn[i], w.cs[i], aa) + w.c_ang[i];
+        al = pnr_rot_t<CHAIN>(p, i, w.sn[i], w.cs[i], t) + w.c_lin[i];
         qdd[i] = (w.u[i] - dot(w.u_ang[i], aa) - dot(w.u_lin[i], al)) * w.dinv[i];
-        aa = aa + ax * qdd[i];
+        aa = aa + pnr_axis_scaled<CHAIN>(p, i, qdd[i]);
     }
 }
 
@@ -229,6 +297,7 @@ __device__ __forceinline__ float pnr_control_torque(const PnrParams& p, int i, f
 }
 
 // frame_skip substeps of semi-implicit Euler: qd += qdd dt; q += qd dt; inelastic stops at the joint limits
+template <int CHAIN>
 __device__ __forceinline__ void pnr_dynamic_substeps(const PnrParams& p, float (&q)[PNR_DOF], float (&qd)[PNR_DOF],
                                                      const float (&action)[PNR_DOF]) {
 #pragma unroll 1
@@ -236,7 +305,7 @@ __device__ __forceinline__ void pnr_dynamic_substeps(const PnrParams& p, float (
         float tau[PNR_DOF], qdd[PNR_DOF];
 #pragma unroll
         for (int i = 0; i < PNR_DOF; ++i) tau[i] = pnr_control_torque(p, i, action[i], q[i], qd[i]);
-        pnr_aba(p, q, qd, tau, qdd);
+        pnr_aba<CHAIN>(p, q, qd, tau, qdd);
 #pragma unroll
         for (int i = 0; i < PNR_DOF; ++i) {
             float v = fmaf(qdd[i], p.dyn_dt, qd[i]);

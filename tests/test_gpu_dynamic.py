@@ -124,3 +124,43 @@ def test_kinematic_mode_is_untouched_by_the_dynamic_fields():
         ob, rb, fb = b.step_tensor(act)
         assert torch.equal(oa, ob) and torch.equal(ra, rb)
     a.close(); b.close()
+
+
+def test_generic_chain_kernel_against_the_oracle(tmp_path):
+    """A robot that is NOT the shipped axis pattern (tilted axis, rotated joint origin) takes the generic dynamics
+    and kinematics code paths (runtime axis codes, Rodrigues rotation, origin rotation): same bars."""
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv, SimulationConfig
+    from pioneer_b200.urdf import DEFAULT_URDF
+    text = open(DEFAULT_URDF).read()
+    text = text.replace('<origin xyz="0 0 11"/><axis xyz="0 1 0"/>', '<origin xyz="0 0 11" rpy="0.3 -0.2 0.5"/><axis xyz="0 0.6 0.8"/>')
+    text = text.replace('<origin xyz="11 0 0"/><axis xyz="0 1 0"/>', '<origin xyz="11 0 0"/><axis xyz="0 -1 0"/>')
+    path = tmp_path / "tilted.urdf"
+    path.write_text(text)
+    n = 256
+    kw = dict(gravity=9.81, kp=500.0, kd=100.0, torque_scale=1e4)
+    env = BatchedPioneerEnv(n, urdf_path=str(path), seed=3, simulation_config=SimulationConfig(gravity=9.81),
+                            batch_config=BatchConfig(mode="dynamic", kp=500.0, kd=100.0, torque_scale=1e4,
+                                                     max_episode_steps=0, auto_reset=False))
+    assert not np.allclose(env.chain.origin_rot[2], np.eye(3)) and np.allclose(env.chain.axis[2], (0, 0.6, 0.8))
+    dyn, kin = chain_of(env)
+    cfg = DynConfig(**kw)
+    rng = np.random.default_rng(9)
+    q0 = (rng.uniform(env.r_lo, env.r_hi, size=(n, 6)) * 0.7).astype(np.float32)
+    qd0 = (rng.normal(size=(n, 6)) * 0.3).astype(np.float32)
+    env.set_state(r=q0, v=qd0)
+    act = rng.uniform(env.r_lo, env.r_hi, size=(n, 6)).astype(np.float32)
+    obs, _, _ = env.step_tensor(torch.as_tensor(act).cuda())
+    s = env.state()
+    q1, qd1 = s["r"].cpu().numpy(), s["v"].cpu().numpy()
+    for k in range(0, n, 8):
+        qo, qdo = dynamic_substeps(dyn, cfg, q0[k], qd0[k], act[k], env.r_lo, env.r_hi)
+        assert np.abs(q1[k] - qo).max() <= 2e-5 and np.abs(qd1[k] - qdo).max() <= 2e-4
+        assert np.abs(obs[k, 126:129].cpu().numpy() - fk_pointer(kin, qo)).max() <= 5e-4
+    env.close()
+    # and the kinematic mode on the same robot: pointer position against the float64 FK
+    kenv = BatchedPioneerEnv(n, urdf_path=str(path), seed=3, batch_config=BatchConfig(max_episode_steps=0, auto_reset=False))
+    kenv.reset_world(q0, np.tile(np.array([[20, 0, 4]], np.float32), (n, 1)))
+    o = kenv.step_tensor(torch.zeros((n, 6), device="cuda"))[0].cpu().numpy()
+    for k in range(0, n, 8):
+        assert np.abs(o[k, 126:129] - fk_pointer(kin, q0[k])).max() <= 2e-4
+    kenv.close()
