@@ -353,6 +353,10 @@ def ours_arm(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries exactly ONE JSON line: native libraries (NCCL prints its version banner on fd 1) go to stderr
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world == 1 and args.gpus > 1:
         raise SystemExit("bench.py: for --gpus N > 1 launch with torch.distributed.run, one rank per GPU")
     device = torch.device("cuda", local_rank)
@@ -519,7 +523,7 @@ def ours_arm(args):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": _host_cores(), "kind": "port",
                                     "sample": f"failed: {exc!r}"}
     if rank == 0:
-        print(json.dumps(line), flush=True)
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -143,6 +143,19 @@ __device__ __forceinline__ void pnr_bulk_wait_read() {      // returns once at m
 }
 __device__ __forceinline__ void pnr_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
+// named CTA barriers (ids 1..15; id 0 is __syncthreads): producer warps ARRIVE without waiting, the consumer SYNCs.
+// `count` = all participating threads (arrivers + waiters).  Both order prior shared / global accesses of the CTA.
+// The ids are immediates: with register ids ptxas reserves all 16 barriers per CTA, which caps the SM at 4 CTAs.
+template <int ID, int COUNT>
+__device__ __forceinline__ void pnr_bar_sync() { asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+template <int ID, int COUNT>
+__device__ __forceinline__ void pnr_bar_arrive() { asm volatile("bar.arrive %0, %1;" ::"n"(ID), "n"(COUNT) : "memory"); }
+// barrier pair selected by the (CTA-uniform) tile buffer index
+template <int ID, int COUNT>
+__device__ __forceinline__ void pnr_bar_sync2(int buf) { if (buf) pnr_bar_sync<ID + 1, COUNT>(); else pnr_bar_sync<ID, COUNT>(); }
+template <int ID, int COUNT>
+__device__ __forceinline__ void pnr_bar_arrive2(int buf) { if (buf) pnr_bar_arrive<ID + 1, COUNT>(); else pnr_bar_arrive<ID, COUNT>(); }
+
 // orderable unsigned encoding of a float (for atomicMax/atomicMin on episode returns)
 __device__ __host__ __forceinline__ uint32_t pnr_float_to_ordered(float f) {
 #ifdef __CUDA_ARCH__

@@ -2,6 +2,7 @@
 // sm_100a; launched from pnr_api.cu.
 #include "pnr_kernels.cuh"
 #include "pnr_launch.h"
+#include <cstdlib>
 
 // ---------------------------------------------------------------------------------------------
 // K1: the fused env step.  One CTA of 4 warps owns a tile of 32 envs (lane = env); the work of ONE env is
@@ -13,8 +14,12 @@
 //                                from the tile), reward / done / TimeLimit (:151-165), episode statistics,
 //                                auto-reset (reset_world, :76-105), observation tail, planes X0, X1,
 //                                reward / done outputs, and the TMA bulk store of the finished tile
-// Three CTA barriers per tile: B0 tile free (previous bulk store has read it), B1 joint angles and their
-// sin/cos are in the tile, B2 tile complete.  Each warp prefetches its own planes of the CTA's next tile.
+// The two roles run as a producer / consumer pipeline over TWO tile buffers, coupled only by named barriers:
+//   HEAD[b]  joint warps arrive once r, cos r, sin r of their joints are in buffer b; the task warp waits on it
+//   DONE[b]  joint warps arrive once all their columns and planes are written; the task warp waits, then stores
+//   FREE[b]  the task warp arrives once the bulk store of buffer b has been read; joint warps wait before reuse
+// so the joint warps of a CTA work on tile i+1 while its task warp finishes tile i (before: 49 % of stall samples
+// were joint warps parked at a CTA-wide barrier).  Each warp prefetches its own planes of the CTA's next tile.
 // Grid = min(tiles, resident CTAs of the whole GPU); grid-stride over tiles.
 // ---------------------------------------------------------------------------------------------
 // In-kernel auto-reset of ONE env by the task warp after the tile is complete: new joint angles and target from
@@ -115,8 +120,8 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
     };
     issue_loads(t_idx);
     PNR_MARK(2);
-    int stores_in_flight = 0;                                 // bulk stores committed by the task warp's lane 0
     int buf = 0;
+    int64_t iter = 0;                                         // tiles this CTA has started
 
     for (; t_idx < n_tiles; t_idx += stride) {
         const int64_t env_raw = t_idx * PNR_TILE_ENVS + lane;
@@ -135,19 +140,17 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             pnr_integrate_joint<ARITH>(p, vmax1, rlo1, rhi1, c2.y, c4.w, c4.y, v1[1], r1[1]);
             pnr_sincos_fast(r1[0], sn[0], cs[0]);             // r is inside the joint limits: fast path
             pnr_sincos_fast(r1[1], sn[1], cs[1]);
-        } else if (lane == 0 && stores_in_flight >= PNR_STEP_BUFS) {
-            // the copy engine must have finished READING this buffer (the store issued PNR_STEP_BUFS tiles ago)
-            if (PNR_STEP_BUFS == 1) pnr_bulk_wait_read<0>(); else pnr_bulk_wait_read<PNR_STEP_BUFS - 1>();
-        }
-        PNR_MARK(3);
-        __syncthreads();                                      // B0: the tile may be written
-        PNR_MARK(4);
-
-        if (part < 3) {
+            PNR_MARK(3);
+            if (iter >= PNR_STEP_BUFS) pnr_bar_sync2<PNR_BAR_FREE, PNR_STEP_THREADS>(buf);   // buffer reusable
+            PNR_MARK(4);
             pnr_pack_joint_head(rowj, r1[0], sn[0], cs[0]);
             pnr_pack_joint_head(rowj + 1, r1[1], sn[1], cs[1]);
+            pnr_bar_arrive2<PNR_BAR_HEAD, PNR_STEP_THREADS>(buf);
+        } else {
+            PNR_MARK(3);
+            pnr_bar_sync2<PNR_BAR_HEAD, PNR_STEP_THREADS>(buf);   // r, cos r, sin r of all six joints are in the tile
+            PNR_MARK(4);
         }
-        __syncthreads();                                      // B1: r, cos r, sin r of all six joints are in the tile
         PNR_MARK(5);
 
         bool do_reset = false;
@@ -215,38 +218,44 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         }
         PNR_MARK(6);
         pnr_fence_async_smem();                               // generic-proxy tile writes -> async proxy
-        __syncthreads();                                      // B2: tile complete, joint planes stored
+        const bool bulk = pnr_tile_is_bulk(rows_valid);       // CTA-uniform
+        if (!bulk) __syncthreads();                           // ragged last tile of the grid: everybody streams it out
+        else if (part < 3) pnr_bar_arrive2<PNR_BAR_DONE, PNR_STEP_THREADS>(buf);
+        else pnr_bar_sync2<PNR_BAR_DONE, PNR_STEP_THREADS>(buf);   // tile complete, joint planes stored
         PNR_MARK(7);
 
-        const bool bulk = pnr_tile_is_bulk(rows_valid);       // CTA-uniform
         if (part == 3) {
             if (__any_sync(PNR_FULL_MASK, do_reset)) {         // rare: auto-reset (reset_world, :76-105)
                 if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, tick, row);
                 pnr_fence_async_smem();
                 __syncwarp();
             }
-            if (bulk && lane == 0) {
-                pnr_bulk_store(obs + t_idx * (int64_t)PNR_TILE_FLOATS, tile,
-                               (uint32_t)(rows_valid * PNR_OBS_DIM * sizeof(float)));
-                pnr_bulk_commit();
+            if (bulk) {
+                if (lane == 0) {
+                    pnr_bulk_store(obs + t_idx * (int64_t)PNR_TILE_FLOATS, tile,
+                                   (uint32_t)(rows_valid * PNR_OBS_DIM * sizeof(float)));
+                    pnr_bulk_commit();
+                    // every store but the one just committed has finished READING its buffer: the previous tile's
+                    // buffer is free again (only signalled if a tile that will reuse it exists)
+                    if (iter >= 1) pnr_bulk_wait_read<1>();
+                }
+                __syncwarp();
+                if (iter >= 1 && t_idx + stride < n_tiles) pnr_bar_arrive2<PNR_BAR_FREE, PNR_STEP_THREADS>(buf ^ 1);
             }
         }
         PNR_MARK(8);
         PNR_TRACE_NEXT();
-        if (bulk) {
-            ++stores_in_flight;
-        } else {                                              // ragged last tile: all 128 threads stream it out
+        if (!bulk) {                                          // ragged last tile: all 128 threads stream it out
             __syncthreads();
             pnr_emit_tile_manual(tile, obs + t_idx * (int64_t)PNR_TILE_FLOATS, rows_valid, threadIdx.x, PNR_STEP_THREADS);
         }
-        if (PNR_STEP_BUFS > 1) {                              // next tile goes into the other buffer
-            buf = (buf + 1) % PNR_STEP_BUFS;
-            tile = tiles + buf * PNR_TILE_FLOATS;
-            row = tile + lane * PNR_OBS_DIM;
-            rowj = row + j0;
-        }
+        buf ^= 1;                                             // next tile goes into the other buffer
+        ++iter;
+        tile = tiles + buf * PNR_TILE_FLOATS;
+        row = tile + lane * PNR_OBS_DIM;
+        rowj = row + j0;
     }
-    if (part == 3 && lane == 0 && stores_in_flight) pnr_bulk_wait_read<0>();   // smem must outlive the copy engine's reads
+    if (part == 3 && lane == 0) pnr_bulk_wait_read<0>();      // smem must outlive the copy engine's reads
 #ifdef PNR_TRACE
     trace_iter = 0;
 #endif
@@ -389,7 +398,15 @@ cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_m
         cudaError_t e = pnr_prepare(k, PNR_STEP_SMEM, &resident);
         if (e != cudaSuccess) return e;
     }
-    const int64_t grid = pnr_grid_for(p.n_envs, PNR_TILE_ENVS, resident);
+    // Resident CTAs per SM, measured on B200 (profiles/r01_v4_cta_sweep.md): long grid-stride runs stream best with
+    // 4 CTAs per SM (87 % of the HBM copy peak at 2M envs against 80 % with 6), short ones need all 6 to fill the GPU.
+    int dev_sms = 0;
+    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
+    const int64_t n_tiles = (p.n_envs + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
+    int per_sm = n_tiles >= 16384 ? 4 : (n_tiles >= 8192 ? 5 : 6);
+    if (const char* e = getenv("PNR_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // developer knob
+    int cap = per_sm * dev_sms < resident ? per_sm * dev_sms : resident;
+    const int64_t grid = pnr_grid_for(p.n_envs, PNR_TILE_ENVS, cap);
     k<<<(unsigned)grid, PNR_STEP_THREADS, PNR_STEP_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick);
     return cudaGetLastError();
 }

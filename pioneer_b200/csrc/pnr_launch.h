@@ -8,9 +8,10 @@
 #ifndef PNR_STEP_MIN_CTAS
 #define PNR_STEP_MIN_CTAS 6                                                  // 24 warps / SM, <= 85 registers: no spills (8 CTAs spill)
 #endif
-#ifndef PNR_STEP_BUFS
-#define PNR_STEP_BUFS 1                                                      // observation tiles per CTA (2 = double buffering: measured no gain)
-#endif
+#define PNR_STEP_BUFS 2                                                      // observation tile buffers per CTA (producer / consumer pipeline)
+#define PNR_BAR_HEAD 1                                                       // named barrier ids: HEAD[2], DONE[2], FREE[2]
+#define PNR_BAR_DONE 3
+#define PNR_BAR_FREE 5
 #define PNR_STEP_SMEM (PNR_STEP_BUFS * 32 * PNR_OBS_DIM * sizeof(float))     // step kernel: 17,536 B per tile buffer
 #define PNR_RO_SMEM (PNR_STEP_WARPS * 32 * PNR_OBS_DIM * sizeof(float))      // reset/observe: one tile per warp
 #define PNR_MAX_DEVICES 16
