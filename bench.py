@@ -516,6 +516,31 @@ def ours_arm(args):
         e.close()
         del a, o, r, f
 
+    # ---- N2: fused observation normaliser (one pass: push statistics + normalise in place) -------------------------
+    if world == 1 and not args.no_sweep:
+        from pioneer_b200.obs_filter import MeanStdObsFilter
+        filt = []
+        for m in (args.envs_per_gpu, 1048576):
+            e = BatchedPioneerEnv(m, device=device, seed=0)
+            flt_ = MeanStdObsFilter(e)
+            ring = torch.randn((max(2, min(8, (1 << 30) // (m * OBS_DIM * 4))), m, OBS_DIM), device=device)
+            for k in range(3):
+                flt_(ring[k % ring.shape[0]])
+            evs = []
+            for k in range(50):
+                flush()
+                a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a_.record(); flt_(ring[k % ring.shape[0]]); b_.record()
+                evs.append((a_, b_))
+            torch.cuda.synchronize()
+            ms = sum(a_.elapsed_time(b_) for a_, b_ in evs) / len(evs)
+            gbs = 2 * OBS_DIM * 4 * m / (ms / 1e3) / 1e9
+            filt.append({"rows": m, "ms": ms, "rows_per_sec": m / (ms / 1e3), "achieved_gbs": gbs, "frac": gbs / peak,
+                         "bytes_per_row": 2 * OBS_DIM * 4})
+            e.close()
+            del ring
+        line["obs_filter"] = filt
+
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             line["cpu_baseline"] = cpu_baseline_subprocess()

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PNR_ABI_VERSION 1
+#define PNR_ABI_VERSION 2
 #define PNR_DOF 6                 /* revolute joints of the Pioneer arm (pioneer_knm_env.py:213-215) */
 #define PNR_OBS_DIM 137           /* 21*dof + 11 (pioneer_knm_env.py:194-211)                          */
 #define PNR_MAX_CAPSULES 8
@@ -170,6 +170,27 @@ int pnr_stats(pnr_handle* h, double* out, int clear, void* stream);
 /* Same 8 numbers written to a caller-owned DEVICE double[8] without synchronising, for an NCCL
  * all-reduce on the same stream (SUM over {0,1,2,3,6,7}, MAX over {4, -5}). */
 int pnr_stats_device(pnr_handle* h, double* out_device, int clear, void* stream);
+
+/* ---- observation normaliser: the 'MeanStdFilter' observation_filter of the reference launcher
+ * (pioneer/launch/pioneer_knm_train.py:66; the filter itself is RLlib's, third party) --------------------------------
+ * pnr_filter_apply: ONE pass over obs_in DEVICE float[n_rows,137]: if `update`, the rows enter the statistics
+ * accumulated since the last pnr_filter_sync; if `normalize`, obs_out = clip((obs_in - mean) / (std + 1e-8), +-clip)
+ * with the mean / std of the last synchronisation (obs_out may alias obs_in; with normalize = 0 and obs_out == obs_in
+ * nothing is written).  Defaults: clip = 10, demean and destd on (RLlib's MeanStdFilter). */
+#define PNR_FILTER_DELTA_LEN (1 + 2 * PNR_OBS_DIM)   /* rows, sum(x - mean)[137], sum((x - mean)^2)[137] */
+int pnr_filter_configure(pnr_handle* h, double clip, int demean, int destd);
+int pnr_filter_apply(pnr_handle* h, const float* obs_in, float* obs_out, int64_t n_rows, int update, int normalize,
+                     void* stream);
+/* Copy the statistics accumulated since the last sync to a caller-owned DEVICE double[PNR_FILTER_DELTA_LEN]
+ * (not synchronised): sum it over the ranks with one NCCL all-reduce, then hand it to pnr_filter_sync on every rank. */
+int pnr_filter_delta_device(pnr_handle* h, double* out_device, void* stream);
+/* Merge a delta (HOST double[PNR_FILTER_DELTA_LEN], or NULL = this handle's own) into the running statistics, refresh the
+ * mean / std used by pnr_filter_apply, clear the accumulator.  Synchronises `stream`. */
+int pnr_filter_sync(pnr_handle* h, const double* merged_delta_host, void* stream);
+/* Running statistics: HOST count[1], mean[137], var[137] (var = M2 / (count - 1), or mean^2 while count < 2, as
+ * RLlib's RunningStat reports it). */
+int pnr_filter_get(pnr_handle* h, double* count, double* mean, double* var);
+int pnr_filter_set(pnr_handle* h, double count, const double* mean, const double* var, void* stream);
 
 /* Number of kernel launches issued by this handle so far (bench.py's gpu_launches). */
 int64_t pnr_launch_count(const pnr_handle* h);

@@ -11,12 +11,13 @@ from typing import Optional
 
 from . import build as _build
 
-PNR_ABI_VERSION = 1
+PNR_ABI_VERSION = 2
 PNR_DOF = 6
 PNR_OBS_DIM = 137
 PNR_MAX_CAPSULES = 8
 PNR_MAX_OBSTACLES = 4
 PNR_STATS_LEN = 8
+PNR_FILTER_DELTA_LEN = 1 + 2 * PNR_OBS_DIM
 
 PNR_OK = 0
 PNR_ARITH_F32, PNR_ARITH_LEGACY64 = 0, 1
@@ -84,6 +85,12 @@ SIGNATURES = {
     "pnr_set_state": (C.c_int, [_H, _P, _P, _P, _P, _P, _P, _P, _S]),
     "pnr_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.c_int, _S]),
     "pnr_stats_device": (C.c_int, [_H, _P, C.c_int, _S]),
+    "pnr_filter_configure": (C.c_int, [_H, C.c_double, C.c_int, C.c_int]),
+    "pnr_filter_apply": (C.c_int, [_H, _P, _P, C.c_int64, C.c_int, C.c_int, _S]),
+    "pnr_filter_delta_device": (C.c_int, [_H, _P, _S]),
+    "pnr_filter_sync": (C.c_int, [_H, C.POINTER(C.c_double), _S]),
+    "pnr_filter_get": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "pnr_filter_set": (C.c_int, [_H, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), _S]),
     "pnr_launch_count": (C.c_int64, [_H]),
 }
 

@@ -36,6 +36,13 @@ struct pnr_handle {
     double env_steps = 0.0;
     int64_t launches = 0;
     float a_max[PNR_DOF];
+    // observation normaliser (pnr_filter_*): device accumulator, applied statistics, host-side running statistics
+    double* filt_delta = nullptr;        // device double[PNR_FILTER_DELTA_LEN]
+    float* filt_applied = nullptr;       // device float[2 * PNR_OBS_DIM]: mean, 1 / (std + 1e-8)
+    double filt_count = 0.0;
+    double filt_mean[PNR_OBS_DIM] = {}, filt_m2[PNR_OBS_DIM] = {};
+    double filt_clip = 10.0;
+    int filt_demean = 1, filt_destd = 1;
     // host-buffer path (pnr_step_host)
     float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
     uint8_t* h_done = nullptr;
@@ -250,6 +257,7 @@ extern "C" void pnr_destroy(pnr_handle* h) {
     PnrDeviceGuard guard(h->device);
     if (h->host_stream) { cudaStreamSynchronize(h->host_stream); cudaStreamDestroy(h->host_stream); }
     cudaFree(h->state); cudaFree(h->stats); cudaFree(h->stats_out);
+    cudaFree(h->filt_delta); cudaFree(h->filt_applied);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_done);
     if (h->stats_host) cudaFreeHost(h->stats_host);
     delete h;
@@ -376,4 +384,119 @@ extern "C" int pnr_stats(pnr_handle* h, double* out, int clear, void* stream) {
     PNR_CUDA(cudaStreamSynchronize((cudaStream_t)stream));
     std::memcpy(out, h->stats_host, sizeof(double) * PNR_STATS_LEN);
     return PNR_OK;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// observation normaliser
+// ---------------------------------------------------------------------------------------------------------------
+static int pnr_filter_upload_applied(pnr_handle* h, cudaStream_t stream) {
+    float host[2 * PNR_OBS_DIM];
+    for (int c = 0; c < PNR_OBS_DIM; ++c) {
+        // RunningStat.var: S / (n - 1) if n > 1 else mean^2 (RLlib, restated); std = sqrt(var)
+        const double var = h->filt_count > 1.0 ? h->filt_m2[c] / (h->filt_count - 1.0) : h->filt_mean[c] * h->filt_mean[c];
+        host[c] = h->filt_demean ? (float)h->filt_mean[c] : 0.f;
+        host[PNR_OBS_DIM + c] = h->filt_destd ? (float)(1.0 / (std::sqrt(var) + 1e-8)) : 1.f;
+    }
+    PNR_CUDA(cudaMemcpyAsync(h->filt_applied, host, sizeof(host), cudaMemcpyHostToDevice, stream));
+    PNR_CUDA(cudaStreamSynchronize(stream));                    // `host` is a stack buffer
+    return PNR_OK;
+}
+
+static int pnr_filter_ensure(pnr_handle* h, cudaStream_t stream) {
+    if (h->filt_delta) return PNR_OK;
+    PNR_CUDA(cudaMalloc(&h->filt_delta, sizeof(double) * PNR_FILTER_DELTA_LEN));
+    PNR_CUDA(cudaMalloc(&h->filt_applied, sizeof(float) * 2 * PNR_OBS_DIM));
+    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_DELTA_LEN, stream));
+    return pnr_filter_upload_applied(h, stream);
+}
+
+extern "C" int pnr_filter_configure(pnr_handle* h, double clip, int demean, int destd) {
+    if (!h || !(clip > 0.0)) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_configure: bad argument");
+    PnrDeviceGuard guard(h->device);
+    h->filt_clip = clip; h->filt_demean = demean ? 1 : 0; h->filt_destd = destd ? 1 : 0;
+    int rc = pnr_filter_ensure(h, nullptr);
+    if (rc != PNR_OK) return rc;
+    // the accumulator is relative to the applied mean: rows pushed under the old setting are dropped
+    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_DELTA_LEN, nullptr));
+    return pnr_filter_upload_applied(h, nullptr);
+}
+
+extern "C" int pnr_filter_apply(pnr_handle* h, const float* obs_in, float* obs_out, int64_t n_rows, int update,
+                                int normalize, void* stream) {
+    if (!h || !obs_in || !obs_out || n_rows < 0) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_apply: bad argument");
+    if ((reinterpret_cast<uintptr_t>(obs_in) & 15) || (reinterpret_cast<uintptr_t>(obs_out) & 15))
+        return pnr_fail(PNR_ERR_INVALID, "pnr_filter_apply: observation buffers must be 16-byte aligned");
+    PnrDeviceGuard guard(h->device);
+    int rc = pnr_filter_ensure(h, (cudaStream_t)stream);
+    if (rc != PNR_OK) return rc;
+    PNR_CUDA(pnr_launch_filter(h->device, obs_in, obs_out, n_rows, h->filt_applied, h->filt_delta, (float)h->filt_clip,
+                               update, normalize, (cudaStream_t)stream));
+    h->launches += (n_rows > 0);
+    return PNR_OK;
+}
+
+extern "C" int pnr_filter_delta_device(pnr_handle* h, double* out_device, void* stream) {
+    if (!h || !out_device) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_delta_device: null argument");
+    PnrDeviceGuard guard(h->device);
+    int rc = pnr_filter_ensure(h, (cudaStream_t)stream);
+    if (rc != PNR_OK) return rc;
+    PNR_CUDA(cudaMemcpyAsync(out_device, h->filt_delta, sizeof(double) * PNR_FILTER_DELTA_LEN, cudaMemcpyDeviceToDevice,
+                             (cudaStream_t)stream));
+    return PNR_OK;
+}
+
+extern "C" int pnr_filter_sync(pnr_handle* h, const double* merged, void* stream) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_sync: null handle");
+    PnrDeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = pnr_filter_ensure(h, s);
+    if (rc != PNR_OK) return rc;
+    double d[PNR_FILTER_DELTA_LEN];
+    if (merged) {
+        std::memcpy(d, merged, sizeof(d));
+        PNR_CUDA(cudaStreamSynchronize(s));
+    } else {
+        PNR_CUDA(cudaMemcpyAsync(d, h->filt_delta, sizeof(d), cudaMemcpyDeviceToHost, s));
+        PNR_CUDA(cudaStreamSynchronize(s));
+    }
+    const double nb = d[0];
+    if (nb > 0.0) {
+        // the batch statistics are relative to the APPLIED mean (what the kernel subtracted); Chan et al. merge
+        const double na = h->filt_count, n = na + nb;
+        for (int c = 0; c < PNR_OBS_DIM; ++c) {
+            const double applied_mean = h->filt_demean ? (double)(float)h->filt_mean[c] : 0.0;
+            const double mean_b = applied_mean + d[1 + c] / nb;
+            const double m2_b = d[1 + PNR_OBS_DIM + c] - d[1 + c] * d[1 + c] / nb;
+            const double delta = mean_b - h->filt_mean[c];
+            h->filt_m2[c] = h->filt_m2[c] + (m2_b > 0.0 ? m2_b : 0.0) + delta * delta * na * nb / n;
+            h->filt_mean[c] = h->filt_mean[c] + delta * nb / n;
+        }
+        h->filt_count = n;
+    }
+    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_DELTA_LEN, s));
+    return pnr_filter_upload_applied(h, s);
+}
+
+extern "C" int pnr_filter_get(pnr_handle* h, double* count, double* mean, double* var) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_get: null handle");
+    if (count) *count = h->filt_count;
+    for (int c = 0; c < PNR_OBS_DIM; ++c) {
+        if (mean) mean[c] = h->filt_mean[c];
+        if (var) var[c] = h->filt_count > 1.0 ? h->filt_m2[c] / (h->filt_count - 1.0) : h->filt_mean[c] * h->filt_mean[c];
+    }
+    return PNR_OK;
+}
+
+extern "C" int pnr_filter_set(pnr_handle* h, double count, const double* mean, const double* var, void* stream) {
+    if (!h || !mean || !var || count < 0.0) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_set: bad argument");
+    PnrDeviceGuard guard(h->device);
+    int rc = pnr_filter_ensure(h, (cudaStream_t)stream);
+    if (rc != PNR_OK) return rc;
+    h->filt_count = count;
+    for (int c = 0; c < PNR_OBS_DIM; ++c) {
+        h->filt_mean[c] = mean[c];
+        h->filt_m2[c] = count > 1.0 ? var[c] * (count - 1.0) : 0.0;
+    }
+    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_DELTA_LEN, (cudaStream_t)stream));
+    return pnr_filter_upload_applied(h, (cudaStream_t)stream);
 }

@@ -1,0 +1,130 @@
+// N2: fused observation normaliser (the MeanStdFilter the reference launcher configures for its rollout workers,
+// pioneer/launch/pioneer_knm_train.py:66 'observation_filter': 'MeanStdFilter').  ONE streaming pass over the
+// observation batch does what the host-side filter does in three (push statistics, demean, scale): a CTA pulls a
+// tile of 32 rows into shared memory with a TMA bulk load, every thread owns one of the 137 columns -- accumulates
+// sum and sum of squares of (x - applied_mean) over the tile's rows, rewrites the column as
+// clip((x - mean) * inv_std) -- and the tile leaves with a TMA bulk store.  Bound: HBM, 548 B read + 548 B written
+// per row.  Statistics of the rows seen since the last synchronisation accumulate in float64 on the device
+// (one atomicAdd per column per CTA); pnr_filter_sync merges them into the running mean / M2 (Chan et al.
+// parallel update) and refreshes the applied mean / inverse std, so between synchronisations every rank
+// normalises with the SAME statistics (what RLlib's synchronised filters converge to once per iteration).
+#include <cuda_runtime.h>
+#include <cstdint>
+#include "pnr_device.cuh"
+#include "pnr_launch.h"
+
+#define PNR_FILTER_THREADS 160                      // >= PNR_OBS_DIM columns, 5 warps
+#define PNR_FILTER_ROWS 32
+#define PNR_FILTER_TILE_BYTES (PNR_FILTER_ROWS * PNR_OBS_DIM * 4)
+
+__device__ __forceinline__ void pnr_mbar_init(uint64_t* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(pnr_smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void pnr_mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(pnr_smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void pnr_bulk_load(void* sdst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(pnr_smem_u32(sdst)), "l"(gsrc), "r"(bytes), "r"(pnr_smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void pnr_mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@!p bra WAIT_LOOP;\n"
+        "}\n" ::"r"(pnr_smem_u32(bar)), "r"(parity) : "memory");
+}
+
+// applied: [mean[137], inv_std[137]] float; delta: [count, sum_d[137], sumsq_d[137]] double
+__global__ void __launch_bounds__(PNR_FILTER_THREADS)
+pnr_filter_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t n_rows,
+                  const float* __restrict__ applied, double* __restrict__ delta, float clip, int update,
+                  int normalize) {
+    extern __shared__ __align__(128) float tile[];
+    __shared__ __align__(8) uint64_t bar;
+    const int tid = threadIdx.x;
+    const bool col_ok = tid < PNR_OBS_DIM;
+    const float mean = col_ok ? applied[tid] : 0.f;
+    const float inv_std = col_ok ? applied[PNR_OBS_DIM + tid] : 0.f;
+    if (tid == 0) pnr_mbar_init(&bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    __syncthreads();
+    const int64_t n_tiles = (n_rows + PNR_FILTER_ROWS - 1) / PNR_FILTER_ROWS;
+    double acc_s = 0.0, acc_q = 0.0;
+    uint32_t phase = 0;
+    for (int64_t t = blockIdx.x; t < n_tiles; t += gridDim.x) {
+        const int64_t row0 = t * PNR_FILTER_ROWS;
+        const int rows = (int)((n_rows - row0) < PNR_FILTER_ROWS ? (n_rows - row0) : PNR_FILTER_ROWS);
+        const float* src = in + row0 * PNR_OBS_DIM;
+        float* dst = out + row0 * PNR_OBS_DIM;
+        const bool bulk = (rows & 3) == 0;                      // byte count a multiple of 16
+        if (bulk) {
+            if (tid == 0) {
+                pnr_mbar_expect_tx(&bar, (uint32_t)(rows * PNR_OBS_DIM * 4));
+                pnr_bulk_load(tile, src, (uint32_t)(rows * PNR_OBS_DIM * 4), &bar);
+            }
+            pnr_mbar_wait(&bar, phase);
+            phase ^= 1;
+        } else {
+            for (int i = tid; i < rows * PNR_OBS_DIM; i += PNR_FILTER_THREADS) tile[i] = src[i];
+            __syncthreads();
+        }
+        if (col_ok) {
+            // float64 accumulation (B200 has the FP64 rate for 2 DFMA per element of an HBM-bound stream): before the
+            // first synchronisation the applied mean is 0, and sum(x^2) - sum(x)^2 / n of a constant column must
+            // cancel to ~0, which float32 partial sums do not deliver
+#pragma unroll 8
+            for (int r = 0; r < rows; ++r) {
+                const float x = tile[r * PNR_OBS_DIM + tid];
+                const float d = x - mean;
+                const double dd = (double)d;
+                acc_s += dd;
+                acc_q = fma(dd, dd, acc_q);
+                if (normalize) tile[r * PNR_OBS_DIM + tid] = fminf(fmaxf(d * inv_std, -clip), clip);
+            }
+        }
+        if (normalize || out != in) {
+            pnr_fence_async_smem();
+            __syncthreads();
+            if (bulk) {
+                if (tid == 0) {
+                    pnr_bulk_store(dst, tile, (uint32_t)(rows * PNR_OBS_DIM * 4));
+                    pnr_bulk_commit();
+                    pnr_bulk_wait_read<0>();
+                }
+            } else {
+                for (int i = tid; i < rows * PNR_OBS_DIM; i += PNR_FILTER_THREADS) dst[i] = tile[i];
+            }
+        }
+        __syncthreads();                                        // the tile may be overwritten
+    }
+    if (update && col_ok) {
+        atomicAdd(&delta[1 + tid], acc_s);
+        atomicAdd(&delta[1 + PNR_OBS_DIM + tid], acc_q);
+    }
+    if (update && blockIdx.x == 0 && tid == 0) atomicAdd(&delta[0], (double)n_rows);
+}
+
+cudaError_t pnr_launch_filter(int device, const float* in, float* out, int64_t n_rows, const float* applied,
+                              double* delta, float clip, int update, int normalize, cudaStream_t stream) {
+    static int resident[PNR_MAX_DEVICES] = {};
+    int& res = resident[device % PNR_MAX_DEVICES];
+    if (res == 0) {
+        cudaError_t e = cudaFuncSetAttribute((const void*)pnr_filter_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             PNR_FILTER_TILE_BYTES);
+        if (e != cudaSuccess) return e;
+        int sms = 0, per_sm = 0;
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (const void*)pnr_filter_kernel, PNR_FILTER_THREADS,
+                                                      PNR_FILTER_TILE_BYTES);
+        res = sms * (per_sm < 1 ? 1 : per_sm);
+    }
+    if (n_rows <= 0) return cudaSuccess;
+    int64_t grid = (n_rows + PNR_FILTER_ROWS - 1) / PNR_FILTER_ROWS;
+    if (grid > res) grid = res;
+    pnr_filter_kernel<<<(unsigned)grid, PNR_FILTER_THREADS, PNR_FILTER_TILE_BYTES, stream>>>(in, out, n_rows, applied, delta,
+                                                                                            clip, update, normalize);
+    return cudaGetLastError();
+}

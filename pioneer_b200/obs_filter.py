@@ -1,0 +1,91 @@
+"""Observation normaliser for the rollout loop: the ``'observation_filter': 'MeanStdFilter'`` the reference launcher
+configures (pioneer/launch/pioneer_knm_train.py:66; the filter itself is RLlib's).  One streaming CUDA pass per batch
+(pnr_filter_apply) pushes the rows into the running statistics and rewrites them as
+``clip((x - mean) / (std + 1e-8), +-clip)``; ``sync()`` merges what was pushed since the last call -- summed over the
+ranks with one all-reduce when torch.distributed is initialised -- into the running mean / variance, which is the
+once-per-iteration filter synchronisation RLlib performs between its rollout workers and the trainer.
+
+Between two ``sync()`` calls every rank normalises with the same statistics (RLlib workers keep updating their local
+copy in between; the difference vanishes once the statistics have converged)."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+from . import _cabi
+from .batched_env import OBS_DIM, BatchedPioneerEnv
+
+
+class MeanStdObsFilter:
+    def __init__(self, env: BatchedPioneerEnv, clip: float = 10.0, demean: bool = True, destd: bool = True):
+        self.env = env
+        self._lib, self._h = env._lib, env._h
+        self.clip, self.demean, self.destd = float(clip), bool(demean), bool(destd)
+        with torch.cuda.device(env.device):
+            _cabi.check(self._lib.pnr_filter_configure(self._h, self.clip, int(demean), int(destd)), "pnr_filter_configure")
+
+    def __call__(self, obs: torch.Tensor, update: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """Normalise ``obs`` [n, 137] (float32, on the env's device); ``out`` defaults to in-place."""
+        out = obs if out is None else out
+        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape[-1] == OBS_DIM and obs.device == self.env.device
+        assert out.dtype == torch.float32 and out.is_contiguous() and out.shape == obs.shape
+        with torch.cuda.device(self.env.device):
+            _cabi.check(self._lib.pnr_filter_apply(self._h, obs.data_ptr(), out.data_ptr(), obs.numel() // OBS_DIM,
+                                                   int(update), 1, self.env._stream()), "pnr_filter_apply")
+        return out
+
+    def push(self, obs: torch.Tensor) -> None:
+        """Statistics only; ``obs`` is left untouched."""
+        assert obs.dtype == torch.float32 and obs.is_contiguous() and obs.shape[-1] == OBS_DIM
+        with torch.cuda.device(self.env.device):
+            _cabi.check(self._lib.pnr_filter_apply(self._h, obs.data_ptr(), obs.data_ptr(), obs.numel() // OBS_DIM,
+                                                   1, 0, self.env._stream()), "pnr_filter_apply")
+
+    def sync(self, group: Optional[dist.ProcessGroup] = None) -> None:
+        """Merge the rows pushed since the last sync (of ALL ranks) into the running statistics."""
+        with torch.cuda.device(self.env.device):
+            if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+                delta = torch.empty(_cabi.PNR_FILTER_DELTA_LEN, dtype=torch.float64, device=self.env.device)
+                _cabi.check(self._lib.pnr_filter_delta_device(self._h, delta.data_ptr(), self.env._stream()),
+                            "pnr_filter_delta_device")
+                dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
+                host = delta.cpu().numpy()
+                _cabi.check(self._lib.pnr_filter_sync(self._h, host.ctypes.data_as(C.POINTER(C.c_double)),
+                                                      self.env._stream()), "pnr_filter_sync")
+            else:
+                _cabi.check(self._lib.pnr_filter_sync(self._h, None, self.env._stream()), "pnr_filter_sync")
+
+    def _get(self):
+        n = C.c_double()
+        mean = (C.c_double * OBS_DIM)()
+        var = (C.c_double * OBS_DIM)()
+        _cabi.check(self._lib.pnr_filter_get(self._h, C.byref(n), mean, var), "pnr_filter_get")
+        return n.value, np.array(mean), np.array(var)
+
+    @property
+    def n(self) -> float:
+        return self._get()[0]
+
+    @property
+    def mean(self) -> np.ndarray:
+        return self._get()[1]
+
+    @property
+    def var(self) -> np.ndarray:
+        return self._get()[2]
+
+    @property
+    def std(self) -> np.ndarray:
+        return np.sqrt(self.var)
+
+    def set_stats(self, count: float, mean, var) -> None:
+        m = np.ascontiguousarray(mean, dtype=np.float64)
+        v = np.ascontiguousarray(var, dtype=np.float64)
+        assert m.shape == (OBS_DIM,) and v.shape == (OBS_DIM,)
+        with torch.cuda.device(self.env.device):
+            _cabi.check(self._lib.pnr_filter_set(self._h, float(count), m.ctypes.data_as(C.POINTER(C.c_double)),
+                                                 v.ctypes.data_as(C.POINTER(C.c_double)), self.env._stream()), "pnr_filter_set")
