@@ -172,7 +172,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "substeps_per_sec": value * FRAME_SKIP, "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(_finite(line)), flush=True)
 
 
 def cpu_baseline_subprocess(seconds_budget: float = 20.0):
@@ -548,10 +548,21 @@ def ours_arm(args):
             line["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": _host_cores(), "kind": "port",
                                     "sample": f"failed: {exc!r}"}
     if rank == 0:
-        os.write(json_fd, (json.dumps(line) + "\n").encode())
+        os.write(json_fd, (json.dumps(_finite(line)) + "\n").encode())
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def _finite(x):
+    """Strict JSON: NaN / inf become null."""
+    if isinstance(x, float):
+        return x if math.isfinite(x) else None
+    if isinstance(x, dict):
+        return {k: _finite(v) for k, v in x.items()}
+    if isinstance(x, (list, tuple)):
+        return [_finite(v) for v in x]
+    return x
 
 
 def main():

@@ -48,8 +48,11 @@ def summarize(stats: torch.Tensor) -> Dict[str, float]:
     """episode_reward_max/min/mean, episode_len_mean, episodes_total (cli.py:32-38) from the packed vector."""
     s = [float(x) for x in stats.tolist()]
     n = s[0]
-    mean = s[1] / n if n else float("nan")
-    var = max(s[3] / n - mean * mean, 0.0) if n else float("nan")
-    return {"episodes_total": n, "episode_reward_mean": mean, "episode_reward_std": var ** 0.5 if n else float("nan"),
-            "episode_reward_max": s[4] if n else float("nan"), "episode_reward_min": s[5] if n else float("nan"),
-            "episode_len_mean": s[2] / n if n else float("nan"), "env_steps": s[6], "reached_target": s[7]}
+    if not n:      # no episode finished in the window: None (JSON null), never NaN / inf
+        return {"episodes_total": 0.0, "episode_reward_mean": None, "episode_reward_std": None, "episode_reward_max": None,
+                "episode_reward_min": None, "episode_len_mean": None, "env_steps": s[6], "reached_target": s[7]}
+    mean = s[1] / n
+    var = max(s[3] / n - mean * mean, 0.0)
+    return {"episodes_total": n, "episode_reward_mean": mean, "episode_reward_std": var ** 0.5,
+            "episode_reward_max": s[4], "episode_reward_min": s[5], "episode_len_mean": s[2] / n, "env_steps": s[6],
+            "reached_target": s[7]}

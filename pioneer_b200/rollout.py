@@ -1,0 +1,90 @@
+"""Device-resident rollout worker: what an RLlib RolloutWorker does around the reference env
+(pioneer/launch/pioneer_knm_train.py:43-73 -- sample `train_batch_size` env steps with the current policy, observation
+filter 'MeanStdFilter', episode metrics back to the trainer), with every tensor staying on the GPU:
+
+    obs --(pnr_filter_apply)--> normalised obs --(policy MLP)--> action --(pnr_step)--> obs', reward, done
+
+The policy here is the launcher's model shape (fcnet_hiddens [256, 256], tanh; `pioneer_knm_train.py:59-61`) as a
+plain torch module with a diagonal-Gaussian head -- a stand-in for the PPO policy, which is RLlib's (out of scope);
+PyTorch / cuBLAS are plumbing on this side of the boundary.  The trainer is not reproduced: ``collect()`` returns
+the fragment tensors a trainer would consume.  Once per iteration ``sync()`` all-reduces the episode statistics and
+the filter statistics over the ranks (the only collectives of the path)."""
+from __future__ import annotations
+
+from typing import Dict, Optional
+
+import torch
+import torch.nn as nn
+
+from .batched_env import DOF, OBS_DIM, BatchedPioneerEnv
+from .distributed import reduce_episode_stats, summarize
+from .obs_filter import MeanStdObsFilter
+
+
+class GaussianMlpPolicy(nn.Module):
+    """137 -> 256 -> 256 -> 12 (mean, log_std), tanh: the launcher's `fcnet_hiddens` / `fcnet_activation`."""
+
+    def __init__(self, hiddens=(256, 256), dtype=torch.float32):
+        super().__init__()
+        layers, d = [], OBS_DIM
+        for h in hiddens:
+            layers += [nn.Linear(d, h), nn.Tanh()]
+            d = h
+        layers.append(nn.Linear(d, 2 * DOF))
+        self.net = nn.Sequential(*layers).to(dtype)
+        with torch.no_grad():
+            self.net[-1].weight.mul_(0.01)
+            self.net[-1].bias.zero_()
+
+    def forward(self, obs: torch.Tensor):
+        out = self.net(obs.to(self.net[0].weight.dtype)).float()
+        return out[:, :DOF], out[:, DOF:].clamp(-5.0, 2.0)
+
+
+class RolloutWorker:
+    def __init__(self, env: BatchedPioneerEnv, fragment_length: int = 8, policy: Optional[nn.Module] = None,
+                 use_filter: bool = True, seed: int = 0, policy_dtype=torch.bfloat16):
+        self.env, self.T = env, int(fragment_length)
+        dev, n = env.device, env.n_envs
+        self.policy = (policy or GaussianMlpPolicy(dtype=policy_dtype)).to(dev)
+        self.filter = MeanStdObsFilter(env) if use_filter else None
+        self.gen = torch.Generator(device=dev).manual_seed(seed)
+        self.a_max = torch.as_tensor(env.a_max, device=dev)
+        f32 = dict(dtype=torch.float32, device=dev)
+        # fragment storage [T, N, ...]: raw observations are overwritten in place by their normalised version
+        self.obs = torch.empty((self.T + 1, n, OBS_DIM), **f32)
+        self.actions = torch.empty((self.T, n, DOF), **f32)
+        self.logp = torch.empty((self.T, n), **f32)
+        self.reward = torch.empty((self.T, n), **f32)
+        self.flags = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
+        self._have_first = False
+
+    @torch.no_grad()
+    def collect(self) -> Dict[str, torch.Tensor]:
+        """T env steps of every env; returns views of the fragment buffers (valid until the next call)."""
+        env = self.env
+        if not self._have_first:
+            self.obs[0].copy_(env.reset())
+            if self.filter is not None:
+                self.filter(self.obs[0])
+            self._have_first = True
+        else:
+            self.obs[0].copy_(self.obs[self.T])
+        for t in range(self.T):
+            mean, log_std = self.policy(self.obs[t])
+            noise = torch.randn(mean.shape, device=mean.device, generator=self.gen)
+            raw = mean + log_std.exp() * noise
+            self.logp[t] = (-0.5 * noise.pow(2) - log_std).sum(-1)
+            torch.mul(torch.tanh(raw), self.a_max, out=self.actions[t])          # squash into the action space
+            env.step_tensor(self.actions[t], out=(self.obs[t + 1], self.reward[t], self.flags[t]))
+            if self.filter is not None:
+                self.filter(self.obs[t + 1])                                      # push + normalise in place
+        return dict(obs=self.obs[:self.T], next_obs=self.obs[1:], actions=self.actions, logp=self.logp,
+                    reward=self.reward, done=(self.flags & 1).bool(), truncated=(self.flags & 2).bool())
+
+    def sync(self, group=None) -> Dict[str, float]:
+        """Once per training iteration: episode statistics and filter statistics of all ranks."""
+        stats = reduce_episode_stats(self.env.episode_stats_tensor(clear=True), group)
+        if self.filter is not None:
+            self.filter.sync(group)
+        return summarize(stats)

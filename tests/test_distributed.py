@@ -35,7 +35,9 @@ def test_summarize_matches_numpy():
     np.testing.assert_allclose(s["episode_len_mean"], lengths.mean())
     assert s["episode_reward_max"] == returns.max() and s["episode_reward_min"] == returns.min()
     empty = summarize(torch.tensor([0, 0, 0, 0, -np.inf, np.inf, 0, 0], dtype=torch.float64))
-    assert empty["episodes_total"] == 0 and np.isnan(empty["episode_reward_mean"])
+    assert empty["episodes_total"] == 0 and empty["episode_reward_mean"] is None and empty["episode_reward_max"] is None
+    import json
+    json.loads(json.dumps(empty, allow_nan=False))                 # strict JSON
 
 
 def _free_port():

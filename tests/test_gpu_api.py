@@ -152,3 +152,26 @@ def test_scene_mirrors_answer_from_device_state():
     env.scene.joints[1].reset_state(0.5)
     np.testing.assert_allclose(env.joint_positions(), [0, 0.5, 0, 0, 0, 0])
     env.close()
+
+
+def test_rollout_worker_collects_fragments_on_the_device():
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    from pioneer_b200.rollout import RolloutWorker
+    n, T = 512, 6
+    env = BatchedPioneerEnv(n, seed=3, batch_config=BatchConfig(max_episode_steps=10))
+    w = RolloutWorker(env, fragment_length=T, policy_dtype=torch.float32)
+    for it in range(4):
+        b = w.collect()
+        assert b["obs"].shape == (T, n, 137) and b["actions"].shape == (T, n, 6) and b["reward"].shape == (T, n)
+        a_max = torch.as_tensor(env.a_max).cuda()
+        assert (b["actions"].abs() <= a_max).all() and torch.isfinite(b["obs"]).all() and torch.isfinite(b["logp"]).all()
+        assert float(b["obs"].abs().max()) <= 10.0                      # normalised + clipped
+        s = w.sync()
+    assert s["env_steps"] == n * T and w.filter.n == n * (4 * T + 1)
+    # 24 steps with TimeLimit 10: every env finished 2 episodes, the last sync window saw the second batch
+    assert env.episode_stats()["episodes"] == 0 and s["episodes_total"] == n
+    # fragments chain: the first observation of a fragment is the last of the previous one
+    last = w.obs[T].clone()
+    b = w.collect()
+    assert torch.equal(b["obs"][0], last)
+    env.close()
