@@ -43,7 +43,7 @@ L2_FLUSH_BYTES = 512 << 20                           # > 4x the 126 MB L2
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of pnr_step_kernel from the committed `ncu --set full`
 # captures (profiles/r01_v3_step_65536.md, profiles/r01_v3_step_1m.md).  At 65,536 envs most of the 36 MB of
 # observations is still dirty in the 126 MB L2 when the kernel ends, so DRAM writes read far below the algorithmic bytes.
-NCU_TRAFFIC_BYTES = {65536: 7.91e6 + 0.75e6, 1048576: 126.1e6 + 625.7e6}
+NCU_TRAFFIC_BYTES = {65536: 7.91e6 + 0.63e6, 1048576: 126.2e6 + 623.1e6}      # profiles/r01_v4_step_{65536,1m}.md
 
 
 def parse_args():
@@ -496,6 +496,12 @@ def ours_arm(args):
             e.close()
             del a, o, r, f
         line["sweep"] = sweep
+        big = sweep[-1]
+        # the same kernel where the launch is long enough for the fixed costs of the timing method to vanish
+        line["roofline_large_batch"] = {
+            "bound": "hbm", "achieved": big["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": big["frac"],
+            "traffic": NCU_TRAFFIC_BYTES.get(big["envs"]), "kernel": "pnr_step_kernel<F32,TERMINAL>",
+            "bytes_per_env_step": BYTES_PER_ENV_STEP, "units_per_launch": big["envs"], "peak_source": peak_src}
 
     # ---- Tier-B dynamic mode (ABA + PD control, 10 substeps per env step), reported separately ---------------
     if world == 1 and not args.no_sweep:

@@ -141,7 +141,6 @@ template <int PENDING>
 __device__ __forceinline__ void pnr_bulk_wait_read() {      // returns once at most PENDING groups still read smem
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
 }
-__device__ __forceinline__ void pnr_bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 
 // named CTA barriers (ids 1..15; id 0 is __syncthreads): producer warps ARRIVE without waiting, the consumer SYNCs.
 // `count` = all participating threads (arrivers + waiters).  Both order prior shared / global accesses of the CTA.

@@ -400,8 +400,9 @@ cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_m
     }
     // Resident CTAs per SM, measured on B200 (profiles/r01_v4_cta_sweep.md): long grid-stride runs stream best with
     // 4 CTAs per SM (87 % of the HBM copy peak at 2M envs against 80 % with 6), short ones need all 6 to fill the GPU.
-    int dev_sms = 0;
-    cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
+    static int sms_of[PNR_MAX_DEVICES] = {};
+    int& dev_sms = sms_of[device % PNR_MAX_DEVICES];
+    if (dev_sms == 0) cudaDeviceGetAttribute(&dev_sms, cudaDevAttrMultiProcessorCount, device);
     const int64_t n_tiles = (p.n_envs + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
     int per_sm = n_tiles >= 16384 ? 4 : (n_tiles >= 8192 ? 5 : 6);
     if (const char* e = getenv("PNR_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // developer knob

@@ -378,3 +378,33 @@ def test_cfg2_4096_envs_1000_steps_vs_c_oracle():
     assert st["episodes"] == cc.stats[0] and st["env_steps"] == n * steps
     np.testing.assert_allclose(st["sum_return"], cc.stats[1], rtol=1e-5)
     env.close()
+
+
+@pytest.mark.parametrize("n", [262144 + 17, 1048576])
+def test_deep_grid_stride_pipeline_vs_c_oracle(n):
+    """Many tiles per CTA (the producer / consumer pipeline over two tile buffers runs 10-55 iterations deep):
+    every row against the C oracle, plus run-to-run bit-identity of two handles (a barrier protocol error or a
+    tile-buffer race would show up as a mismatch somewhere in 10^6 rows)."""
+    from oracle.c_oracle import COracleBatch
+    seed, steps = 77, 3
+    cc = COracleBatch(oracle_chain(), n, OracleConfig(max_episode_steps=2), arith="np2", seed=seed, obs_mode="terminal")
+    a = make_env(n, max_episode_steps=2, auto_reset=True, obs_mode="terminal", seed=seed)
+    b = make_env(n, max_episode_steps=2, auto_reset=True, obs_mode="terminal", seed=seed)
+    g = torch.Generator(device="cuda").manual_seed(5)
+    a_max = torch.as_tensor(a.a_max).cuda()
+    for t in range(steps):
+        act = (torch.rand((n, 6), device="cuda", generator=g) * 2 - 1) * a_max
+        oa, ra, fa = a.step_tensor(act)
+        ob, rb, fb = b.step_tensor(act)
+        assert torch.equal(oa, ob) and torch.equal(ra, rb) and torch.equal(fa, fb), t
+        o_obs, o_rew, o_flags = cc.step(act.cpu().numpy())
+        assert np.array_equal(fa.cpu().numpy(), o_flags), t
+        o = oa.cpu().numpy().astype(np.float64)
+        assert np.array_equal(o[:, VALUE_COLS], o_obs[:, VALUE_COLS]), t
+        assert np.abs(o[:, POS_COLS] - o_obs[:, POS_COLS]).max() <= POS_TOL
+        assert np.abs(o[:, TRIG_COLS] - o_obs[:, TRIG_COLS]).max() <= TRIG_TOL
+        assert np.abs(ra.cpu().numpy() - o_rew).max() <= REW_TOL
+    sa, sc = a.state(), cc.state()
+    for k in ("r", "v", "a", "t"):
+        assert np.array_equal(sa[k].cpu().numpy(), sc[k]), k
+    a.close(); b.close()
