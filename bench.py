@@ -40,6 +40,12 @@ BYTES_PER_ENV_STEP = BYTES_IO + BYTES_STATE          # 761
 FRAME_SKIP = 10
 FALLBACK_HBM_GBS = 6650.0                            # /opt/skills/guides/B200_PROFILING.md fallback
 L2_FLUSH_BYTES = 512 << 20                           # > 4x the 126 MB L2
+# Tier-B dynamic kernel, from the committed ncu capture (profiles/r01_dyn_v2_step_dynamic_65536.md): FFMA 9,639 +
+# FMUL 6,663 + FADD 4,834 thread instructions per env-step (10 ABA substeps) = 30,775 flop; FP32 FMA peak measured on
+# this pool's B200 with tools/fma_peak.py = 72.6 TFLOP/s (nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)
+DYN_FLOP_PER_ENV_STEP = 2 * 9639 + 6663 + 4834
+DYN_FP_INSTR_PER_ENV_STEP = 9639 + 6663 + 4834
+FP32_PEAK_TFLOPS = 72.6
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of pnr_step_kernel from the committed `ncu --set full`
 # captures (profiles/r01_v3_step_65536.md, profiles/r01_v3_step_1m.md).  At 65,536 envs most of the 36 MB of
 # observations is still dirty in the 126 MB L2 when the kernel ends, so DRAM writes read far below the algorithmic bytes.
@@ -515,10 +521,17 @@ def ours_arm(args):
         a = (a / torch.as_tensor(e.a_max, device=device)) * 0.5 * (hi - lo) + 0.5 * (hi + lo)   # desired joint positions
         k_steps = min(args.steps, 300)
         ms, _ = time_device_steps(torch, e, a.contiguous(), o, r, f, k_steps, 10, flush)
+        dyn_value = m * k_steps / (ms / 1e3)
+        dyn_tflops = dyn_value * DYN_FLOP_PER_ENV_STEP / 1e12
         line["dynamic_mode"] = {
             "workload": f"{m} envs, gravity 9.81, PD position control (kp 2000, kd 500), {FRAME_SKIP} ABA substeps per env step",
-            "ms_per_step": ms / k_steps, "value": m * k_steps / (ms / 1e3), "unit": UNIT,
-            "substeps_per_sec": FRAME_SKIP * m * k_steps / (ms / 1e3), "parity": "float64 oracle, unpinned vs PyBullet"}
+            "ms_per_step": ms / k_steps, "value": dyn_value, "unit": UNIT,
+            "substeps_per_sec": FRAME_SKIP * dyn_value, "parity": "float64 oracle, unpinned vs PyBullet",
+            "roofline": {"bound": "fp32", "achieved": dyn_tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                         "frac": dyn_tflops / FP32_PEAK_TFLOPS, "flop_per_env_step": DYN_FLOP_PER_ENV_STEP,
+                         "fp32_issue_frac": dyn_value * DYN_FP_INSTR_PER_ENV_STEP / (FP32_PEAK_TFLOPS / 2 * 1e12),
+                         "peak_source": "tools/fma_peak.py on this pool's B200 (FMA = 2 flop)",
+                         "kernel": "pnr_step_dynamic_kernel<TERMINAL,false,PIONEER>"}}
         e.close()
         del a, o, r, f
 

@@ -6,8 +6,11 @@
 #include "pnr_dynamics.cuh"
 #include "pnr_launch.h"
 
+#ifndef PNR_DYN_MIN_CTAS
+#define PNR_DYN_MIN_CTAS 2            // 208 registers: 2 CTAs/SM measured 72 us per 65,536-env step against 93 us with 3 (168 regs), 88 us with 4
+#endif
 template <int OBS_MODE, bool OBSTACLES, int CHAIN>
-__global__ void __launch_bounds__(PNR_STEP_THREADS)
+__global__ void __launch_bounds__(PNR_STEP_THREADS, PNR_DYN_MIN_CTAS)
 pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                         float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                         PnrStats* __restrict__ stats, uint32_t tick) {
