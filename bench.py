@@ -40,11 +40,11 @@ BYTES_PER_ENV_STEP = BYTES_IO + BYTES_STATE          # 761
 FRAME_SKIP = 10
 FALLBACK_HBM_GBS = 6650.0                            # /opt/skills/guides/B200_PROFILING.md fallback
 L2_FLUSH_BYTES = 512 << 20                           # > 4x the 126 MB L2
-# Tier-B dynamic kernel, from the committed ncu capture (profiles/r01_dyn_v2_step_dynamic_65536.md): FFMA 9,639 +
-# FMUL 6,663 + FADD 4,834 thread instructions per env-step (10 ABA substeps) = 30,775 flop; FP32 FMA peak measured on
+# Tier-B dynamic kernel, from the committed ncu capture (profiles/r01_dyn_v3_step_dynamic_65536.md): FFMA 8,056 +
+# FMUL 4,734 + FADD 3,733 thread instructions per env-step (10 ABA substeps) = 24,579 flop; FP32 FMA peak measured on
 # this pool's B200 with tools/fma_peak.py = 72.6 TFLOP/s (nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)
-DYN_FLOP_PER_ENV_STEP = 2 * 9639 + 6663 + 4834
-DYN_FP_INSTR_PER_ENV_STEP = 9639 + 6663 + 4834
+DYN_FLOP_PER_ENV_STEP = 2 * 8056 + 4734 + 3733
+DYN_FP_INSTR_PER_ENV_STEP = 8056 + 4734 + 3733
 FP32_PEAK_TFLOPS = 72.6
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of pnr_step_kernel from the committed `ncu --set full`
 # captures (profiles/r01_v3_step_65536.md, profiles/r01_v3_step_1m.md).  At 65,536 envs most of the 36 MB of

@@ -170,8 +170,11 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
     {   // the shipped robot's axis pattern gets the specialised dynamics kernel (pnr_dynamics.cuh, PNR_CHAIN_PIONEER)
         const int pattern[PNR_DOF] = {PNR_AXIS_Z, PNR_AXIS_Y, PNR_AXIS_Y, PNR_AXIS_X, PNR_AXIS_Y, PNR_AXIS_X};
         bool match = true;
-        for (int j = 0; j < PNR_DOF; ++j)
+        const int origin_axis[PNR_DOF] = {-1, 2, 2, 1, 0, -1};       // the only non-zero origin component (-1: none)
+        for (int j = 0; j < PNR_DOF; ++j) {
             match = match && p.axis_code[j] == pattern[j] && p.axis_sign[j] > 0.f && !p.origin_has_rot[j];
+            for (int k = 0; k < 3; ++k) match = match && (k == origin_axis[j] || m.origin_xyz[j][k] == 0.0);
+        }
         p.chain_kind = match ? 1 : 0;
     }
     p.dyn_kp = (float)c.kp; p.dyn_kd = (float)c.kd;

@@ -104,6 +104,20 @@ __device__ __forceinline__ V3 pnr_matT_axis(const PnrParams& p, int j, const Mat
     return matTmul(a, pnr_axis<CHAIN>(p, j));
 }
 
+// origin_j x v.  The shipped robot's joint origins lie on one coordinate axis of the parent frame (joint 0 and 5: zero,
+// 1 and 2: along z, 3: along y, 4: along x; pioneer_knm_6dof.urdf:209-264), so the cross product is two multiplies.
+template <int CHAIN>
+__device__ __forceinline__ V3 pnr_origin_cross(const PnrParams& p, int j, V3 v) {
+    if (CHAIN == PNR_CHAIN_PIONEER) {
+        if (j == 0 || j == 5) return v3(0.f, 0.f, 0.f);
+        if (j == 1 || j == 2) { const float z = p.origin_xyz[j][2]; return v3(-z * v.y, z * v.x, 0.f); }
+        if (j == 3) { const float y = p.origin_xyz[j][1]; return v3(y * v.z, 0.f, -y * v.x); }
+        const float x = p.origin_xyz[j][0];
+        return v3(0.f, -x * v.z, x * v.y);
+    }
+    return cross(v3(p.origin_xyz[j][0], p.origin_xyz[j][1], p.origin_xyz[j][2]), v);
+}
+
 // rotation about joint j's axis by the angle whose (sin, cos) are given; axis-aligned axes cost 4 FMA.
 template <int CHAIN>
 __device__ __forceinline__ V3 pnr_axis_rot(const PnrParams& p, int j, float s, float c, V3 v) {
@@ -181,8 +195,7 @@ __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR
 #pragma unroll
     for (int i = 0; i < PNR_DOF; ++i) {
         pnr_sincos_fast(q[i], w.sn[i], w.cs[i]);                       // q is inside the joint limits
-        const V3 pi = v3(p.origin_xyz[i][0], p.origin_xyz[i][1], p.origin_xyz[i][2]);
-        const V3 t = vl - cross(pi, om);
+        const V3 t = vl - pnr_origin_cross<CHAIN>(p, i, om);
         om = pnr_rot_t<CHAIN>(p, i, w.sn[i], w.cs[i], om);
         vl = pnr_rot_t<CHAIN>(p, i, w.sn[i], w.cs[i], t);
         om = om + pnr_axis_scaled<CHAIN>(p, i, qd[i]);
@@ -242,20 +255,19 @@ __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR
             const Mat3 Ir = pnr_rot_block<CHAIN>(p, i, s, c, sym_to_mat(I));
             const Mat3 Hr = pnr_rot_block<CHAIN>(p, i, s, c, H);
             const Mat3 Mr = pnr_rot_block<CHAIN>(p, i, s, c, sym_to_mat(M));
-            const V3 pi = v3(p.origin_xyz[i][0], p.origin_xyz[i][1], p.origin_xyz[i][2]);
             // A = p x M' (column-wise); H'' = H' + A
-            const V3 a0 = cross(pi, v3(Mr.m[0], Mr.m[3], Mr.m[6]));
-            const V3 a1 = cross(pi, v3(Mr.m[1], Mr.m[4], Mr.m[7]));
-            const V3 a2 = cross(pi, v3(Mr.m[2], Mr.m[5], Mr.m[8]));
+            const V3 a0 = pnr_origin_cross<CHAIN>(p, i, v3(Mr.m[0], Mr.m[3], Mr.m[6]));
+            const V3 a1 = pnr_origin_cross<CHAIN>(p, i, v3(Mr.m[1], Mr.m[4], Mr.m[7]));
+            const V3 a2 = pnr_origin_cross<CHAIN>(p, i, v3(Mr.m[2], Mr.m[5], Mr.m[8]));
             const Mat3 A = {{a0.x, a1.x, a2.x, a0.y, a1.y, a2.y, a0.z, a1.z, a2.z}};
             // K = p x H'^T (columns of K = p x rows of H'); A P^T has rows p x (rows of A)
-            const V3 k0 = cross(pi, v3(Hr.m[0], Hr.m[1], Hr.m[2]));
-            const V3 k1 = cross(pi, v3(Hr.m[3], Hr.m[4], Hr.m[5]));
-            const V3 k2 = cross(pi, v3(Hr.m[6], Hr.m[7], Hr.m[8]));
+            const V3 k0 = pnr_origin_cross<CHAIN>(p, i, v3(Hr.m[0], Hr.m[1], Hr.m[2]));
+            const V3 k1 = pnr_origin_cross<CHAIN>(p, i, v3(Hr.m[3], Hr.m[4], Hr.m[5]));
+            const V3 k2 = pnr_origin_cross<CHAIN>(p, i, v3(Hr.m[6], Hr.m[7], Hr.m[8]));
             const Mat3 K = {{k0.x, k1.x, k2.x, k0.y, k1.y, k2.y, k0.z, k1.z, k2.z}};
-            const V3 q0 = cross(pi, v3(A.m[0], A.m[1], A.m[2]));
-            const V3 q1 = cross(pi, v3(A.m[3], A.m[4], A.m[5]));
-            const V3 q2 = cross(pi, v3(A.m[6], A.m[7], A.m[8]));
+            const V3 q0 = pnr_origin_cross<CHAIN>(p, i, v3(A.m[0], A.m[1], A.m[2]));
+            const V3 q1 = pnr_origin_cross<CHAIN>(p, i, v3(A.m[3], A.m[4], A.m[5]));
+            const V3 q2 = pnr_origin_cross<CHAIN>(p, i, v3(A.m[6], A.m[7], A.m[8]));
             Mat3 In;
             In.m[0] = Ir.m[0] + 2.f * K.m[0] + q0.x;
             In.m[1] = Ir.m[1] + K.m[1] + K.m[3] + q0.y;
@@ -271,7 +283,7 @@ __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR
             for (int k = 0; k < 9; ++k) H.m[k] = Hr.m[k] + A.m[k];
             M = mat_to_sym(Mr);
             const V3 fp = pnr_rot<CHAIN>(p, i, s, c, pa_lin);
-            pa_ang = pnr_rot<CHAIN>(p, i, s, c, pa_ang) + cross(pi, fp);
+            pa_ang = pnr_rot<CHAIN>(p, i, s, c, pa_ang) + pnr_origin_cross<CHAIN>(p, i, fp);
             pa_lin = fp;
         }
     }
@@ -279,8 +291,7 @@ __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR
     V3 aa = v3(0.f, 0.f, 0.f), al = v3(0.f, 0.f, p.dyn_gravity);
 #pragma unroll
     for (int i = 0; i < PNR_DOF; ++i) {
-        const V3 pi = v3(p.origin_xyz[i][0], p.origin_xyz[i][1], p.origin_xyz[i][2]);
-        const V3 t = al - cross(pi, aa);
+        const V3 t = al - pnr_origin_cross<CHAIN>(p, i, aa);
         aa = pnr_rot_t<CHAIN>(p, i, w.sn[i], w.cs[i], aa) + w.c_ang[i];
         al = pnr_rot_t<CHAIN>(p, i, w.sn[i], w.cs[i], t) + w.c_lin[i];
         qdd[i] = (w.u[i] - dot(w.u_ang[i], aa) - dot(w.u_lin[i], al)) * w.dinv[i];
