@@ -2,6 +2,7 @@
 // No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -46,7 +47,8 @@ struct pnr_handle {
     // host-buffer path (pnr_step_host)
     float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
     uint8_t* h_done = nullptr;
-    cudaStream_t host_stream = nullptr;
+    cudaStream_t host_stream = nullptr, host_stream2 = nullptr;
+    cudaEvent_t host_event = nullptr;
 };
 
 struct PnrDeviceGuard {
@@ -259,6 +261,8 @@ extern "C" void pnr_destroy(pnr_handle* h) {
     if (!h) return;
     PnrDeviceGuard guard(h->device);
     if (h->host_stream) { cudaStreamSynchronize(h->host_stream); cudaStreamDestroy(h->host_stream); }
+    if (h->host_stream2) { cudaStreamSynchronize(h->host_stream2); cudaStreamDestroy(h->host_stream2); }
+    if (h->host_event) cudaEventDestroy(h->host_event);
     cudaFree(h->state); cudaFree(h->stats); cudaFree(h->stats_out);
     cudaFree(h->filt_delta); cudaFree(h->filt_applied);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_done);
@@ -332,6 +336,10 @@ extern "C" int pnr_step_host(pnr_handle* h, const float* actions, float* obs, fl
     const size_t n = (size_t)h->n_envs;
     if (!h->host_stream) {
         PNR_CUDA(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
+        if (!getenv("PNR_HOST_ONE_STREAM")) {                   // developer knob: single-stream copies
+            PNR_CUDA(cudaStreamCreateWithFlags(&h->host_stream2, cudaStreamNonBlocking));
+            PNR_CUDA(cudaEventCreateWithFlags(&h->host_event, cudaEventDisableTiming));
+        }
         PNR_CUDA(cudaMalloc(&h->h_actions, n * PNR_DOF * sizeof(float)));
         PNR_CUDA(cudaMalloc(&h->h_obs, n * PNR_OBS_DIM * sizeof(float)));
         PNR_CUDA(cudaMalloc(&h->h_reward, n * sizeof(float)));
@@ -341,9 +349,22 @@ extern "C" int pnr_step_host(pnr_handle* h, const float* actions, float* obs, fl
     PNR_CUDA(cudaMemcpyAsync(h->h_actions, actions, n * PNR_DOF * sizeof(float), cudaMemcpyHostToDevice, s));
     int rc = pnr_step(h, h->h_actions, h->h_obs, h->h_reward, h->h_done, s);
     if (rc != PNR_OK) return rc;
-    PNR_CUDA(cudaMemcpyAsync(obs, h->h_obs, n * PNR_OBS_DIM * sizeof(float), cudaMemcpyDeviceToHost, s));
+    // The 548 B/env observation copy is what bounds this call (PCIe).  Two copy engines working on the two halves
+    // keep the link fuller than one; reward / done ride on the first stream.
+    const size_t half = (n / 2) * PNR_OBS_DIM;
+    const size_t total = n * PNR_OBS_DIM;
+    if (h->host_stream2 && half > 0) {
+        PNR_CUDA(cudaEventRecord(h->host_event, s));
+        PNR_CUDA(cudaStreamWaitEvent(h->host_stream2, h->host_event, 0));
+        PNR_CUDA(cudaMemcpyAsync(obs + half, h->h_obs + half, (total - half) * sizeof(float), cudaMemcpyDeviceToHost,
+                                 h->host_stream2));
+        PNR_CUDA(cudaMemcpyAsync(obs, h->h_obs, half * sizeof(float), cudaMemcpyDeviceToHost, s));
+    } else {
+        PNR_CUDA(cudaMemcpyAsync(obs, h->h_obs, total * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
     PNR_CUDA(cudaMemcpyAsync(reward, h->h_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
     PNR_CUDA(cudaMemcpyAsync(done, h->h_done, n, cudaMemcpyDeviceToHost, s));
+    if (h->host_stream2) PNR_CUDA(cudaStreamSynchronize(h->host_stream2));
     PNR_CUDA(cudaStreamSynchronize(s));
     return PNR_OK;
 }
