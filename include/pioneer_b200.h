@@ -163,6 +163,12 @@ int pnr_get_state(pnr_handle* h, float* r, float* v, float* a, float* potential,
 int pnr_set_state(pnr_handle* h, const float* r, const float* v, const float* a, const float* potential,
                   const float* target, const int32_t* t, const float* ep_return, void* stream);
 
+/* Host-side counters of the handle, for checkpoint / resume together with pnr_get_state / pnr_set_state: `tick` keys the
+ * reset generator (one per reset / step call), `env_steps` feeds pnr_stats.  (The reference env has no state
+ * save / restore of its own -- it is re-created from constructor arguments, pioneer_knm_env.py:38,51.) */
+int pnr_get_counters(const pnr_handle* h, uint32_t* tick, double* env_steps, uint64_t* seed);
+int pnr_set_counters(pnr_handle* h, uint32_t tick, double env_steps);
+
 /* Episode statistics accumulated on the device since the last clear (the columns cli.py:32-38 prints):
  * out HOST double[8] = {episodes, sum_return, sum_length, sum_return^2, max_return, min_return,
  * env_steps, reached_target}.  Synchronises `stream`. */

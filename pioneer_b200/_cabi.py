@@ -77,6 +77,8 @@ SIGNATURES = {
     "pnr_get_bounds": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float)]),
     "pnr_seed": (C.c_int, [_H, C.c_uint64]),
+    "pnr_get_counters": (C.c_int, [_H, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
+    "pnr_set_counters": (C.c_int, [_H, C.c_uint32, C.c_double]),
     "pnr_reset": (C.c_int, [_H, _P, C.c_int64, _P, _P, _P, _S]),
     "pnr_step": (C.c_int, [_H, _P, _P, _P, _P, _S]),
     "pnr_step_host": (C.c_int, [_H, _P, _P, _P, _P]),

@@ -291,6 +291,26 @@ class BatchedPioneerEnv:
             _cabi.check(self._lib.pnr_set_state(self._h, *[None if x is None else x.data_ptr() for x in keep],
                                                 self._stream()), "pnr_set_state")
 
+    # ---- checkpoint / resume -------------------------------------------------------------------
+    def state_dict(self) -> Dict[str, object]:
+        """Everything needed to continue bit-identically: per-env state (host copies), the reset generator's seed and
+        call counter, and the episode statistics of the current window.  (The reference env has no save / restore; it
+        is re-created from constructor arguments, pioneer_knm_env.py:38,51.)"""
+        tick, steps, seed = C.c_uint32(), C.c_double(), C.c_uint64()
+        _cabi.check(self._lib.pnr_get_counters(self._h, C.byref(tick), C.byref(steps), C.byref(seed)), "pnr_get_counters")
+        return {"n_envs": self.n_envs, "env_id_base": self.env_id_base, "seed": int(seed.value), "tick": int(tick.value),
+                "env_steps": float(steps.value), "step_index": self.step_index,
+                "state": {k: v.cpu() for k, v in self.state().items()}}
+
+    def load_state_dict(self, sd: Dict[str, object]) -> None:
+        assert sd["n_envs"] == self.n_envs and sd["env_id_base"] == self.env_id_base, "checkpoint is for another shard"
+        st = sd["state"]
+        self.set_state(r=st["r"], v=st["v"], a=st["a"], potential=st["potential"], target=st["target"], t=st["t"],
+                       ep_return=st["ep_return"])
+        self.seed(int(sd["seed"]))
+        _cabi.check(self._lib.pnr_set_counters(self._h, int(sd["tick"]), float(sd["env_steps"])), "pnr_set_counters")
+        self.step_index = int(sd["step_index"])
+
     # the reference's per-env attributes, batched
     @property
     def r(self): return self.state()["r"]

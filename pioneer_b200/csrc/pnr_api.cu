@@ -284,6 +284,21 @@ extern "C" int pnr_get_bounds(const pnr_handle* h, float* r_lo, float* r_hi, flo
     return PNR_OK;
 }
 
+extern "C" int pnr_get_counters(const pnr_handle* h, uint32_t* tick, double* env_steps, uint64_t* seed) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_get_counters: null handle");
+    if (tick) *tick = h->tick;
+    if (env_steps) *env_steps = h->env_steps;
+    if (seed) *seed = ((uint64_t)h->params.seed_hi << 32) | h->params.seed_lo;
+    return PNR_OK;
+}
+
+extern "C" int pnr_set_counters(pnr_handle* h, uint32_t tick, double env_steps) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_set_counters: null handle");
+    h->tick = tick;
+    h->env_steps = env_steps;
+    return PNR_OK;
+}
+
 extern "C" int pnr_seed(pnr_handle* h, uint64_t seed) {
     if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_seed: null handle");
     h->params.seed_lo = (uint32_t)seed;

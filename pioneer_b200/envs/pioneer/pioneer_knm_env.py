@@ -30,6 +30,8 @@ class PioneerKinematicEnv(BulletEnv):
                  simulation_config: Optional[SimulationConfig] = None,
                  render_config: Optional[RenderConfig] = None,
                  device=None, arith: str = "f32"):
+        # gym.utils.EzPickle (pioneer_knm_env.py:38,51): the env pickles as its constructor arguments
+        self._ctor_args = (headless, pioneer_config, simulation_config, render_config, device, arith)
         self.np_random: Optional[np.random.RandomState] = None
         self.seed()
         self.config = pioneer_config or PioneerKinematicConfig()
@@ -138,6 +140,9 @@ class PioneerKinematicEnv(BulletEnv):
         low = np.full(observation.shape, -float("inf"), dtype=np.float32)
         high = np.full(observation.shape, float("inf"), dtype=np.float32)
         return Box(low, high, dtype=observation.dtype)
+
+    def __reduce__(self):
+        return (type(self), self._ctor_args)
 
     def close(self):
         self._batch.close()

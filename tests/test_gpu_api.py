@@ -175,3 +175,35 @@ def test_rollout_worker_collects_fragments_on_the_device():
     b = w.collect()
     assert torch.equal(b["obs"][0], last)
     env.close()
+
+
+def test_checkpoint_resume_is_bit_identical(tmp_path):
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    n = 700
+    g = torch.Generator(device="cuda").manual_seed(2)
+    env = BatchedPioneerEnv(n, seed=6, batch_config=BatchConfig(max_episode_steps=4))
+    acts = (torch.rand((12, n, 6), device="cuda", generator=g) * 2 - 1) * 60
+    for t in range(5):
+        env.step_tensor(acts[t])
+    torch.save(env.state_dict(), tmp_path / "env.pt")
+    want = [tuple(x.clone() for x in env.step_tensor(acts[t])) for t in range(5, 12)]
+    stats_want = env.episode_stats()
+    # a fresh env (different seed, different history) continues from the checkpoint
+    other = BatchedPioneerEnv(n, seed=99, batch_config=BatchConfig(max_episode_steps=4))
+    other.step_tensor(acts[0])
+    other.load_state_dict(torch.load(tmp_path / "env.pt"))
+    for k, t in enumerate(range(5, 12)):
+        o, r, f = other.step_tensor(acts[t])
+        assert torch.equal(o, want[k][0]) and torch.equal(r, want[k][1]) and torch.equal(f, want[k][2]), t
+    assert other.episode_stats()["env_steps"] == stats_want["env_steps"]
+    env.close(); other.close()
+
+
+def test_facade_pickles_as_constructor_arguments():
+    import pickle
+    from pioneer_b200.envs.pioneer import PioneerKinematicConfig, PioneerKinematicEnv
+    env = PioneerKinematicEnv(pioneer_config=PioneerKinematicConfig(award_done=7.5))
+    clone = pickle.loads(pickle.dumps(env))                       # EzPickle semantics: re-constructed, not copied
+    assert isinstance(clone, PioneerKinematicEnv) and clone.config.award_done == 7.5
+    assert clone.reset().shape == (137,)
+    env.close(); clone.close()
