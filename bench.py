@@ -554,10 +554,18 @@ def ours_arm(args):
             torch.cuda.synchronize()
             ms = sum(a_.elapsed_time(b_) for a_, b_ in evs) / len(evs)
             gbs = 2 * OBS_DIM * 4 * m / (ms / 1e3) / 1e9
+            # the same normalisation fused into the step kernel (pnr_filter_fuse): no second pass over the observations
+            flt_.set_fused(True)
+            a2, o2, r2, f2 = make_buffers(torch, e, m, device, seed=3)
+            k2 = min(args.steps, 300)
+            ms_fused, _ = time_device_steps(torch, e, a2, o2, r2, f2, k2, 10, flush)
+            flt_.set_fused(False)
+            ms_plain, _ = time_device_steps(torch, e, a2, o2, r2, f2, k2, 10, flush)
             filt.append({"rows": m, "ms": ms, "rows_per_sec": m / (ms / 1e3), "achieved_gbs": gbs, "frac": gbs / peak,
-                         "bytes_per_row": 2 * OBS_DIM * 4})
+                         "bytes_per_row": 2 * OBS_DIM * 4, "step_ms_plain": ms_plain / k2,
+                         "step_ms_fused_normaliser": ms_fused / k2, "step_plus_filter_pass_ms": ms_plain / k2 + ms})
             e.close()
-            del ring
+            del ring, a2, o2, r2, f2
         line["obs_filter"] = filt
 
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

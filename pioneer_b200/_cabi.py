@@ -89,6 +89,7 @@ SIGNATURES = {
     "pnr_stats_device": (C.c_int, [_H, _P, C.c_int, _S]),
     "pnr_filter_configure": (C.c_int, [_H, C.c_double, C.c_int, C.c_int]),
     "pnr_filter_apply": (C.c_int, [_H, _P, _P, C.c_int64, C.c_int, C.c_int, _S]),
+    "pnr_filter_fuse": (C.c_int, [_H, C.c_int, C.c_int]),
     "pnr_filter_delta_device": (C.c_int, [_H, _P, _S]),
     "pnr_filter_sync": (C.c_int, [_H, C.POINTER(C.c_double), _S]),
     "pnr_filter_get": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),

@@ -44,6 +44,7 @@ struct pnr_handle {
     double filt_mean[PNR_OBS_DIM] = {}, filt_m2[PNR_OBS_DIM] = {};
     double filt_clip = 10.0;
     int filt_demean = 1, filt_destd = 1;
+    int filt_fused = 0, filt_fused_update = 1;   // pnr_filter_fuse: the step kernel normalises and pushes statistics
     // host-buffer path (pnr_step_host)
     float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
     uint8_t* h_done = nullptr;
@@ -338,7 +339,9 @@ extern "C" int pnr_step(pnr_handle* h, const float* actions, float* obs, float* 
                                          h->stats, h->tick, (cudaStream_t)stream));
     else
         PNR_CUDA(pnr_launch_step(h->params, h->device, h->cfg.arith, h->cfg.obs_mode, h->state, actions, obs, reward, done,
-                                 h->stats, h->tick, (cudaStream_t)stream));
+                                 h->stats, h->tick, h->filt_fused ? h->filt_applied : nullptr,
+                                 (h->filt_fused && h->filt_fused_update) ? h->filt_delta : nullptr, (float)h->filt_clip,
+                                 (cudaStream_t)stream));
     h->tick += 1;
     h->env_steps += (double)h->n_envs;
     h->launches += 1;
@@ -458,6 +461,21 @@ extern "C" int pnr_filter_configure(pnr_handle* h, double clip, int demean, int 
     // the accumulator is relative to the applied mean: rows pushed under the old setting are dropped
     PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_DELTA_LEN, nullptr));
     return pnr_filter_upload_applied(h, nullptr);
+}
+
+extern "C" int pnr_filter_fuse(pnr_handle* h, int on, int update) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_fuse: null handle");
+    if (on && (h->cfg.mode != PNR_MODE_KINEMATIC || h->cfg.arith != PNR_ARITH_F32 || h->cfg.obs_mode != PNR_OBS_TERMINAL))
+        return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_filter_fuse: the fused normaliser is built for the kinematic mode, float32 "
+                                             "arithmetic and terminal observations; use pnr_filter_apply otherwise");
+    PnrDeviceGuard guard(h->device);
+    if (on) {
+        int rc = pnr_filter_ensure(h, nullptr);
+        if (rc != PNR_OK) return rc;
+    }
+    h->filt_fused = on ? 1 : 0;
+    h->filt_fused_update = update ? 1 : 0;
+    return PNR_OK;
 }
 
 extern "C" int pnr_filter_apply(pnr_handle* h, const float* obs_in, float* obs_out, int64_t n_rows, int update,

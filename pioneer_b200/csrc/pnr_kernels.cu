@@ -65,16 +65,27 @@ extern "C" int pnr_debug_trace(unsigned long long* out_host) {
 #define PNR_TRACE_NEXT()
 #endif
 
-template <int ARITH, int OBS_MODE, bool OBSTACLES>
-__global__ void __launch_bounds__(PNR_STEP_THREADS, PNR_STEP_MIN_CTAS)
+// FILTER = true fuses the observation normaliser (pnr_filter.cu, 'MeanStdFilter') into the step: what leaves the
+// kernel is clip((x - mean) * inv_std), and the column statistics of the raw values go to the same float64 accumulator
+// pnr_filter_apply feeds, so the 548 B/env observation is never re-read.  Every warp normalises the columns it owns
+// while the tile is still in shared memory: a joint warp runs one column pass (lane = one of its 30 changing
+// columns, 32 rows, float64 sum / sum of squares of x - mean), the task warp normalises its 11 tail values in
+// registers and keeps per-lane float partial sums; the 36 constant columns are normalised once per CTA and their
+// statistics are added analytically by block 0.  The raw r / cos r / sin r the task warp needs for the forward
+// kinematics travel through a small scratch area next to the tile buffers (the tile copy gets normalised).
+template <int ARITH, int OBS_MODE, bool OBSTACLES, bool FILTER>
+__global__ void __launch_bounds__(PNR_STEP_THREADS, FILTER ? PNR_STEP_MIN_CTAS_FILTER : PNR_STEP_MIN_CTAS)
 pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
-                PnrStats* __restrict__ stats, uint32_t tick) {
+                PnrStats* __restrict__ stats, uint32_t tick, const float* __restrict__ f_applied,
+                double* __restrict__ f_delta, float f_clip) {
     extern __shared__ __align__(128) float tiles[];           // PNR_STEP_BUFS tiles: the bulk store of one drains
     const int lane = threadIdx.x & 31;                        // while the next is being filled
     const int part = threadIdx.x >> 5;                        // warp-uniform role
     float* tile = tiles;
     float* row = tile + lane * PNR_OBS_DIM;
+    float* scratch = tiles + PNR_STEP_BUFS * PNR_TILE_FLOATS; // FILTER only: raw r, cos r, sin r per env, per buffer
+    float* srow = scratch + lane * PNR_FSCRATCH_STRIDE;
     const int64_t N = p.n_envs;
     const int64_t n_tiles = (N + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
     const int64_t stride = gridDim.x;
@@ -101,6 +112,32 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         for (int b = 0; b < PNR_STEP_BUFS; ++b) {
             pnr_pack_joint_const(p, row + b * PNR_TILE_FLOATS, j0);
             pnr_pack_joint_const(p, row + b * PNR_TILE_FLOATS, j0 + 1);
+        }
+    }
+    // fused normaliser: the column this lane owns in the column pass, its applied statistics and accumulators
+    int f_col = 0;
+    float f_mean = 0.f, f_inv = 0.f;
+    double f_sum = 0.0, f_sq = 0.0;
+    float t_sum[11], t_sq[11];
+    if (FILTER) {
+        if (part < 3) {
+            // lanes 0..5 -> column blocks 0..2 (r, cos r, sin r), lanes 6..29 -> blocks 9..20; blocks 3..8 are constant
+            const int kk = lane < 6 ? (lane >> 1) : (lane >> 1) + 6;
+            f_col = 6 * kk + j0 + (lane & 1);
+            if (lane < 30) { f_mean = f_applied[f_col]; f_inv = f_applied[PNR_OBS_DIM + f_col]; }
+#pragma unroll
+            for (int g = 0; g < 6; ++g) {                      // normalise the constant columns in place
+#pragma unroll
+                for (int jj = 0; jj < 2; ++jj) {
+                    const int c = 18 + 6 * g + j0 + jj;
+                    const float y = pnr_normalise(row[c], f_applied[c], f_applied[PNR_OBS_DIM + c], f_clip);
+#pragma unroll
+                    for (int b = 0; b < PNR_STEP_BUFS; ++b) row[b * PNR_TILE_FLOATS + c] = y;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 11; ++i) { t_sum[i] = 0.f; t_sq[i] = 0.f; }
         }
     }
 
@@ -145,6 +182,10 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             PNR_MARK(4);
             pnr_pack_joint_head(rowj, r1[0], sn[0], cs[0]);
             pnr_pack_joint_head(rowj + 1, r1[1], sn[1], cs[1]);
+            if (FILTER) {                                      // the raw values for the task warp's forward kinematics
+                pnr_pack_joint_head(srow + j0, r1[0], sn[0], cs[0]);
+                pnr_pack_joint_head(srow + j0 + 1, r1[1], sn[1], cs[1]);
+            }
             pnr_bar_arrive2<PNR_BAR_HEAD, PNR_STEP_THREADS>(buf);
         } else {
             PNR_MARK(3);
@@ -163,11 +204,26 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                 rv_plane[env] = make_float4(r1[0], r1[1], v1[0], v1[1]);
                 a_plane[env] = c_act;
             }
+            if (FILTER) {                                      // column pass over this warp's 30 changing columns
+                __syncwarp();
+                if (lane < 30) {
+                    float* colp = tile + f_col;
+#pragma unroll 8
+                    for (int r = 0; r < rows_valid; ++r) {
+                        const float d = colp[r * PNR_OBS_DIM] - f_mean;
+                        const double dd = (double)d;
+                        f_sum += dd;
+                        f_sq = fma(dd, dd, f_sq);
+                        colp[r * PNR_OBS_DIM] = fminf(fmaxf(d * f_inv, -f_clip), f_clip);
+                    }
+                }
+            }
         } else {
             // --- pose from the joint warps' sin/cos, distance, reward, done
             PnrPose o;
+            const float* head = FILTER ? srow : row;           // raw r | cos r | sin r of this env
 #pragma unroll
-            for (int i = 0; i < PNR_DOF; ++i) { o.cs[i] = row[6 + i]; o.sn[i] = row[12 + i]; }
+            for (int i = 0; i < PNR_DOF; ++i) { o.cs[i] = head[6 + i]; o.sn[i] = head[12 + i]; }
             float tgt[3] = {c4.x, c4.y, c4.z};
             int32_t t = __float_as_int(c4.w);
             const float pot_old = c2.x;
@@ -179,7 +235,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             if (fabsf(o.dist - p.done_distance) < p.done_band) {   // decide in float64 where float32 could flip it
                 float rr[PNR_DOF];
 #pragma unroll
-                for (int i = 0; i < PNR_DOF; ++i) rr[i] = row[i];
+                for (int i = 0; i < PNR_DOF; ++i) rr[i] = head[i];
                 pnr_fk_tip_f64(p, rr, tgt, o.ptr, o.dist, reached);
             }
             const float pot_new = pnr_potential(p, o.dist);
@@ -204,11 +260,18 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             pnr_episode_stats(stats, is_done && active, reached && active, ep_ret, t, lane);
 
             // observation tail: pointer, target, difference, distance, potential (terminal values)
-            row[126] = o.ptr[0]; row[127] = o.ptr[1]; row[128] = o.ptr[2];
-            row[129] = tgt[0]; row[130] = tgt[1]; row[131] = tgt[2];
-            row[132] = tgt[0] - o.ptr[0]; row[133] = tgt[1] - o.ptr[1]; row[134] = tgt[2] - o.ptr[2];
-            row[135] = o.dist;
-            row[136] = pot_new;
+            float tail[11] = {o.ptr[0], o.ptr[1], o.ptr[2], tgt[0], tgt[1], tgt[2],
+                              tgt[0] - o.ptr[0], tgt[1] - o.ptr[1], tgt[2] - o.ptr[2], o.dist, pot_new};
+            if (FILTER) {                                      // normalise in registers, per-lane partial statistics
+#pragma unroll
+                for (int i = 0; i < 11; ++i) {
+                    const float d = tail[i] - f_applied[126 + i];
+                    if (active) { t_sum[i] += d; t_sq[i] = fmaf(d, d, t_sq[i]); }
+                    tail[i] = fminf(fmaxf(d * f_applied[PNR_OBS_DIM + 126 + i], -f_clip), f_clip);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 11; ++i) row[126 + i] = tail[i];
 
             if (active) {
                 x0_plane[env] = make_float4(tgt[0], tgt[1], tgt[2], __int_as_float(t));
@@ -254,6 +317,38 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         tile = tiles + buf * PNR_TILE_FLOATS;
         row = tile + lane * PNR_OBS_DIM;
         rowj = row + j0;
+        if (FILTER) srow = scratch + buf * PNR_FSCRATCH_FLOATS + lane * PNR_FSCRATCH_STRIDE;
+    }
+    if (FILTER && f_delta != nullptr) {                       // column statistics of this CTA's rows
+        if (part < 3) {
+            if (lane < 30) {
+                atomicAdd(&f_delta[1 + f_col], f_sum);
+                atomicAdd(&f_delta[1 + PNR_OBS_DIM + f_col], f_sq);
+            }
+            if (blockIdx.x == 0 && lane < 12) {                // the constant columns of all N rows, analytically
+                const int g = lane >> 1, j = j0 + (lane & 1), c = 18 + 6 * g + j;
+                const float x = g == 0 ? p.r_lo[j] : g == 1 ? p.cos_r_lo[j] : g == 2 ? p.sin_r_lo[j]
+                              : g == 3 ? p.r_hi[j] : g == 4 ? p.cos_r_hi[j] : p.sin_r_hi[j];
+                const double d = (double)(x - f_applied[c]);
+                atomicAdd(&f_delta[1 + c], (double)N * d);
+                atomicAdd(&f_delta[1 + PNR_OBS_DIM + c], (double)N * d * d);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < 11; ++i) {
+                float a = t_sum[i], b = t_sq[i];
+#pragma unroll
+                for (int ofs = 16; ofs > 0; ofs >>= 1) {
+                    a += __shfl_xor_sync(PNR_FULL_MASK, a, ofs);
+                    b += __shfl_xor_sync(PNR_FULL_MASK, b, ofs);
+                }
+                if (lane == 0) {
+                    atomicAdd(&f_delta[1 + 126 + i], (double)a);
+                    atomicAdd(&f_delta[1 + PNR_OBS_DIM + 126 + i], (double)b);
+                }
+            }
+            if (blockIdx.x == 0 && lane == 0) atomicAdd(&f_delta[0], (double)N);
+        }
     }
     if (part == 3 && lane == 0) pnr_bulk_wait_read<0>();      // smem must outlive the copy engine's reads
 #ifdef PNR_TRACE
@@ -381,21 +476,28 @@ static int64_t pnr_grid_for(int64_t n_envs, int envs_per_cta, int resident) {
 }
 
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions, float* obs,
-                            float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, cudaStream_t stream) {
-    typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t);
-    // the obstacle variant is a separate instantiation: the plain kernel carries no trace of it (a call site alone
-    // cost 40 % at 1M envs through caller-saved register spills)
+                            float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, const float* f_applied,
+                            double* f_delta, float f_clip, cudaStream_t stream) {
+    typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, const float*,
+                         double*, float);
+    // the obstacle variant and the fused normaliser are separate instantiations: the plain kernel carries no trace of
+    // them (a call site alone cost 40 % at 1M envs through caller-saved register spills)
     static Kern kernels[2][2][2] = {
-        {{pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_TERMINAL, false>, pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_TERMINAL, true>},
-         {pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_AUTORESET, false>, pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_AUTORESET, true>}},
-        {{pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_TERMINAL, false>, pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_TERMINAL, true>},
-         {pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_AUTORESET, false>, pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_AUTORESET, true>}}};
-    static int grids[PNR_MAX_DEVICES][2][2][2] = {};  // cudaFuncSetAttribute is per device
+        {{pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_TERMINAL, false, false>, pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_TERMINAL, true, false>},
+         {pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_AUTORESET, false, false>, pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_AUTORESET, true, false>}},
+        {{pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_TERMINAL, false, false>, pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_TERMINAL, true, false>},
+         {pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_AUTORESET, false, false>, pnr_step_kernel<PNR_ARITH_LEGACY64, PNR_OBS_AUTORESET, true, false>}}};
+    static Kern fused[2] = {pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_TERMINAL, false, true>,
+                            pnr_step_kernel<PNR_ARITH_F32, PNR_OBS_TERMINAL, true, true>};
+    static int grids[PNR_MAX_DEVICES][2][2][2][2] = {};  // cudaFuncSetAttribute is per device
     const int obst = p.n_obstacles > 0 ? 1 : 0;
-    Kern k = kernels[arith][obs_mode][obst];
-    int& resident = grids[device % PNR_MAX_DEVICES][arith][obs_mode][obst];
+    const int filt = f_applied != nullptr ? 1 : 0;
+    if (filt && (arith != PNR_ARITH_F32 || obs_mode != PNR_OBS_TERMINAL)) return cudaErrorInvalidValue;
+    Kern k = filt ? fused[obst] : kernels[arith][obs_mode][obst];
+    const size_t smem = filt ? PNR_STEP_SMEM_FILTER : PNR_STEP_SMEM;
+    int& resident = grids[device % PNR_MAX_DEVICES][arith][obs_mode][obst][filt];
     if (resident == 0) {
-        cudaError_t e = pnr_prepare(k, PNR_STEP_SMEM, &resident);
+        cudaError_t e = pnr_prepare(k, smem, &resident);
         if (e != cudaSuccess) return e;
     }
     // Resident CTAs per SM, measured on B200 (profiles/r01_v4_cta_sweep.md): long grid-stride runs stream best with
@@ -408,7 +510,8 @@ cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_m
     if (const char* e = getenv("PNR_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // developer knob
     int cap = per_sm * dev_sms < resident ? per_sm * dev_sms : resident;
     const int64_t grid = pnr_grid_for(p.n_envs, PNR_TILE_ENVS, cap);
-    k<<<(unsigned)grid, PNR_STEP_THREADS, PNR_STEP_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick);
+    k<<<(unsigned)grid, PNR_STEP_THREADS, smem, stream>>>(p, state, actions, obs, reward, done, stats, tick, f_applied, f_delta,
+                                                          f_clip);
     return cudaGetLastError();
 }
 

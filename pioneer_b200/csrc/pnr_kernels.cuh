@@ -340,6 +340,11 @@ __device__ __forceinline__ void pnr_pack_obs_dyn(const PnrParams& p, float* __re
     }
 }
 
+// the observation normaliser's element map: clip((x - mean) * inv_std, +-clip)   (pnr_filter.cu, fused step kernel)
+__device__ __forceinline__ float pnr_normalise(float x, float mean, float inv_std, float clip) {
+    return fminf(fmaxf((x - mean) * inv_std, -clip), clip);
+}
+
 // ---- per-joint column groups for the step kernel's joint warps (joint j owns columns j, 6+j, ..., 120+j) ----
 __device__ __forceinline__ void pnr_pack_joint_const(const PnrParams& p, float* __restrict__ row, int j) {
     row[18 + j] = p.r_lo[j];   row[24 + j] = p.cos_r_lo[j];  row[30 + j] = p.sin_r_lo[j];

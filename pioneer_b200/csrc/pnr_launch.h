@@ -9,6 +9,10 @@
 #define PNR_STEP_MIN_CTAS 6                                                  // 24 warps / SM, <= 85 registers: no spills (8 CTAs spill)
 #endif
 #define PNR_STEP_BUFS 2                                                      // observation tile buffers per CTA (producer / consumer pipeline)
+#define PNR_STEP_MIN_CTAS_FILTER 4                                           // fused normaliser: 39.9 KB of shared memory per CTA, <= 128 registers
+#define PNR_FSCRATCH_STRIDE 19                                               // raw r | cos r | sin r per env (18 floats, odd stride)
+#define PNR_FSCRATCH_FLOATS (32 * PNR_FSCRATCH_STRIDE)
+#define PNR_STEP_SMEM_FILTER (PNR_STEP_SMEM + PNR_STEP_BUFS * PNR_FSCRATCH_FLOATS * sizeof(float))
 #define PNR_BAR_HEAD 1                                                       // named barrier ids: HEAD[2], DONE[2], FREE[2]
 #define PNR_BAR_DONE 3
 #define PNR_BAR_FREE 5
@@ -16,9 +20,10 @@
 #define PNR_RO_SMEM (PNR_STEP_WARPS * 32 * PNR_OBS_DIM * sizeof(float))      // reset/observe: one tile per warp
 #define PNR_MAX_DEVICES 16
 
+// f_applied != NULL selects the fused-normaliser instantiation (float32, terminal observations only); f_delta may be NULL
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions,
                             float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick,
-                            cudaStream_t stream);
+                            const float* f_applied, double* f_delta, float f_clip, cudaStream_t stream);
 cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode, float4* state, const float* actions,
                                     float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick,
                                     cudaStream_t stream);

@@ -21,12 +21,23 @@ from .batched_env import OBS_DIM, BatchedPioneerEnv
 
 
 class MeanStdObsFilter:
-    def __init__(self, env: BatchedPioneerEnv, clip: float = 10.0, demean: bool = True, destd: bool = True):
+    def __init__(self, env: BatchedPioneerEnv, clip: float = 10.0, demean: bool = True, destd: bool = True,
+                 fused: bool = False, update: bool = True):
+        """``fused=True``: the env's step kernel itself normalises the observations it writes and pushes their raw values
+        into the statistics (pnr_filter_fuse) -- ``env.step_tensor`` then returns normalised observations and this
+        object is only needed for ``sync()``; the first observations of a run (``env.reset()``) still go through
+        ``__call__``.  Kinematic mode, float32 arithmetic, terminal observations only."""
         self.env = env
         self._lib, self._h = env._lib, env._h
-        self.clip, self.demean, self.destd = float(clip), bool(demean), bool(destd)
+        self.clip, self.demean, self.destd, self.fused = float(clip), bool(demean), bool(destd), bool(fused)
         with torch.cuda.device(env.device):
             _cabi.check(self._lib.pnr_filter_configure(self._h, self.clip, int(demean), int(destd)), "pnr_filter_configure")
+            if fused:
+                _cabi.check(self._lib.pnr_filter_fuse(self._h, 1, int(update)), "pnr_filter_fuse")
+
+    def set_fused(self, on: bool, update: bool = True) -> None:
+        _cabi.check(self._lib.pnr_filter_fuse(self._h, int(on), int(update)), "pnr_filter_fuse")
+        self.fused = bool(on)
 
     def __call__(self, obs: torch.Tensor, update: bool = True, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         """Normalise ``obs`` [n, 137] (float32, on the env's device); ``out`` defaults to in-place."""

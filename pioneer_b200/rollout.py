@@ -43,11 +43,12 @@ class GaussianMlpPolicy(nn.Module):
 
 class RolloutWorker:
     def __init__(self, env: BatchedPioneerEnv, fragment_length: int = 8, policy: Optional[nn.Module] = None,
-                 use_filter: bool = True, seed: int = 0, policy_dtype=torch.bfloat16):
+                 use_filter: bool = True, seed: int = 0, policy_dtype=torch.bfloat16, fused_filter: bool = True):
         self.env, self.T = env, int(fragment_length)
         dev, n = env.device, env.n_envs
         self.policy = (policy or GaussianMlpPolicy(dtype=policy_dtype)).to(dev)
-        self.filter = MeanStdObsFilter(env) if use_filter else None
+        self.fused = bool(use_filter and fused_filter)          # the step kernel normalises and pushes statistics itself
+        self.filter = MeanStdObsFilter(env, fused=self.fused) if use_filter else None
         self.gen = torch.Generator(device=dev).manual_seed(seed)
         self.a_max = torch.as_tensor(env.a_max, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
@@ -77,7 +78,7 @@ class RolloutWorker:
             self.logp[t] = (-0.5 * noise.pow(2) - log_std).sum(-1)
             torch.mul(torch.tanh(raw), self.a_max, out=self.actions[t])          # squash into the action space
             env.step_tensor(self.actions[t], out=(self.obs[t + 1], self.reward[t], self.flags[t]))
-            if self.filter is not None:
+            if self.filter is not None and not self.fused:
                 self.filter(self.obs[t + 1])                                      # push + normalise in place
         return dict(obs=self.obs[:self.T], next_obs=self.obs[1:], actions=self.actions, logp=self.logp,
                     reward=self.reward, done=(self.flags & 1).bool(), truncated=(self.flags & 2).bool())

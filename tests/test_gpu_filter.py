@@ -80,3 +80,41 @@ def test_filter_large_batch_matches_torch():
     moving = ref.std(0, unbiased=True) > 1e-3
     assert torch.allclose(y[:, moving].double(), want[:, moving], atol=1e-4)
     env.close()
+
+
+@pytest.mark.parametrize("n", [1000, 70000])
+def test_fused_step_normaliser_equals_the_two_pass_path(n):
+    """pnr_filter_fuse: the step kernel writes normalised observations and pushes the statistics itself; same numbers
+    as pnr_step followed by pnr_filter_apply (normalised values bit for bit; statistics to float rounding)."""
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    from pioneer_b200.obs_filter import MeanStdObsFilter
+    a = BatchedPioneerEnv(n, seed=4, batch_config=BatchConfig(max_episode_steps=6))
+    b = BatchedPioneerEnv(n, seed=4, batch_config=BatchConfig(max_episode_steps=6))
+    fa, fb = MeanStdObsFilter(a), MeanStdObsFilter(b, fused=True)
+    g = torch.Generator(device="cuda").manual_seed(1)
+    a_max = torch.as_tensor(a.a_max).cuda()
+    for it in range(3):
+        for t in range(4):
+            act = (torch.rand((n, 6), device="cuda", generator=g) * 2 - 1) * a_max
+            oa, ra, fl_a = a.step_tensor(act)
+            ya = fa(oa.clone())
+            ob, rb, fl_b = b.step_tensor(act)                  # already normalised
+            assert torch.equal(ra, rb) and torch.equal(fl_a, fl_b)
+            if it == 0:                                        # same applied statistics on both sides: bit for bit
+                assert torch.equal(ya, ob), (t, float((ya - ob).abs().max()))
+            else:                                              # the two accumulators differ by float rounding after a sync
+                assert torch.allclose(ya, ob, rtol=0, atol=2e-5), (it, t, float((ya - ob).abs().max()))
+        fa.sync(); fb.sync()
+        assert fa.n == fb.n == n * 4 * (it + 1)
+        np.testing.assert_allclose(fb.mean, fa.mean, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(fb.var, fa.var, rtol=1e-4, atol=1e-8)
+    # the env state itself is untouched by the normalisation
+    sa, sb = a.state(), b.state()
+    assert torch.equal(sa["r"], sb["r"]) and torch.equal(sa["potential"], sb["potential"])
+    # unsupported combinations are refused loudly
+    from pioneer_b200 import _cabi
+    c = BatchedPioneerEnv(64, batch_config=BatchConfig(obs_mode="autoreset"))
+    with pytest.raises(_cabi.PioneerB200Error):
+        MeanStdObsFilter(c, fused=True)
+    for e in (a, b, c):
+        e.close()
