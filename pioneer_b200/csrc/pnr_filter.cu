@@ -75,15 +75,27 @@ pnr_filter_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t
             // float64 accumulation (B200 has the FP64 rate for 2 DFMA per element of an HBM-bound stream): before the
             // first synchronisation the applied mean is 0, and sum(x^2) - sum(x)^2 / n of a constant column must
             // cancel to ~0, which float32 partial sums do not deliver
-#pragma unroll 8
-            for (int r = 0; r < rows; ++r) {
-                const float x = tile[r * PNR_OBS_DIM + tid];
-                const float d = x - mean;
+            double s[4] = {0.0, 0.0, 0.0, 0.0}, q[4] = {0.0, 0.0, 0.0, 0.0};   // four independent FP64 chains
+            int r = 0;
+            for (; r + 3 < rows; r += 4) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float d = tile[(r + k) * PNR_OBS_DIM + tid] - mean;
+                    const double dd = (double)d;
+                    s[k] += dd;
+                    q[k] = fma(dd, dd, q[k]);
+                    if (normalize) tile[(r + k) * PNR_OBS_DIM + tid] = fminf(fmaxf(d * inv_std, -clip), clip);
+                }
+            }
+            for (; r < rows; ++r) {
+                const float d = tile[r * PNR_OBS_DIM + tid] - mean;
                 const double dd = (double)d;
-                acc_s += dd;
-                acc_q = fma(dd, dd, acc_q);
+                s[0] += dd;
+                q[0] = fma(dd, dd, q[0]);
                 if (normalize) tile[r * PNR_OBS_DIM + tid] = fminf(fmaxf(d * inv_std, -clip), clip);
             }
+            acc_s += (s[0] + s[1]) + (s[2] + s[3]);
+            acc_q += (q[0] + q[1]) + (q[2] + q[3]);
         }
         if (normalize || out != in) {
             pnr_fence_async_smem();

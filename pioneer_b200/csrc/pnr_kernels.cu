@@ -208,14 +208,24 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                 __syncwarp();
                 if (lane < 30) {
                     float* colp = tile + f_col;
-#pragma unroll 8
-                    for (int r = 0; r < rows_valid; ++r) {
-                        const float d = colp[r * PNR_OBS_DIM] - f_mean;
-                        const double dd = (double)d;
-                        f_sum += dd;
-                        f_sq = fma(dd, dd, f_sq);
-                        colp[r * PNR_OBS_DIM] = fminf(fmaxf(d * f_inv, -f_clip), f_clip);
+                    double s1 = 0.0, q1 = 0.0;                 // second accumulator pair: two independent FP64 chains
+                    int r = 0;
+#pragma unroll 4
+                    for (; r + 1 < rows_valid; r += 2) {
+                        const float d0 = colp[r * PNR_OBS_DIM] - f_mean, d1 = colp[(r + 1) * PNR_OBS_DIM] - f_mean;
+                        const double e0 = (double)d0, e1 = (double)d1;
+                        f_sum += e0; f_sq = fma(e0, e0, f_sq);
+                        s1 += e1; q1 = fma(e1, e1, q1);
+                        colp[r * PNR_OBS_DIM] = fminf(fmaxf(d0 * f_inv, -f_clip), f_clip);
+                        colp[(r + 1) * PNR_OBS_DIM] = fminf(fmaxf(d1 * f_inv, -f_clip), f_clip);
                     }
+                    if (r < rows_valid) {
+                        const float d0 = colp[r * PNR_OBS_DIM] - f_mean;
+                        const double e0 = (double)d0;
+                        f_sum += e0; f_sq = fma(e0, e0, f_sq);
+                        colp[r * PNR_OBS_DIM] = fminf(fmaxf(d0 * f_inv, -f_clip), f_clip);
+                    }
+                    f_sum += s1; f_sq += q1;
                 }
             }
         } else {
