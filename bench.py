@@ -60,9 +60,10 @@ def parse_args():
     ap.add_argument("--envs-per-gpu", type=int, default=65536)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-sweep", action="store_true", help="skip the env-count sweep (N=1 only)")
-    ap.add_argument("--flush", default="write", choices=["write", "write+read"],
+    ap.add_argument("--flush", default="write", choices=["write", "write+read", "none"],
                     help="L2 flush between timed steps: 512 MiB memset, optionally followed by a 512 MiB read sweep "
-                         "(leaves the L2 full of CLEAN lines instead of dirty ones)")
+                         "(leaves the L2 full of CLEAN lines instead of dirty ones); 'none' is for profiler launch lists "
+                         "only (the number it prints is L2-warm and is not a bench value)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-steps-per-proc", type=int, default=0,
                     help="reference arm: env-steps per process per bench step (0 = sized for ~20 s in total)")
@@ -380,6 +381,9 @@ def ours_arm(args):
     if args.flush == "write":
         def flush():
             flush_buf.zero_()
+    elif args.flush == "none":
+        def flush():
+            pass
     else:
         flush_src = torch.zeros(L2_FLUSH_BYTES // 4, dtype=torch.float32, device=device)
 
@@ -460,9 +464,10 @@ def ours_arm(args):
                                "TimeLimit 500, in-kernel auto-reset, uniform random actions in [-a_max, a_max]",
                    "envs_per_gpu": n, "total_envs": total_envs, "mode": "kinematic (the reference env)",
                    "arith": "f32", "obs": "float32[N,137] terminal observations, 8-slot rollout ring",
-                   "l2": f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB memset"
-                         + (" then a 512 MiB read sweep" if args.flush != "write" else "") + ", untimed); each step "
-                         "timed by its own CUDA-event pair on the launching stream",
+                   "l2": ("NOT FLUSHED (profiling run, not a bench value); each step " if args.flush == "none" else
+                          f"flushed between timed steps ({L2_FLUSH_BYTES >> 20} MiB memset"
+                          + (" then a 512 MiB read sweep" if args.flush != "write" else "") + ", untimed); each step ")
+                         + "timed by its own CUDA-event pair on the launching stream",
                    "parallelism": f"env-sharded x{world}, no data-path collective; one stats all-reduce per iteration"},
         "substeps_per_sec": value * FRAME_SKIP,
         "timing_floor_ms": floor_ms,
