@@ -408,3 +408,49 @@ def test_deep_grid_stride_pipeline_vs_c_oracle(n):
     for k in ("r", "v", "a", "t"):
         assert np.array_equal(sa[k].cpu().numpy(), sc[k]), k
     a.close(); b.close()
+
+
+def test_non_finite_and_degenerate_actions_follow_the_reference_arithmetic():
+    """The reference stores the action unclipped (pioneer_knm_env.py:144) and feeds it to the next step's integrator:
+    NaN propagates through every comparison, +-inf saturates the velocity with a zero first phase, a = -eps makes the
+    divisor of the saturation time exactly zero.  Same bits as the oracle, NaN for NaN."""
+    n = 64
+    chain = oracle_chain()
+    ob = OracleBatch(chain, n, OracleConfig(max_episode_steps=0), arith="np2", seed=8, auto_reset=False)
+    env = make_env(n, max_episode_steps=0, auto_reset=False, seed=8)
+    rng = np.random.default_rng(0)
+    eps32 = np.float32(1e-5)
+    specials = np.array([np.nan, np.inf, -np.inf, 3e38, -3e38, -eps32, 0.0, -0.0, 1e-40, 1.2e5, -1.2e5], np.float32)
+    for t in range(8):
+        act = (rng.uniform(-1, 1, size=(n, 6)) * env.a_max).astype(np.float32)
+        if t in (1, 4):                                       # sprinkle the special values over the batch
+            pick = rng.integers(0, len(specials), size=(n, 6))
+            mask = rng.random((n, 6)) < 0.5
+            act = np.where(mask, specials[pick], act).astype(np.float32)
+        with np.errstate(all="ignore"):
+            o_obs, o_rew, o_flags = ob.step(act)
+        obs, rew, flags = env.step_tensor(torch.as_tensor(act).cuda())
+        s, os_ = env.state(), ob.state()
+        for k in ("r", "v", "a"):
+            got, want = s[k].cpu().numpy(), os_[k]
+            assert np.array_equal(got, want, equal_nan=True), (k, t)
+            assert np.array_equal(np.signbit(got[want == 0]), np.signbit(want[want == 0])), (k, t)   # signed zeros too
+        assert np.array_equal(flags.cpu().numpy(), o_flags), t
+        o = obs.cpu().numpy().astype(np.float64)
+        # NaN exactly where the reference has it -- except that the oracle's Rodrigues FK turns the WHOLE pointer into
+        # NaN when one joint angle is NaN, while the kernel's axis-aligned rotations leave the coordinate along that
+        # axis finite (distance, potential and reward are NaN on both sides)
+        strict = np.r_[0:126, 129:132, 135:137]
+        assert np.array_equal(np.isnan(o[:, strict]), np.isnan(o_obs[:, strict])), t
+        loose = np.r_[126:129, 132:135]
+        assert not (np.isnan(o[:, loose]) & ~np.isnan(o_obs[:, loose])).any(), t
+        o_obs = np.where(np.isnan(o), np.nan, o_obs)
+        o = np.where(np.isnan(o_obs), np.nan, o)
+        inf = np.isinf(o_obs)
+        assert np.array_equal(o[inf], o_obs[inf]), t                                 # +-inf where the reference has it
+        fin = np.isfinite(o_obs)
+        tol = 1e-3 + 1e-6 * np.abs(o_obs[fin])                                      # stored actions reach 3e38
+        assert (np.abs(o[fin] - o_obs[fin]) <= tol).all(), t
+        assert np.array_equal(np.isnan(rew.cpu().numpy()), np.isnan(o_rew))
+    assert np.isnan(env.state()["r"].cpu().numpy()).any() and np.isfinite(env.state()["r"].cpu().numpy()).any()
+    env.close()
