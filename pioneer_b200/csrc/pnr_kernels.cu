@@ -234,7 +234,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             const float* head = FILTER ? srow : row;           // raw r | cos r | sin r of this env
 #pragma unroll
             for (int i = 0; i < PNR_DOF; ++i) { o.cs[i] = head[6 + i]; o.sn[i] = head[12 + i]; }
-            float tgt[3] = {c4.x, c4.y, c4.z};
+            const float tgt[3] = {c4.x, c4.y, c4.z};
             int32_t t = __float_as_int(c4.w);
             const float pot_old = c2.x;
             float ep_ret = c2.y;
@@ -243,10 +243,14 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             o.dist = sqrtf(fmaf(dx, dx, fmaf(dy, dy, dz * dz)));
             bool reached = o.dist < p.done_distance;
             if (fabsf(o.dist - p.done_distance) < p.done_band) {   // decide in float64 where float32 could flip it
-                float rr[PNR_DOF];
+                PnrBandIn in;
 #pragma unroll
-                for (int i = 0; i < PNR_DOF; ++i) rr[i] = head[i];
-                pnr_fk_tip_f64(p, rr, tgt, o.ptr, o.dist, reached);
+                for (int i = 0; i < PNR_DOF; ++i) in.r[i] = head[i];
+                in.tgt[0] = tgt[0]; in.tgt[1] = tgt[1]; in.tgt[2] = tgt[2];
+                const PnrBandOut bo = pnr_fk_band_f64(p, in);
+                o.ptr[0] = bo.ptr[0]; o.ptr[1] = bo.ptr[1]; o.ptr[2] = bo.ptr[2];
+                o.dist = bo.dist;
+                reached = bo.within != 0;
             }
             const float pot_new = pnr_potential(p, o.dist);
             // (potential - old_potential) + (-penalty_step) + (award_done | 0), pioneer_knm_env.py:162-165

@@ -165,11 +165,31 @@ __device__ __forceinline__ void pnr_fk_stage(const PnrParams& p, int j, float sn
     x += p.origin_xyz[j][0]; y += p.origin_xyz[j][1]; z += p.origin_xyz[j][2];
 }
 
+// rotation of (x, y, z) about a coordinate axis known at compile time, then the joint origin translation
+template <int CODE>
+__device__ __forceinline__ void pnr_fk_stage_fixed(const PnrParams& p, int j, float s, float c, float& x, float& y, float& z) {
+    if (CODE == PNR_AXIS_X) { const float ny = fmaf(c, y, -s * z), nz = fmaf(s, y, c * z); y = ny; z = nz; }
+    else if (CODE == PNR_AXIS_Y) { const float nx = fmaf(c, x, s * z), nz = fmaf(-s, x, c * z); x = nx; z = nz; }
+    else { const float nx = fmaf(c, x, -s * y), ny = fmaf(s, x, c * y); x = nx; y = ny; }
+    x += p.origin_xyz[j][0]; y += p.origin_xyz[j][1]; z += p.origin_xyz[j][2];
+}
+
 __device__ __forceinline__ void pnr_fk_tip(const PnrParams& p, const float (&sn)[PNR_DOF], const float (&cs)[PNR_DOF],
                                            float (&out)[3]) {
     float x = p.tip_xyz[0], y = p.tip_xyz[1], z = p.tip_xyz[2];
+    if (p.chain_kind == 1) {
+        // the shipped robot (axes Z Y Y X Y X, positive, no origin rotations; detected by pnr_create): one uniform
+        // branch instead of three per joint on the task warp's critical path.  Same operations, same results.
+        pnr_fk_stage_fixed<PNR_AXIS_X>(p, 5, sn[5], cs[5], x, y, z);
+        pnr_fk_stage_fixed<PNR_AXIS_Y>(p, 4, sn[4], cs[4], x, y, z);
+        pnr_fk_stage_fixed<PNR_AXIS_X>(p, 3, sn[3], cs[3], x, y, z);
+        pnr_fk_stage_fixed<PNR_AXIS_Y>(p, 2, sn[2], cs[2], x, y, z);
+        pnr_fk_stage_fixed<PNR_AXIS_Y>(p, 1, sn[1], cs[1], x, y, z);
+        pnr_fk_stage_fixed<PNR_AXIS_Z>(p, 0, sn[0], cs[0], x, y, z);
+    } else {
 #pragma unroll
-    for (int j = PNR_DOF - 1; j >= 0; --j) pnr_fk_stage(p, j, sn[j], cs[j], x, y, z);
+        for (int j = PNR_DOF - 1; j >= 0; --j) pnr_fk_stage(p, j, sn[j], cs[j], x, y, z);
+    }
     out[0] = x; out[1] = y; out[2] = z;
 }
 
@@ -233,12 +253,16 @@ static __device__ __noinline__ float pnr_contact_depth(const PnrParams& p, PnrSi
 // float64 twin, only for envs whose float32 distance falls inside the done band: the reference
 // evaluates `distance < done_distance` in double (pioneer_knm_env.py:155-160), so the done mask is
 // decided in double exactly where float32 could flip it.  Rare => deliberately not inlined.
-static __device__ __noinline__ void pnr_fk_tip_f64(const PnrParams& p, const float (&r)[PNR_DOF], const float (&tgt)[3],
-                                             float (&ptr_out)[3], float& dist_out, bool& within) {
+// Arguments and results travel BY VALUE: arrays passed by reference to a non-inlined function would have to live
+// in local memory on every step, taken or not (18 local stores per tile in the task warp before this).
+struct PnrBandIn { float r[PNR_DOF]; float tgt[3]; };
+struct PnrBandOut { float ptr[3]; float dist; int within; };
+
+static __device__ __noinline__ PnrBandOut pnr_fk_band_f64(const PnrParams& p, PnrBandIn in) {
     double x = p.tip_xyz64[0], y = p.tip_xyz64[1], z = p.tip_xyz64[2];
     for (int j = PNR_DOF - 1; j >= 0; --j) {
         double s, c;
-        sincos((double)r[j], &s, &c);
+        sincos((double)in.r[j], &s, &c);
         const double kx = p.axis64[j][0], ky = p.axis64[j][1], kz = p.axis64[j][2];
         const double kp = (kx * x + ky * y + kz * z) * (1.0 - c);
         const double nx = x * c + (ky * z - kz * y) * s + kx * kp;
@@ -249,11 +273,26 @@ static __device__ __noinline__ void pnr_fk_tip_f64(const PnrParams& p, const flo
         y = R[3] * nx + R[4] * ny + R[5] * nz + p.origin_xyz64[j][1];
         z = R[6] * nx + R[7] * ny + R[8] * nz + p.origin_xyz64[j][2];
     }
-    const double dx = (double)tgt[0] - x, dy = (double)tgt[1] - y, dz = (double)tgt[2] - z;
+    const double dx = (double)in.tgt[0] - x, dy = (double)in.tgt[1] - y, dz = (double)in.tgt[2] - z;
     const double d = sqrt(dx * dx + dy * dy + dz * dz);
-    ptr_out[0] = (float)x; ptr_out[1] = (float)y; ptr_out[2] = (float)z;
-    dist_out = (float)d;
-    within = d < p.done_distance64;
+    PnrBandOut o;
+    o.ptr[0] = (float)x; o.ptr[1] = (float)y; o.ptr[2] = (float)z;
+    o.dist = (float)d;
+    o.within = d < p.done_distance64 ? 1 : 0;
+    return o;
+}
+
+// convenience wrapper for the thread-per-env kernels (not the step kernel's task warp)
+__device__ __forceinline__ void pnr_fk_tip_f64(const PnrParams& p, const float (&r)[PNR_DOF], const float (&tgt)[3],
+                                               float (&ptr_out)[3], float& dist_out, bool& within) {
+    PnrBandIn in;
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) in.r[i] = r[i];
+    in.tgt[0] = tgt[0]; in.tgt[1] = tgt[1]; in.tgt[2] = tgt[2];
+    const PnrBandOut o = pnr_fk_band_f64(p, in);
+    ptr_out[0] = o.ptr[0]; ptr_out[1] = o.ptr[1]; ptr_out[2] = o.ptr[2];
+    dist_out = o.dist;
+    within = o.within != 0;
 }
 
 // sincos of the joint angles + tip position + distance to the target for the current r
