@@ -47,9 +47,9 @@ DYN_FLOP_PER_ENV_STEP = 2 * 8056 + 4734 + 3733
 DYN_FP_INSTR_PER_ENV_STEP = 8056 + 4734 + 3733
 FP32_PEAK_TFLOPS = 72.6
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of pnr_step_kernel from the committed `ncu --set full`
-# captures (profiles/r01_v3_step_65536.md, profiles/r01_v3_step_1m.md).  At 65,536 envs most of the 36 MB of
+# captures (profiles/r01_v5_step_65536.md, profiles/r01_v5_step_1m.md).  At 65,536 envs most of the 36 MB of
 # observations is still dirty in the 126 MB L2 when the kernel ends, so DRAM writes read far below the algorithmic bytes.
-NCU_TRAFFIC_BYTES = {65536: 7.91e6 + 0.63e6, 1048576: 126.2e6 + 623.1e6}      # profiles/r01_v4_step_{65536,1m}.md
+NCU_TRAFFIC_BYTES = {65536: 7.93e6 + 0.26e6, 1048576: 128.9e6 + 622.6e6}      # profiles/r01_v5_step_{65536,1m}.md
 
 
 def parse_args():
