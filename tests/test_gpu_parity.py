@@ -454,3 +454,41 @@ def test_non_finite_and_degenerate_actions_follow_the_reference_arithmetic():
         assert np.array_equal(np.isnan(rew.cpu().numpy()), np.isnan(o_rew))
     assert np.isnan(env.state()["r"].cpu().numpy()).any() and np.isfinite(env.state()["r"].cpu().numpy()).any()
     env.close()
+
+
+@pytest.mark.parametrize("case", range(4))
+def test_randomised_configs_vs_c_oracle(case):
+    """Every knob of PioneerKinematicConfig / SimulationConfig / TimeLimit travels through pnr_config into the kernel:
+    randomised settings (limits ratios, done distance, reward shaping, target box, timestep, frame_skip) against the C
+    oracle on the same seeds and actions."""
+    from oracle.c_oracle import COracleBatch
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv, PioneerKinematicConfig, SimulationConfig
+    rng = np.random.default_rng(1000 + case)
+    lo = rng.uniform([-5, -12, 0], [10, -2, 3])
+    hi = lo + rng.uniform(1, 12, size=3)
+    kw = dict(max_v_to_r=float(rng.uniform(0.5, 4)), max_a_to_v=float(rng.uniform(2, 20)),
+              done_distance=float(rng.uniform(0.05, 6.0)), award_max=float(rng.uniform(50, 200)),
+              award_done=float(rng.uniform(0, 20)), award_potential_slope=float(rng.uniform(2, 30)),
+              penalty_step=float(rng.uniform(0, 0.1)), target_lo=tuple(lo), target_hi=tuple(hi))
+    timestep, frame_skip, limit = float(rng.uniform(1 / 480, 1 / 60)), int(rng.integers(1, 20)), int(rng.integers(3, 12))
+    n, seed = 2048 + case, 40 + case
+    cc = COracleBatch(oracle_chain(), n, OracleConfig(max_episode_steps=limit, timestep=timestep, frame_skip=frame_skip, **kw),
+                      arith="np2", seed=seed, env_id_base=5 * case)
+    env = BatchedPioneerEnv(n, seed=seed, env_id_base=5 * case, pioneer_config=PioneerKinematicConfig(**kw),
+                            simulation_config=SimulationConfig(timestep=timestep, frame_skip=frame_skip),
+                            batch_config=BatchConfig(max_episode_steps=limit))
+    assert np.array_equal(env.a_max, cc.a_max) and np.array_equal(env.v_max, cc.v_max)
+    reached = 0
+    for t in range(30):
+        act = (rng.uniform(-1, 1, size=(n, 6)) * env.a_max).astype(np.float32)
+        obs, rew, flags = env.step_tensor(torch.as_tensor(act).cuda())
+        o_obs, o_rew, o_flags = cc.step(act)
+        assert np.array_equal(flags.cpu().numpy(), o_flags), (case, t)
+        reached += int(((o_flags & 1) != 0).sum() - ((o_flags & 2) != 0).sum())
+        o = obs.cpu().numpy().astype(np.float64)
+        assert np.array_equal(o[:, VALUE_COLS], o_obs[:, VALUE_COLS]), (case, t)
+        assert np.abs(o[:, POS_COLS] - o_obs[:, POS_COLS]).max() <= POS_TOL
+        assert np.abs(rew.cpu().numpy() - o_rew).max() <= REW_TOL * max(1.0, kw["award_max"] / 100)
+    st = env.episode_stats()
+    assert st["episodes"] == cc.stats[0] and st["reached_target"] == cc.stats[7]
+    env.close()

@@ -72,3 +72,30 @@ def test_c_oracle_matches_python_oracle(arith, obs_mode):
         assert np.array_equal(o1[:, VALUE_COLS], o2[:, VALUE_COLS])
     np.testing.assert_allclose(py.stats, cc.stats, rtol=1e-12)
     assert py.stats[0] == n * (steps // 9)
+
+
+def test_c_oracle_matches_python_oracle_on_random_configs():
+    """Property check (hypothesis): for random reward / limit / timing knobs and random (also out-of-range) actions the two
+    independent restatements produce the same joint state bit for bit and the same done masks."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=25, deadline=None)
+    @given(st.floats(0.5, 4.0), st.floats(2.0, 20.0), st.floats(0.05, 8.0), st.floats(0.0, 0.1), st.integers(1, 20),
+           st.integers(2, 9), st.integers(0, 2 ** 31), st.sampled_from(["np2", "legacy"]))
+    def check(max_v_to_r, max_a_to_v, done_distance, penalty_step, frame_skip, limit, seed, arith):
+        cfg = OracleConfig(max_v_to_r=max_v_to_r, max_a_to_v=max_a_to_v, done_distance=done_distance,
+                           penalty_step=penalty_step, frame_skip=frame_skip, max_episode_steps=limit)
+        n = 6
+        py = OracleBatch(CHAIN, n, cfg, arith=arith, seed=seed)
+        cc = COracleBatch(CHAIN, n, cfg, arith=arith, seed=seed)
+        rng = np.random.default_rng(seed)
+        for t in range(12):
+            act = (rng.uniform(-1, 1, size=(n, 6)) * cc.a_max * rng.choice([0.01, 1.0, 25.0])).astype(np.float32)
+            _, r1, f1 = py.step(act)
+            _, r2, f2 = cc.step(act)
+            assert np.array_equal(f1, f2)
+            s1, s2 = py.state(), cc.state()
+            assert np.array_equal(s1["r"], s2["r"]) and np.array_equal(s1["v"], s2["v"]) and np.array_equal(s1["t"], s2["t"])
+            np.testing.assert_allclose(r1, r2, rtol=0, atol=1e-10)
+
+    check()
