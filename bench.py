@@ -368,6 +368,8 @@ def ours_arm(args):
         raise SystemExit("bench.py: for --gpus N > 1 launch with torch.distributed.run, one rank per GPU")
     device = torch.device("cuda", local_rank)
     torch.cuda.set_device(device)
+    from pioneer_b200.distributed import bind_to_gpu_numa_node
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None    # pinned e2e buffers on the GPU's socket
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         os.environ["NCCL_DEBUG"] = os.environ.get("PNR_NCCL_DEBUG", "WARN")   # keep stdout to the one JSON line
@@ -484,6 +486,7 @@ def ours_arm(args):
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n * DOF * 4,
                 "d2h_bytes_per_step": n * (OBS_DIM * 4 + 4 + 1), "steps": e2e_steps,
                 "api": "BatchedPioneerEnv.step_host -> pnr_step_host (pinned host buffers, copies inside the timed region)",
+                "numa_node_rank0": numa_node,
                 "timer": "host perf_counter around synchronous calls, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES.get(n), "kernel": "pnr_step_kernel<F32,TERMINAL>",

@@ -19,6 +19,32 @@ SUM_SLOTS = (0, 1, 2, 3, 6, 7)
 MAX_SLOTS = (4, 5)
 
 
+def bind_to_gpu_numa_node(device_index: int) -> Optional[int]:
+    """Pin this process to the CPUs of the NUMA node the GPU hangs off, BEFORE any pinned host buffer is allocated, so
+    that the host side of the H2D / D2H copies (pnr_step_host) is local memory.  One rank per GPU on a two-socket box
+    otherwise lands its pinned buffers wherever the scheduler started it.  Returns the node, or None if unknown."""
+    import os
+    try:
+        bus = torch.cuda.get_device_properties(device_index).pci_bus_id
+        dom = getattr(torch.cuda.get_device_properties(device_index), "pci_domain_id", 0)
+        dev = torch.cuda.get_device_properties(device_index).pci_device_id
+        path = f"/sys/bus/pci/devices/{dom:04x}:{bus:02x}:{dev:02x}.0/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        allowed = cpus & set(os.sched_getaffinity(0))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # noqa: BLE001 - sysfs layout / permissions differ between boxes: binding is best effort
+        return None
+
+
 def shard_range(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
     """(env_id_base, n_local): contiguous split, the first ``total % world`` ranks get one more."""
     assert 0 <= rank < world_size and total_envs >= world_size
