@@ -152,6 +152,52 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
         if (c.mode == PNR_MODE_DYNAMIC && !(m_ > 0.0))
             return pnr_fail(PNR_ERR_INVALID, "dynamic mode needs a positive composite mass on every moving frame");
     }
+    {   // tip joint: I^A = own body only, so U = I^A S, d = S^T U and I^a = I^A - U U^T / d do not depend on the state
+        const int j = PNR_DOF - 1;
+        const double m_ = m.body_mass[j];
+        const double* c_ = m.body_com[j];
+        const double* I_ = m.body_inertia[j];
+        const double cc = c_[0] * c_[0] + c_[1] * c_[1] + c_[2] * c_[2];
+        double I3[3][3], H3[3][3], M3[3][3];
+        const double mc[3] = {m_ * c_[0], m_ * c_[1], m_ * c_[2]};
+        for (int a = 0; a < 3; ++a)
+            for (int b = 0; b < 3; ++b) {
+                I3[a][b] = I_[3 * a + b] + m_ * ((a == b ? cc : 0.0) - c_[a] * c_[b]);
+                M3[a][b] = a == b ? m_ : 0.0;
+            }
+        H3[0][0] = 0; H3[0][1] = -mc[2]; H3[0][2] = mc[1];
+        H3[1][0] = mc[2]; H3[1][1] = 0; H3[1][2] = -mc[0];
+        H3[2][0] = -mc[1]; H3[2][1] = mc[0]; H3[2][2] = 0;
+        double ua[3], ul[3], d = 0;
+        for (int a = 0; a < 3; ++a) {
+            ua[a] = ul[a] = 0;
+            for (int b = 0; b < 3; ++b) { ua[a] += I3[a][b] * m.axis[j][b]; ul[a] += H3[b][a] * m.axis[j][b]; }
+        }
+        for (int a = 0; a < 3; ++a) d += m.axis[j][a] * ua[a];
+        const double dinv = d != 0.0 ? 1.0 / d : 0.0;
+        const int idx[6][2] = {{0, 0}, {0, 1}, {0, 2}, {1, 1}, {1, 2}, {2, 2}};
+        for (int k = 0; k < 6; ++k) {
+            const int a = idx[k][0], b = idx[k][1];
+            p.dyn_tip_I[k] = (float)(I3[a][b] - ua[a] * ua[b] * dinv);
+            p.dyn_tip_M[k] = (float)(M3[a][b] - ul[a] * ul[b] * dinv);
+        }
+        for (int a = 0; a < 3; ++a) {
+            for (int b = 0; b < 3; ++b) p.dyn_tip_H[3 * a + b] = (float)(H3[a][b] - ua[a] * ul[b] * dinv);
+            p.dyn_tip_ua[a] = (float)ua[a];
+            p.dyn_tip_ul[a] = (float)ul[a];
+        }
+        p.dyn_tip_dinv = (float)dinv;
+        // I^a S = 0: for an axis-aligned tip joint (code k) column / row k of I^a and row k of H^a are exact zeros;
+        // the specialised kernel relies on it (pnr_rotk_sym_z), so the rounding residue is cleared
+        const int kt = p.axis_code[j];
+        if (kt != PNR_AXIS_GENERAL)
+            for (int a = 0; a < 3; ++a) {
+                const int lo = a < kt ? a : kt, hi = a < kt ? kt : a;
+                const int sym_index[3][3] = {{0, 1, 2}, {1, 3, 4}, {2, 4, 5}};
+                p.dyn_tip_I[sym_index[lo][hi]] = 0.f;
+                p.dyn_tip_H[3 * kt + a] = 0.f;
+            }
+    }
     // obstacle variant; without a penalty weight there is nothing to compute
     p.contact_penalty = (float)c.contact_penalty;
     p.n_obstacles = (c.contact_penalty != 0.0) ? c.n_obstacles : 0;
@@ -176,6 +222,7 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
         const int origin_axis[PNR_DOF] = {-1, 2, 2, 1, 0, -1};       // the only non-zero origin component (-1: none)
         for (int j = 0; j < PNR_DOF; ++j) {
             match = match && p.axis_code[j] == pattern[j] && p.axis_sign[j] > 0.f && !p.origin_has_rot[j];
+            match = match && std::fabs(m.lower[j]) <= 64.0 && std::fabs(m.upper[j]) <= 64.0;   // pnr_sincos_bounded in the ABA
             for (int k = 0; k < 3; ++k) match = match && (k == origin_axis[j] || m.origin_xyz[j][k] == 0.0);
         }
         p.chain_kind = match ? 1 : 0;
@@ -203,6 +250,20 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
     p.env_id_base = env_id_base;
     p.n_envs = n_envs;
     return PNR_OK;
+}
+
+// Developer / test hook (not part of include/pioneer_b200.h): the parameter block the kernels would receive for this
+// model and configuration, built on the host without touching CUDA.  tests/csrc/aba_check.cu feeds it to the
+// host-compiled dynamics header.  Returns sizeof(PnrParams), or a negative status.
+extern "C" int64_t pnr_debug_build_params(const pnr_model* model, const pnr_config* cfg, int64_t n_envs, void* out,
+                                          int64_t capacity) {
+    if (!model || !cfg) return pnr_fail(PNR_ERR_INVALID, "pnr_debug_build_params: null argument");
+    if (out && capacity >= (int64_t)sizeof(PnrParams)) {
+        float a_max[PNR_DOF];
+        int rc = pnr_build_params(*model, *cfg, n_envs, 0, 0, *static_cast<PnrParams*>(out), a_max);
+        if (rc != PNR_OK) return rc;
+    }
+    return (int64_t)sizeof(PnrParams);
 }
 
 extern "C" int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t n_envs, int64_t env_id_base,

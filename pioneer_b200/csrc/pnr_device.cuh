@@ -47,6 +47,9 @@ struct PnrParams {
     float dyn_mass[PNR_DOF];
     float dyn_tau_max[PNR_DOF];     // effort * torque_scale
     float dyn_damping[PNR_DOF];
+    // the tip body's articulated inertia after its own rank-1 update (I^a = I^A - U U^T / d): constants of the robot,
+    // float64 on the host (pnr_build_params).  I, M symmetric (xx xy xz yy yz zz), H row-major, U = (ua; ul), 1 / d
+    float dyn_tip_I[6], dyn_tip_H[9], dyn_tip_M[6], dyn_tip_ua[3], dyn_tip_ul[3], dyn_tip_dinv;
     float dyn_kp, dyn_kd, dyn_dt, dyn_gravity;
     int32_t dyn_frame_skip, dyn_use_pd;
     int32_t chain_kind;             // 1: axes Z Y Y X Y X, positive, identity origin rotations (the shipped robot)

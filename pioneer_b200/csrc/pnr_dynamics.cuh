@@ -9,29 +9,34 @@
 // is the north_star extension, parity unpinned vs PyBullet; the fact the reference does pin -- zero velocity,
 // gravity and torque leave the state bit-unchanged -- holds exactly (every term is an exact zero).
 #pragma once
-#include "pnr_kernels.cuh"
+#include <cmath>
+#include "pnr_device.cuh"
+#include "pnr_trig.cuh"
+
+// host + device: tests/csrc/aba_check.cu compiles this header for the CPU and checks it against the float64 oracle
+#define PNR_HD __host__ __device__ __forceinline__
 
 struct V3 { float x, y, z; };
 struct Sym3 { float xx, xy, xz, yy, yz, zz; };
 struct Mat3 { float m[9]; };          // row-major
 
-__device__ __forceinline__ V3 v3(float x, float y, float z) { V3 r = {x, y, z}; return r; }
-__device__ __forceinline__ V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
-__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
-__device__ __forceinline__ V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
-__device__ __forceinline__ float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
-__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+PNR_HD V3 v3(float x, float y, float z) { V3 r = {x, y, z}; return r; }
+PNR_HD V3 operator+(V3 a, V3 b) { return v3(a.x + b.x, a.y + b.y, a.z + b.z); }
+PNR_HD V3 operator-(V3 a, V3 b) { return v3(a.x - b.x, a.y - b.y, a.z - b.z); }
+PNR_HD V3 operator*(V3 a, float s) { return v3(a.x * s, a.y * s, a.z * s); }
+PNR_HD float dot(V3 a, V3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
+PNR_HD V3 cross(V3 a, V3 b) {
     return v3(fmaf(a.y, b.z, -a.z * b.y), fmaf(a.z, b.x, -a.x * b.z), fmaf(a.x, b.y, -a.y * b.x));
 }
-__device__ __forceinline__ V3 symmul(const Sym3& s, V3 v) {
+PNR_HD V3 symmul(const Sym3& s, V3 v) {
     return v3(fmaf(s.xx, v.x, fmaf(s.xy, v.y, s.xz * v.z)), fmaf(s.xy, v.x, fmaf(s.yy, v.y, s.yz * v.z)),
               fmaf(s.xz, v.x, fmaf(s.yz, v.y, s.zz * v.z)));
 }
-__device__ __forceinline__ V3 matmul(const Mat3& a, V3 v) {
+PNR_HD V3 matmul(const Mat3& a, V3 v) {
     return v3(fmaf(a.m[0], v.x, fmaf(a.m[1], v.y, a.m[2] * v.z)), fmaf(a.m[3], v.x, fmaf(a.m[4], v.y, a.m[5] * v.z)),
               fmaf(a.m[6], v.x, fmaf(a.m[7], v.y, a.m[8] * v.z)));
 }
-__device__ __forceinline__ V3 matTmul(const Mat3& a, V3 v) {
+PNR_HD V3 matTmul(const Mat3& a, V3 v) {
     return v3(fmaf(a.m[0], v.x, fmaf(a.m[3], v.y, a.m[6] * v.z)), fmaf(a.m[1], v.x, fmaf(a.m[4], v.y, a.m[7] * v.z)),
               fmaf(a.m[2], v.x, fmaf(a.m[5], v.y, a.m[8] * v.z)));
 }
@@ -46,12 +51,12 @@ __device__ __forceinline__ V3 matTmul(const Mat3& a, V3 v) {
 #define PNR_CHAIN_PIONEER 1
 
 template <int CHAIN>
-__device__ __forceinline__ int pnr_code(const PnrParams& p, int j) {
+PNR_HD int pnr_code(const PnrParams& p, int j) {
     if (CHAIN == PNR_CHAIN_PIONEER) return j == 0 ? PNR_AXIS_Z : ((j == 3 || j == 5) ? PNR_AXIS_X : PNR_AXIS_Y);
     return p.axis_code[j];
 }
 template <int CHAIN>
-__device__ __forceinline__ V3 pnr_axis(const PnrParams& p, int j) {
+PNR_HD V3 pnr_axis(const PnrParams& p, int j) {
     if (CHAIN == PNR_CHAIN_PIONEER) {
         const int c = pnr_code<CHAIN>(p, j);
         return v3(c == PNR_AXIS_X ? 1.f : 0.f, c == PNR_AXIS_Y ? 1.f : 0.f, c == PNR_AXIS_Z ? 1.f : 0.f);
@@ -60,7 +65,7 @@ __device__ __forceinline__ V3 pnr_axis(const PnrParams& p, int j) {
 }
 // axis . v,  axis * s,  v x (axis * s),  I axis (a column),  H^T axis (a row): single components when the axis is known
 template <int CHAIN>
-__device__ __forceinline__ float pnr_axis_dot(const PnrParams& p, int j, V3 v) {
+PNR_HD float pnr_axis_dot(const PnrParams& p, int j, V3 v) {
     if (CHAIN == PNR_CHAIN_PIONEER) {
         const int c = pnr_code<CHAIN>(p, j);
         return c == PNR_AXIS_X ? v.x : (c == PNR_AXIS_Y ? v.y : v.z);
@@ -68,7 +73,7 @@ __device__ __forceinline__ float pnr_axis_dot(const PnrParams& p, int j, V3 v) {
     return dot(pnr_axis<CHAIN>(p, j), v);
 }
 template <int CHAIN>
-__device__ __forceinline__ V3 pnr_axis_scaled(const PnrParams& p, int j, float s) {
+PNR_HD V3 pnr_axis_scaled(const PnrParams& p, int j, float s) {
     if (CHAIN == PNR_CHAIN_PIONEER) {
         const int c = pnr_code<CHAIN>(p, j);
         return v3(c == PNR_AXIS_X ? s : 0.f, c == PNR_AXIS_Y ? s : 0.f, c == PNR_AXIS_Z ? s : 0.f);
@@ -76,7 +81,7 @@ __device__ __forceinline__ V3 pnr_axis_scaled(const PnrParams& p, int j, float s
     return pnr_axis<CHAIN>(p, j) * s;
 }
 template <int CHAIN>
-__device__ __forceinline__ V3 pnr_cross_axis(const PnrParams& p, int j, V3 a, float s) {     // a x (axis * s)
+PNR_HD V3 pnr_cross_axis(const PnrParams& p, int j, V3 a, float s) {     // a x (axis * s)
     if (CHAIN == PNR_CHAIN_PIONEER) {
         const int c = pnr_code<CHAIN>(p, j);
         if (c == PNR_AXIS_X) return v3(0.f, a.z * s, -a.y * s);
@@ -86,7 +91,7 @@ __device__ __forceinline__ V3 pnr_cross_axis(const PnrParams& p, int j, V3 a, fl
     return cross(a, pnr_axis<CHAIN>(p, j) * s);
 }
 template <int CHAIN>
-__device__ __forceinline__ V3 pnr_sym_axis(const PnrParams& p, int j, const Sym3& m) {        // m * axis
+PNR_HD V3 pnr_sym_axis(const PnrParams& p, int j, const Sym3& m) {        // m * axis
     if (CHAIN == PNR_CHAIN_PIONEER) {
         const int c = pnr_code<CHAIN>(p, j);
         if (c == PNR_AXIS_X) return v3(m.xx, m.xy, m.xz);
@@ -96,7 +101,7 @@ __device__ __forceinline__ V3 pnr_sym_axis(const PnrParams& p, int j, const Sym3
     return symmul(m, pnr_axis<CHAIN>(p, j));
 }
 template <int CHAIN>
-__device__ __forceinline__ V3 pnr_matT_axis(const PnrParams& p, int j, const Mat3& a) {       // a^T * axis
+PNR_HD V3 pnr_matT_axis(const PnrParams& p, int j, const Mat3& a) {       // a^T * axis
     if (CHAIN == PNR_CHAIN_PIONEER) {
         const int c = pnr_code<CHAIN>(p, j);
         return v3(a.m[3 * c + 0], a.m[3 * c + 1], a.m[3 * c + 2]);
@@ -107,7 +112,7 @@ __device__ __forceinline__ V3 pnr_matT_axis(const PnrParams& p, int j, const Mat
 // origin_j x v.  The shipped robot's joint origins lie on one coordinate axis of the parent frame (joint 0 and 5: zero,
 // 1 and 2: along z, 3: along y, 4: along x; pioneer_knm_6dof.urdf:209-264), so the cross product is two multiplies.
 template <int CHAIN>
-__device__ __forceinline__ V3 pnr_origin_cross(const PnrParams& p, int j, V3 v) {
+PNR_HD V3 pnr_origin_cross(const PnrParams& p, int j, V3 v) {
     if (CHAIN == PNR_CHAIN_PIONEER) {
         if (j == 0 || j == 5) return v3(0.f, 0.f, 0.f);
         if (j == 1 || j == 2) { const float z = p.origin_xyz[j][2]; return v3(-z * v.y, z * v.x, 0.f); }
@@ -120,7 +125,7 @@ __device__ __forceinline__ V3 pnr_origin_cross(const PnrParams& p, int j, V3 v) 
 
 // rotation about joint j's axis by the angle whose (sin, cos) are given; axis-aligned axes cost 4 FMA.
 template <int CHAIN>
-__device__ __forceinline__ V3 pnr_axis_rot(const PnrParams& p, int j, float s, float c, V3 v) {
+PNR_HD V3 pnr_axis_rot(const PnrParams& p, int j, float s, float c, V3 v) {
     const int code = pnr_code<CHAIN>(p, j);
     if (CHAIN != PNR_CHAIN_PIONEER) s *= p.axis_sign[j];
     if (code == PNR_AXIS_X) return v3(v.x, fmaf(c, v.y, -s * v.z), fmaf(s, v.y, c * v.z));
@@ -135,7 +140,7 @@ __device__ __forceinline__ V3 pnr_axis_rot(const PnrParams& p, int j, float s, f
 
 // child -> parent coordinates: R_j v = O_j Rot(axis_j, q_j) v
 template <int CHAIN>
-__device__ __forceinline__ V3 pnr_rot(const PnrParams& p, int j, float s, float c, V3 v) {
+PNR_HD V3 pnr_rot(const PnrParams& p, int j, float s, float c, V3 v) {
     V3 r = pnr_axis_rot<CHAIN>(p, j, s, c, v);
     if (CHAIN != PNR_CHAIN_PIONEER && p.origin_has_rot[j]) {
         const float* O = p.origin_rot[j];
@@ -146,7 +151,7 @@ __device__ __forceinline__ V3 pnr_rot(const PnrParams& p, int j, float s, float 
 
 // parent -> child coordinates: R_j^T v
 template <int CHAIN>
-__device__ __forceinline__ V3 pnr_rot_t(const PnrParams& p, int j, float s, float c, V3 v) {
+PNR_HD V3 pnr_rot_t(const PnrParams& p, int j, float s, float c, V3 v) {
     if (CHAIN != PNR_CHAIN_PIONEER && p.origin_has_rot[j]) {
         const float* O = p.origin_rot[j];
         v = v3(O[0] * v.x + O[3] * v.y + O[6] * v.z, O[1] * v.x + O[4] * v.y + O[7] * v.z, O[2] * v.x + O[5] * v.y + O[8] * v.z);
@@ -156,7 +161,7 @@ __device__ __forceinline__ V3 pnr_rot_t(const PnrParams& p, int j, float s, floa
 
 // B' = R B R^T for a general 3x3 block: rotate the columns, then the rows
 template <int CHAIN>
-__device__ __forceinline__ Mat3 pnr_rot_block(const PnrParams& p, int j, float s, float c, const Mat3& b) {
+PNR_HD Mat3 pnr_rot_block(const PnrParams& p, int j, float s, float c, const Mat3& b) {
     const V3 c0 = pnr_rot<CHAIN>(p, j, s, c, v3(b.m[0], b.m[3], b.m[6]));
     const V3 c1 = pnr_rot<CHAIN>(p, j, s, c, v3(b.m[1], b.m[4], b.m[7]));
     const V3 c2 = pnr_rot<CHAIN>(p, j, s, c, v3(b.m[2], b.m[5], b.m[8]));
@@ -168,11 +173,11 @@ __device__ __forceinline__ Mat3 pnr_rot_block(const PnrParams& p, int j, float s
     return o;
 }
 
-__device__ __forceinline__ Mat3 sym_to_mat(const Sym3& s) {
+PNR_HD Mat3 sym_to_mat(const Sym3& s) {
     Mat3 o = {{s.xx, s.xy, s.xz, s.xy, s.yy, s.yz, s.xz, s.yz, s.zz}};
     return o;
 }
-__device__ __forceinline__ Sym3 mat_to_sym(const Mat3& a) {     // a is symmetric up to rounding: average the pairs
+PNR_HD Sym3 mat_to_sym(const Mat3& a) {     // a is symmetric up to rounding: average the pairs
     Sym3 o = {a.m[0], 0.5f * (a.m[1] + a.m[3]), 0.5f * (a.m[2] + a.m[6]), a.m[4], 0.5f * (a.m[5] + a.m[7]), a.m[8]};
     return o;
 }
@@ -185,9 +190,11 @@ struct PnrDynWork {                 // per-joint quantities kept between the thr
     float dinv[PNR_DOF], u[PNR_DOF];
 };
 
-// qdd = ABA(q, qd, tau); gravity acts along -z of the base frame
+// qdd = ABA(q, qd, tau); gravity acts along -z of the base frame.  Any serial 6-revolute chain (CHAIN = GENERIC reads the
+// axis codes at run time); with CHAIN = PIONEER this is the first specialisation (kept as the A/B baseline of
+// pnr_aba_pioneer below, tests/csrc/aba_check.cu).
 template <int CHAIN>
-__device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR_DOF], const float (&qd)[PNR_DOF],
+PNR_HD void pnr_aba_general(const PnrParams& p, const float (&q)[PNR_DOF], const float (&qd)[PNR_DOF],
                                         const float (&tau)[PNR_DOF], float (&qdd)[PNR_DOF]) {
     PnrDynWork w;
     // ---- pass 1 (base -> tip): velocities, velocity-product accelerations, bias forces
@@ -299,8 +306,314 @@ __device__ __forceinline__ void pnr_aba(const PnrParams& p, const float (&q)[PNR
     }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// pnr_aba_pioneer: the same algorithm written for the structure of the shipped robot (PNR_CHAIN_PIONEER: joint axes
+// Z Y Y X Y X, positive, no origin rotations, every joint origin on ONE coordinate axis of its parent), with the
+// sparsity that structure implies spelled out instead of left to the compiler (which may not fold x * 0 or x + 0):
+//   * a rotation about coordinate axis k touches only the components a = k+1, b = k+2 (cyclic): vectors cost 4
+//     operations, a SYMMETRIC block R S R^T is evaluated in closed form from cos^2, sin^2, sin cos (12 operations
+//     instead of 24 + 6 to re-symmetrise);
+//   * moving the reference point by p = p_k e_k:  H'' = H' + [p]x M',  I'' = I' + (H' [p]x^T)^T + H'' [p]x^T  has six
+//     distinct entries of I and six of H that change -- 14 FMAs instead of three 3x3 products and a re-symmetrisation;
+//   * the velocity-product terms c = v x (e_k qd) have a zero k-component: the 3x3 products with them skip a column;
+//   * the tip joint's articulated inertia after its own rank-1 update is a constant of the robot: precomputed on the
+//     host in float64 (PnrParams::dyn_tip_*, pnr_build_params);
+//   * joint 0 sits on the fixed base: its velocity is e_k qd and its acceleration bias is zero.
+// ---------------------------------------------------------------------------------------------------------------
+PNR_HD int pnr_pio_code(int i) { return i == 0 ? PNR_AXIS_Z : ((i == 3 || i == 5) ? PNR_AXIS_X : PNR_AXIS_Y); }
+PNR_HD int pnr_pio_ocode(int i) { return (i == 0 || i == 5) ? -1 : (i == 3 ? 1 : (i == 4 ? 0 : 2)); }   // axis the origin lies on
+PNR_HD int pnr_nxt(int k) { return k == 2 ? 0 : k + 1; }       // a: the component after k, cyclic
+PNR_HD int pnr_prv(int k) { return k == 0 ? 2 : k - 1; }       // b: the component before k
+
+PNR_HD float vget(const V3& v, int i) { return i == 0 ? v.x : (i == 1 ? v.y : v.z); }
+PNR_HD void vset(V3& v, int i, float f) { if (i == 0) v.x = f; else if (i == 1) v.y = f; else v.z = f; }
+PNR_HD float sget(const Sym3& s, int i, int j) {
+    const int lo = i < j ? i : j, hi = i < j ? j : i, k = 3 * lo + hi;
+    return k == 0 ? s.xx : (k == 1 ? s.xy : (k == 2 ? s.xz : (k == 4 ? s.yy : (k == 5 ? s.yz : s.zz))));
+}
+PNR_HD void sset(Sym3& s, int i, int j, float f) {
+    const int lo = i < j ? i : j, hi = i < j ? j : i, k = 3 * lo + hi;
+    if (k == 0) s.xx = f; else if (k == 1) s.xy = f; else if (k == 2) s.xz = f; else if (k == 4) s.yy = f;
+    else if (k == 5) s.yz = f; else s.zz = f;
+}
+
+// Rot(e_k, angle) v (child -> parent coordinates); the transpose takes -s
+PNR_HD V3 pnr_rotk(int k, float s, float c, V3 v) {
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    const float va = vget(v, a), vb = vget(v, b);
+    vset(v, a, fmaf(c, va, -s * vb));
+    vset(v, b, fmaf(s, va, c * vb));
+    return v;
+}
+// e_k s + v,  v x (e_k s),  (e_k s) x v
+PNR_HD V3 pnr_add_ek(int k, V3 v, float s) { vset(v, k, vget(v, k) + s); return v; }
+PNR_HD V3 pnr_cross_ek(int k, V3 v, float s) {                 // k-component is an exact zero
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    V3 r = v3(0.f, 0.f, 0.f);
+    vset(r, a, vget(v, b) * s);
+    vset(r, b, -vget(v, a) * s);
+    return r;
+}
+PNR_HD V3 pnr_ek_cross(int k, float s, V3 v) {
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    V3 r = v3(0.f, 0.f, 0.f);
+    vset(r, a, -s * vget(v, b));
+    vset(r, b, s * vget(v, a));
+    return r;
+}
+// v - (e_k pk) x w   and   v + (e_k pk) x w: only two components change
+PNR_HD V3 pnr_sub_origin_cross(int k, float pk, V3 v, V3 w) {
+    if (k < 0) return v;
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    vset(v, a, fmaf(pk, vget(w, b), vget(v, a)));
+    vset(v, b, fmaf(-pk, vget(w, a), vget(v, b)));
+    return v;
+}
+PNR_HD V3 pnr_add_origin_cross(int k, float pk, V3 v, V3 w) { return pnr_sub_origin_cross(k, -pk, v, w); }
+// S v, A v, A^T v for a v whose k-component is an exact zero
+PNR_HD V3 pnr_symmul_z(int k, const Sym3& s, V3 v) {
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    const float va = vget(v, a), vb = vget(v, b);
+    return v3(fmaf(sget(s, 0, a), va, sget(s, 0, b) * vb), fmaf(sget(s, 1, a), va, sget(s, 1, b) * vb),
+              fmaf(sget(s, 2, a), va, sget(s, 2, b) * vb));
+}
+PNR_HD V3 pnr_matmul_z(int k, const Mat3& m, V3 v) {
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    const float va = vget(v, a), vb = vget(v, b);
+    return v3(fmaf(m.m[a], va, m.m[b] * vb), fmaf(m.m[3 + a], va, m.m[3 + b] * vb), fmaf(m.m[6 + a], va, m.m[6 + b] * vb));
+}
+PNR_HD V3 pnr_matTmul_z(int k, const Mat3& m, V3 v) {
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    const float va = vget(v, a), vb = vget(v, b);
+    return v3(fmaf(m.m[3 * a], va, m.m[3 * b] * vb), fmaf(m.m[3 * a + 1], va, m.m[3 * b + 1] * vb),
+              fmaf(m.m[3 * a + 2], va, m.m[3 * b + 2] * vb));
+}
+struct PnrRot2 { float s, c, cc, ss, sc, sc2, cms; };           // sin, cos and the products the closed forms need
+PNR_HD PnrRot2 pnr_rot2(float s, float c) {
+    PnrRot2 r;
+    r.s = s; r.c = c; r.cc = c * c; r.ss = s * s; r.sc = s * c; r.sc2 = r.sc + r.sc; r.cms = r.cc - r.ss;
+    return r;
+}
+// R S R^T for a symmetric block and R = Rot(e_k): closed form; the trace of the (a, b) sub-block is preserved
+PNR_HD Sym3 pnr_rotk_sym(int k, const PnrRot2& r, const Sym3& S) {
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    const float saa = sget(S, a, a), sab = sget(S, a, b), sbb = sget(S, b, b), sak = sget(S, a, k), sbk = sget(S, b, k);
+    Sym3 o = S;
+    const float naa = fmaf(r.cc, saa, fmaf(-r.sc2, sab, r.ss * sbb));
+    sset(o, a, a, naa);
+    sset(o, b, b, (saa + sbb) - naa);
+    sset(o, a, b, fmaf(r.sc, saa - sbb, r.cms * sab));
+    sset(o, a, k, fmaf(r.c, sak, -r.s * sbk));
+    sset(o, b, k, fmaf(r.s, sak, r.c * sbk));
+    return o;
+}
+// R B R^T for a general block: rows a, b mix, then columns a, b
+PNR_HD Mat3 pnr_rotk_block(int k, const PnrRot2& r, const Mat3& B) {
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    Mat3 t = B;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        t.m[3 * a + j] = fmaf(r.c, B.m[3 * a + j], -r.s * B.m[3 * b + j]);
+        t.m[3 * b + j] = fmaf(r.s, B.m[3 * a + j], r.c * B.m[3 * b + j]);
+    }
+    Mat3 o = t;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        o.m[3 * i + a] = fmaf(r.c, t.m[3 * i + a], -r.s * t.m[3 * i + b]);
+        o.m[3 * i + b] = fmaf(r.s, t.m[3 * i + a], r.c * t.m[3 * i + b]);
+    }
+    return o;
+}
+// After joint k's rank-1 update the articulated inertia annihilates the joint axis: column / row k of I^a and row k of
+// H^a are exact zeros (I^a S = 0).  They are not computed; the variants below skip them.
+PNR_HD Sym3 pnr_rotk_sym_z(int k, const PnrRot2& r, const Sym3& S) {       // only the (a, b) block is populated
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    const float saa = sget(S, a, a), sab = sget(S, a, b), sbb = sget(S, b, b);
+    Sym3 o = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float naa = fmaf(r.cc, saa, fmaf(-r.sc2, sab, r.ss * sbb));
+    sset(o, a, a, naa);
+    sset(o, b, b, (saa + sbb) - naa);
+    sset(o, a, b, fmaf(r.sc, saa - sbb, r.cms * sab));
+    return o;
+}
+PNR_HD Mat3 pnr_rotk_block_z(int k, const PnrRot2& r, const Mat3& B) {     // row k of B (and of the result) is zero
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    Mat3 t = {{0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}};
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        t.m[3 * a + j] = fmaf(r.c, B.m[3 * a + j], -r.s * B.m[3 * b + j]);
+        t.m[3 * b + j] = fmaf(r.s, B.m[3 * a + j], r.c * B.m[3 * b + j]);
+    }
+    Mat3 o = t;
+    o.m[3 * a + a] = fmaf(r.c, t.m[3 * a + a], -r.s * t.m[3 * a + b]);
+    o.m[3 * a + b] = fmaf(r.s, t.m[3 * a + a], r.c * t.m[3 * a + b]);
+    o.m[3 * b + a] = fmaf(r.c, t.m[3 * b + a], -r.s * t.m[3 * b + b]);
+    o.m[3 * b + b] = fmaf(r.s, t.m[3 * b + a], r.c * t.m[3 * b + b]);
+    return o;
+}
+// move the reference point of the (rotated) articulated inertia by p = e_k pk (see the header comment); M is unchanged
+PNR_HD void pnr_shift_ek(int k, float pk, Sym3& I, Mat3& H, const Sym3& M) {
+    if (k < 0) return;
+    const int a = pnr_nxt(k), b = pnr_prv(k);
+    const float h_ab = H.m[3 * a + b], h_bb = H.m[3 * b + b], h_kb = H.m[3 * k + b];
+    const float h_ba = H.m[3 * b + a], h_ka = H.m[3 * k + a];
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        H.m[3 * a + j] = fmaf(-pk, sget(M, b, j), H.m[3 * a + j]);
+        H.m[3 * b + j] = fmaf(pk, sget(M, a, j), H.m[3 * b + j]);
+    }
+    sset(I, a, a, fmaf(-pk, h_ab + H.m[3 * a + b], sget(I, a, a)));
+    sset(I, a, b, fmaf(pk, H.m[3 * a + a], fmaf(-pk, h_bb, sget(I, a, b))));
+    sset(I, a, k, fmaf(-pk, h_kb, sget(I, a, k)));
+    sset(I, b, b, fmaf(pk, h_ba + H.m[3 * b + a], sget(I, b, b)));
+    sset(I, b, k, fmaf(pk, h_ka, sget(I, b, k)));
+}
+
+PNR_HD void pnr_aba_pioneer(const PnrParams& p, const float (&q)[PNR_DOF], const float (&qd)[PNR_DOF],
+                            const float (&tau)[PNR_DOF], float (&qdd)[PNR_DOF]) {
+    PnrDynWork w;
+    // ---- pass 1 (base -> tip): velocities, velocity-product accelerations, bias forces of the rigid bodies
+    V3 om = v3(0.f, 0.f, 0.f), vl = v3(0.f, 0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) {
+        const int k = pnr_pio_code(i), ok = pnr_pio_ocode(i), a = pnr_nxt(k), b = pnr_prv(k);
+        pnr_sincos_bounded(q[i], w.sn[i], w.cs[i]);                    // chain_kind 1 implies joint limits within +-64 rad
+        const Sym3 Io = {p.dyn_io[i][0], p.dyn_io[i][1], p.dyn_io[i][2], p.dyn_io[i][3], p.dyn_io[i][4], p.dyn_io[i][5]};
+        const V3 mc = v3(p.dyn_mc[i][0], p.dyn_mc[i][1], p.dyn_mc[i][2]);
+        if (i == 0) {
+            // fixed base: om = e_k qd, vl = 0, c = 0;  n = Io om,  f = -mc x om,  p = (om x n, om x f)
+            const float wq = qd[0];
+            V3 n = v3(sget(Io, 0, k) * wq, sget(Io, 1, k) * wq, sget(Io, 2, k) * wq);
+            V3 f = v3(0.f, 0.f, 0.f);
+            vset(f, a, -vget(mc, b) * wq);
+            vset(f, b, vget(mc, a) * wq);
+            w.p_ang[0] = pnr_ek_cross(k, wq, n);
+            w.p_lin[0] = pnr_ek_cross(k, wq, f);
+            om = v3(0.f, 0.f, 0.f);
+            vset(om, k, wq);
+        } else {
+            const V3 t = pnr_sub_origin_cross(ok, ok >= 0 ? p.origin_xyz[i][ok] : 0.f, vl, om);
+            om = pnr_add_ek(k, pnr_rotk(k, -w.sn[i], w.cs[i], om), qd[i]);
+            vl = pnr_rotk(k, -w.sn[i], w.cs[i], t);
+            w.c_ang[i] = pnr_cross_ek(k, om, qd[i]);
+            w.c_lin[i] = pnr_cross_ek(k, vl, qd[i]);
+            const V3 n = symmul(Io, om) + cross(mc, vl);
+            const V3 f = vl * p.dyn_mass[i] - cross(mc, om);
+            w.p_ang[i] = cross(om, n) + cross(vl, f);
+            w.p_lin[i] = cross(om, f);
+        }
+    }
+    // ---- pass 2 (tip -> base): articulated inertias and bias forces
+    Sym3 I, M;
+    Mat3 H;
+    V3 pa_ang = w.p_ang[PNR_DOF - 1], pa_lin = w.p_lin[PNR_DOF - 1];
+#pragma unroll
+    for (int i = PNR_DOF - 1; i >= 0; --i) {
+        const int k = pnr_pio_code(i), ok = pnr_pio_ocode(i);
+        V3 Ua, Ul;
+        float dinv;
+        if (i == PNR_DOF - 1) {
+            // the tip body's inertia after its own rank-1 update never changes: host-computed constants
+            Sym3 i0 = {p.dyn_tip_I[0], p.dyn_tip_I[1], p.dyn_tip_I[2], p.dyn_tip_I[3], p.dyn_tip_I[4], p.dyn_tip_I[5]};
+            Sym3 m0 = {p.dyn_tip_M[0], p.dyn_tip_M[1], p.dyn_tip_M[2], p.dyn_tip_M[3], p.dyn_tip_M[4], p.dyn_tip_M[5]};
+            I = i0; M = m0;
+#pragma unroll
+            for (int e = 0; e < 9; ++e) H.m[e] = p.dyn_tip_H[e];
+            Ua = v3(p.dyn_tip_ua[0], p.dyn_tip_ua[1], p.dyn_tip_ua[2]);
+            Ul = v3(p.dyn_tip_ul[0], p.dyn_tip_ul[1], p.dyn_tip_ul[2]);
+            dinv = p.dyn_tip_dinv;
+        } else {                                                        // own rigid body + what the child handed up
+            const V3 mc = v3(p.dyn_mc[i][0], p.dyn_mc[i][1], p.dyn_mc[i][2]);
+            const float m = p.dyn_mass[i];
+            I.xx += p.dyn_io[i][0]; I.xy += p.dyn_io[i][1]; I.xz += p.dyn_io[i][2];
+            I.yy += p.dyn_io[i][3]; I.yz += p.dyn_io[i][4]; I.zz += p.dyn_io[i][5];
+            H.m[1] -= mc.z; H.m[2] += mc.y; H.m[3] += mc.z; H.m[5] -= mc.x; H.m[6] -= mc.y; H.m[7] += mc.x;
+            M.xx += m; M.yy += m; M.zz += m;
+            pa_ang = pa_ang + w.p_ang[i];
+            pa_lin = pa_lin + w.p_lin[i];
+            Ua = v3(sget(I, 0, k), sget(I, 1, k), sget(I, 2, k));       // I e_k
+            Ul = v3(H.m[3 * k], H.m[3 * k + 1], H.m[3 * k + 2]);        // H^T e_k
+            dinv = 1.f / vget(Ua, k);
+        }
+        const float u = tau[i] - vget(pa_ang, k);
+        w.u_ang[i] = Ua; w.u_lin[i] = Ul; w.dinv[i] = dinv; w.u[i] = u;
+        if (i > 0) {
+            const int a = pnr_nxt(k), b = pnr_prv(k);
+            if (i != PNR_DOF - 1) {                                     // I^a = I^A - U U^T / d; entries with index k vanish
+                const float uaa = vget(Ua, a), uab = vget(Ua, b);
+                const float da = uaa * dinv, db = uab * dinv;
+                const V3 Uld = Ul * dinv;
+                const float iaa = fmaf(-uaa, da, sget(I, a, a)), iab = fmaf(-uaa, db, sget(I, a, b));
+                const float ibb = fmaf(-uab, db, sget(I, b, b));
+                Sym3 z = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                I = z;
+                sset(I, a, a, iaa); sset(I, a, b, iab); sset(I, b, b, ibb);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    H.m[3 * a + j] = fmaf(-da, vget(Ul, j), H.m[3 * a + j]);
+                    H.m[3 * b + j] = fmaf(-db, vget(Ul, j), H.m[3 * b + j]);
+                    H.m[3 * k + j] = 0.f;
+                }
+                M.xx -= Ul.x * Uld.x; M.xy -= Ul.x * Uld.y; M.xz -= Ul.x * Uld.z;
+                M.yy -= Ul.y * Uld.y; M.yz -= Ul.y * Uld.z; M.zz -= Ul.z * Uld.z;
+            }
+            // p^a = p^A + I^a c + U u / d   (c has a zero k-component; so have I^a c_ang and H^a c_lin)
+            const float ud = u * dinv;
+            const float ca_a = vget(w.c_ang[i], a), ca_b = vget(w.c_ang[i], b);
+            const float cl_a = vget(w.c_lin[i], a), cl_b = vget(w.c_lin[i], b);
+            vset(pa_ang, a, vget(pa_ang, a) + fmaf(sget(I, a, a), ca_a, fmaf(sget(I, a, b), ca_b,
+                            fmaf(H.m[3 * a + a], cl_a, fmaf(H.m[3 * a + b], cl_b, vget(Ua, a) * ud)))));
+            vset(pa_ang, b, vget(pa_ang, b) + fmaf(sget(I, a, b), ca_a, fmaf(sget(I, b, b), ca_b,
+                            fmaf(H.m[3 * b + a], cl_a, fmaf(H.m[3 * b + b], cl_b, vget(Ua, b) * ud)))));
+            vset(pa_ang, k, fmaf(vget(Ua, k), ud, vget(pa_ang, k)));
+            pa_lin = pa_lin + pnr_matTmul_z(k, H, w.c_ang[i]) + pnr_symmul_z(k, M, w.c_lin[i]) + Ul * ud;
+            // hand I^a, p^a up to the parent: rotate by Rot(e_k, q_i), then move the reference point by p_i
+            const PnrRot2 r = pnr_rot2(w.sn[i], w.cs[i]);
+            const float pk = ok >= 0 ? p.origin_xyz[i][ok] : 0.f;
+            I = pnr_rotk_sym_z(k, r, I);
+            M = pnr_rotk_sym(k, r, M);
+            H = pnr_rotk_block_z(k, r, H);
+            pnr_shift_ek(ok, pk, I, H, M);
+            const V3 fp = pnr_rotk(k, r.s, r.c, pa_lin);
+            pa_ang = pnr_add_origin_cross(ok, pk, pnr_rotk(k, r.s, r.c, pa_ang), fp);
+            pa_lin = fp;
+        }
+    }
+    // ---- pass 3 (base -> tip): accelerations.  The base "accelerates" by -g: a_lin = (0, 0, +gravity)
+    V3 aa, al;
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) {
+        const int k = pnr_pio_code(i), ok = pnr_pio_ocode(i);
+        if (i == 0) {                                                   // joint 0 turns about z: gravity stays (0, 0, g)
+            al = v3(0.f, 0.f, p.dyn_gravity);
+            qdd[0] = (w.u[0] - w.u_lin[0].z * p.dyn_gravity) * w.dinv[0];
+            aa = v3(0.f, 0.f, qdd[0]);
+        } else {
+            const V3 t = pnr_sub_origin_cross(ok, ok >= 0 ? p.origin_xyz[i][ok] : 0.f, al, aa);
+            aa = pnr_rotk(k, -w.sn[i], w.cs[i], aa);
+            al = pnr_rotk(k, -w.sn[i], w.cs[i], t);
+            const int a = pnr_nxt(k), b = pnr_prv(k);                   // c_ang, c_lin have a zero k-component
+            vset(aa, a, vget(aa, a) + vget(w.c_ang[i], a)); vset(aa, b, vget(aa, b) + vget(w.c_ang[i], b));
+            vset(al, a, vget(al, a) + vget(w.c_lin[i], a)); vset(al, b, vget(al, b) + vget(w.c_lin[i], b));
+            qdd[i] = (w.u[i] - dot(w.u_ang[i], aa) - dot(w.u_lin[i], al)) * w.dinv[i];
+            aa = pnr_add_ek(k, aa, qdd[i]);
+        }
+    }
+}
+
+template <int CHAIN>
+PNR_HD void pnr_aba(const PnrParams& p, const float (&q)[PNR_DOF], const float (&qd)[PNR_DOF],
+                    const float (&tau)[PNR_DOF], float (&qdd)[PNR_DOF]) {
+#ifdef PNR_ABA_BASELINE                                 // A/B builds: the first specialisation
+    pnr_aba_general<CHAIN>(p, q, qd, tau, qdd);
+#else
+    if (CHAIN == PNR_CHAIN_PIONEER) pnr_aba_pioneer(p, q, qd, tau, qdd);
+    else pnr_aba_general<CHAIN>(p, q, qd, tau, qdd);
+#endif
+}
+
 // joint PD / torque control with effort clamping, then viscous joint damping (oracle/dynamics_oracle.py::control_torque)
-__device__ __forceinline__ float pnr_control_torque(const PnrParams& p, int i, float action, float q, float qd) {
+PNR_HD float pnr_control_torque(const PnrParams& p, int i, float action, float q, float qd) {
     float tau = p.dyn_use_pd ? fmaf(p.dyn_kp, action - q, -p.dyn_kd * qd) : action;
     const float lim = p.dyn_tau_max[i];
     tau = fminf(fmaxf(tau, -lim), lim);
@@ -309,7 +622,7 @@ __device__ __forceinline__ float pnr_control_torque(const PnrParams& p, int i, f
 
 // frame_skip substeps of semi-implicit Euler: qd += qdd dt; q += qd dt; inelastic stops at the joint limits
 template <int CHAIN>
-__device__ __forceinline__ void pnr_dynamic_substeps(const PnrParams& p, float (&q)[PNR_DOF], float (&qd)[PNR_DOF],
+PNR_HD void pnr_dynamic_substeps(const PnrParams& p, float (&q)[PNR_DOF], float (&qd)[PNR_DOF],
                                                      const float (&action)[PNR_DOF]) {
 #pragma unroll 1
     for (int sub = 0; sub < p.dyn_frame_skip; ++sub) {

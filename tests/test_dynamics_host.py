@@ -1,0 +1,128 @@
+"""The float32 articulated-body algorithm of the dynamic-mode kernel (pioneer_b200/csrc/pnr_dynamics.cuh), compiled for
+the HOST with nvcc (tests/csrc/aba_check.cu) and compared with the float64 oracle (oracle/dynamics_oracle.py) on the
+CPU.  Three variants must agree: the run-time generic chain, the first specialisation for the shipped robot and the
+sparsity-aware specialisation the kernel runs (pnr_aba_pioneer).  The parameter block comes from the product
+library's own host-side builder (pnr_debug_build_params), so the constants under test are the ones the GPU gets.
+No CUDA device is needed and no kernel runs here; the GPU tests (tests/test_gpu_dynamic.py) check the kernel itself.
+PARITY UNPINNED vs PyBullet (see the oracle's header)."""
+import ctypes as C
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle.dynamics_oracle import DynChain, DynConfig, aba, dynamic_substeps
+from pioneer_b200 import _cabi
+from pioneer_b200.urdf import flatten_urdf
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+NVCC = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+pytestmark = pytest.mark.skipif(not os.path.exists(NVCC), reason="needs nvcc")
+
+F = C.POINTER(C.c_float)
+
+
+def fp(a):
+    return a.ctypes.data_as(F)
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    out = tmp_path_factory.mktemp("aba") / "aba_check.so"
+    subprocess.run([NVCC, "-Wno-deprecated-gpu-targets", "-O2", "-std=c++17", "-shared", "-Xcompiler", "-fPIC",
+                    "-o", str(out), os.path.join(ROOT, "tests", "csrc", "aba_check.cu")], check=True)
+    lib = C.CDLL(str(out))
+    lib.aba_params_size.restype = C.c_long
+    lib.aba_check.argtypes = [C.c_void_p, C.c_int, C.c_long, F, F, F, F]
+    lib.aba_substeps.argtypes = [C.c_void_p, C.c_int, C.c_long, F, F, F]
+    return lib
+
+
+def params_blob(harness, gravity=9.81, kp=0.0, kd=0.0, torque_scale=1.0):
+    lib = _cabi.load()
+    lib.pnr_debug_build_params.restype = C.c_int64
+    lib.pnr_debug_build_params.argtypes = [C.POINTER(_cabi.pnr_model), C.POINTER(_cabi.pnr_config), C.c_int64,
+                                           C.c_void_p, C.c_int64]
+    chain = flatten_urdf()
+    model = _cabi.model_from_chain(chain)
+    cfg = _cabi.pnr_config()
+    lib.pnr_default_config(C.byref(cfg))
+    cfg.mode, cfg.gravity, cfg.kp, cfg.kd, cfg.torque_scale = _cabi.PNR_MODE_DYNAMIC, gravity, kp, kd, torque_scale
+    size = lib.pnr_debug_build_params(C.byref(model), C.byref(cfg), 1, None, 0)
+    assert size == harness.aba_params_size(), "harness and library disagree on sizeof(PnrParams)"
+    blob = C.create_string_buffer(size)
+    assert lib.pnr_debug_build_params(C.byref(model), C.byref(cfg), 1, blob, size) == size
+    return chain, blob
+
+
+def states(chain, n, seed):
+    rng = np.random.default_rng(seed)
+    lo, hi = np.asarray(chain.lower), np.asarray(chain.upper)
+    q = rng.uniform(lo, hi, size=(n, 6)).astype(np.float32)
+    qd = (rng.normal(size=(n, 6)) * 1.5).astype(np.float32)
+    return rng, q, qd
+
+
+@pytest.mark.parametrize("gravity", [0.0, 9.81])
+def test_three_float32_variants_against_the_float64_oracle(harness, gravity):
+    chain, blob = params_blob(harness, gravity=gravity)
+    dyn = DynChain.from_model(chain)
+    n = 400
+    rng, q, qd = states(chain, n, seed=2)
+    tau = (rng.normal(size=(n, 6)) * 300.0).astype(np.float32)
+    ref = np.stack([aba(dyn, q[e].astype(np.float64), qd[e].astype(np.float64), tau[e].astype(np.float64), gravity)
+                    for e in range(n)])
+    scale = np.abs(ref).max(axis=0) + 1e-9
+    outs = []
+    for variant in (0, 1, 2):
+        out = np.empty((n, 6), np.float32)
+        assert harness.aba_check(blob, variant, n, fp(q), fp(qd), fp(tau), fp(out)) == 0
+        err = np.abs(out - ref) / scale
+        assert err.max() < 2e-4, (variant, err.max())     # float32 against float64, relative to each joint's range
+        outs.append(out)
+    # the sparsity-aware specialisation is at least as close to the oracle as the version it replaces
+    e1 = (np.abs(outs[1] - ref) / scale).mean()
+    e2 = (np.abs(outs[2] - ref) / scale).mean()
+    assert e2 <= 1.5 * e1 + 1e-7, (e1, e2)
+
+
+def test_zero_input_gives_exact_zero_acceleration(harness):
+    """zero velocity, gravity and torque -> every term is an exact zero."""
+    chain, blob = params_blob(harness, gravity=0.0)
+    n = 64
+    _, q, _ = states(chain, n, seed=4)
+    zero = np.zeros((n, 6), np.float32)
+    for variant in (0, 1, 2):
+        out = np.full((n, 6), np.nan, np.float32)
+        assert harness.aba_check(blob, variant, n, fp(q), fp(zero), fp(zero), fp(out)) == 0
+        assert (out == 0).all(), variant
+
+
+@pytest.mark.parametrize("kp,kd,scale", [(0.0, 0.0, 50.0), (800.0, 200.0, 1e4)])
+def test_one_env_step_of_substeps_against_the_oracle(harness, kp, kd, scale):
+    """frame_skip (10) substeps of control + ABA + semi-implicit Euler + limit stops; bars as on the GPU:
+    |dq| <= 2e-5 rad, |dqd| <= 2e-4 rad/s."""
+    gravity = 9.81
+    chain, blob = params_blob(harness, gravity=gravity, kp=kp, kd=kd, torque_scale=scale)
+    dyn = DynChain.from_model(chain)
+    cfg = DynConfig(gravity=gravity, kp=kp, kd=kd, torque_scale=scale)
+    n = 200
+    rng, q, qd = states(chain, n, seed=7)
+    q = (q * 0.8).astype(np.float32)
+    qd = (qd * 0.3).astype(np.float32)
+    lo32, hi32 = np.asarray(chain.lower, np.float32), np.asarray(chain.upper, np.float32)
+    if kp or kd:
+        act = rng.uniform(lo32, hi32, size=(n, 6)).astype(np.float32)
+    else:
+        act = (rng.normal(size=(n, 6)) * scale).astype(np.float32)
+    ref_q, ref_qd = np.empty((n, 6)), np.empty((n, 6))
+    for e in range(n):
+        ref_q[e], ref_qd[e] = dynamic_substeps(dyn, cfg, q[e].astype(np.float64), qd[e].astype(np.float64),
+                                               act[e].astype(np.float64), lo32.astype(np.float64), hi32.astype(np.float64))
+    for pioneer_chain in (0, 1):
+        q1, qd1 = q.copy(), qd.copy()
+        assert harness.aba_substeps(blob, pioneer_chain, n, fp(q1), fp(qd1), fp(act)) == 0
+        assert np.abs(q1 - ref_q).max() <= 2e-5, (pioneer_chain, np.abs(q1 - ref_q).max())
+        assert np.abs(qd1 - ref_qd).max() <= 2e-4, (pioneer_chain, np.abs(qd1 - ref_qd).max())
