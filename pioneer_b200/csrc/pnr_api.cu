@@ -226,6 +226,16 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
             for (int k = 0; k < 3; ++k) match = match && (k == origin_axis[j] || m.origin_xyz[j][k] == 0.0);
         }
         p.chain_kind = match ? 1 : 0;
+        // the stub inertials of the shipped URDF (pioneer_knm_6dof.urdf: mass, identity-like inertia, no <origin>):
+        // composite bodies 0..4 have their centre of mass on the frame origin and an isotropic inertia (PNR_CHAIN_PIONEER_ISO)
+        bool iso = true;
+        for (int j = 0; j + 1 < PNR_DOF; ++j) {
+            const double* c_ = m.body_com[j];
+            const double* I_ = m.body_inertia[j];
+            iso = iso && c_[0] == 0.0 && c_[1] == 0.0 && c_[2] == 0.0 && I_[1] == 0.0 && I_[2] == 0.0 && I_[3] == 0.0 &&
+                  I_[5] == 0.0 && I_[6] == 0.0 && I_[7] == 0.0 && I_[0] == I_[4] && I_[4] == I_[8];
+        }
+        p.dyn_iso_links = iso ? 1 : 0;
     }
     p.dyn_kp = (float)c.kp; p.dyn_kd = (float)c.kd;
     p.dyn_use_pd = (c.kp != 0.0 || c.kd != 0.0) ? 1 : 0;

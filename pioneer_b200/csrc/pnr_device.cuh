@@ -53,6 +53,7 @@ struct PnrParams {
     float dyn_kp, dyn_kd, dyn_dt, dyn_gravity;
     int32_t dyn_frame_skip, dyn_use_pd;
     int32_t chain_kind;             // 1: axes Z Y Y X Y X, positive, identity origin rotations (the shipped robot)
+    int32_t dyn_iso_links;          // 1: every link but the tip has its centre of mass on the frame origin and an isotropic inertia
     // obstacle variant: link capsules (moving-frame coordinates) against static plane / box / sphere obstacles
     int32_t n_capsules, n_obstacles;
     int32_t capsule_body[PNR_MAX_CAPSULES];

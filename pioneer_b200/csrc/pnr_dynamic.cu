@@ -3,12 +3,16 @@
 // registers, then the same task code as the kinematic env (pioneer_knm_env.py:151-211): forward kinematics of
 // the pointer, reward, done, TimeLimit, statistics, auto-reset, 137-float observation staged per warp in shared
 // memory and stored with one TMA bulk copy.  Bound: FP32 pipe (10 x ~2 kflop per env-step against 761 B).
+#include <cstdlib>
 #include "pnr_kernels.cuh"
 #include "pnr_dynamics.cuh"
 #include "pnr_launch.h"
 
 #ifndef PNR_DYN_MIN_CTAS
-#define PNR_DYN_MIN_CTAS 2            // 208 registers: 2 CTAs/SM measured 72 us per 65,536-env step against 93 us with 3 (168 regs), 88 us with 4
+// Resident CTAs per SM, measured on B200 at 1,048,576 envs.  First ABA (223 registers): 2 CTAs 72 us per 65,536-env step
+// against 93 us with 3 (spills).  Sparsity-aware ABA (183 registers at 2 CTAs, 152 at 3, no spills): 486 us with 2,
+// 461 us with 3.
+#define PNR_DYN_MIN_CTAS 3
 #endif
 template <int OBS_MODE, bool OBSTACLES, int CHAIN>
 __global__ void __launch_bounds__(PNR_STEP_THREADS, PNR_DYN_MIN_CTAS)
@@ -106,10 +110,12 @@ cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode
 #define PNR_DYN_ROW(CH) \
     {{pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, false, CH>, pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, true, CH>}, \
      {pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, false, CH>, pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, true, CH>}}
-    static Kern kernels[2][2][2] = {PNR_DYN_ROW(PNR_CHAIN_GENERIC), PNR_DYN_ROW(PNR_CHAIN_PIONEER)};
-    static int grids[PNR_MAX_DEVICES][2][2][2] = {};
+    static Kern kernels[3][2][2] = {PNR_DYN_ROW(PNR_CHAIN_GENERIC), PNR_DYN_ROW(PNR_CHAIN_PIONEER),
+                                    PNR_DYN_ROW(PNR_CHAIN_PIONEER_ISO)};
+    static int grids[PNR_MAX_DEVICES][3][2][2] = {};
     const int obst = p.n_obstacles > 0 ? 1 : 0;
-    const int chain = p.chain_kind == PNR_CHAIN_PIONEER ? 1 : 0;
+    int chain = p.chain_kind == 1 ? (p.dyn_iso_links ? PNR_CHAIN_PIONEER_ISO : PNR_CHAIN_PIONEER) : PNR_CHAIN_GENERIC;
+    if (const char* e = getenv("PNR_DYN_CHAIN")) chain = atoi(e) < chain ? atoi(e) : chain;   // developer / test knob: force a less specialised kernel
     Kern kern = kernels[chain][obs_mode][obst];
     int& resident = grids[device % PNR_MAX_DEVICES][chain][obs_mode][obst];
     if (resident == 0) {

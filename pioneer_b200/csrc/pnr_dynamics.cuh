@@ -49,15 +49,20 @@ PNR_HD V3 matTmul(const Mat3& a, V3 v) {
 // generic body does not fit the instruction cache (71 % of warp stalls were instruction fetch, profiles/r01_dyn_v1).
 #define PNR_CHAIN_GENERIC 0
 #define PNR_CHAIN_PIONEER 1
+// PNR_CHAIN_PIONEER_ISO: additionally the inertials the shipped URDF gives every link but the tip (the stub
+// <inertial> blocks of pioneer_knm_6dof.urdf: centre of mass on the frame origin, isotropic inertia iota * 1): for such
+// a body  omega x (iota omega) = 0  and  v x (m v) = 0, so its bias force is (0, m omega x v) and it adds only three
+// diagonal terms to I and M and nothing to H.  A URDF with other inertials takes PNR_CHAIN_PIONEER.
+#define PNR_CHAIN_PIONEER_ISO 2
 
 template <int CHAIN>
 PNR_HD int pnr_code(const PnrParams& p, int j) {
-    if (CHAIN == PNR_CHAIN_PIONEER) return j == 0 ? PNR_AXIS_Z : ((j == 3 || j == 5) ? PNR_AXIS_X : PNR_AXIS_Y);
+    if (CHAIN != PNR_CHAIN_GENERIC) return j == 0 ? PNR_AXIS_Z : ((j == 3 || j == 5) ? PNR_AXIS_X : PNR_AXIS_Y);
     return p.axis_code[j];
 }
 template <int CHAIN>
 PNR_HD V3 pnr_axis(const PnrParams& p, int j) {
-    if (CHAIN == PNR_CHAIN_PIONEER) {
+    if (CHAIN != PNR_CHAIN_GENERIC) {
         const int c = pnr_code<CHAIN>(p, j);
         return v3(c == PNR_AXIS_X ? 1.f : 0.f, c == PNR_AXIS_Y ? 1.f : 0.f, c == PNR_AXIS_Z ? 1.f : 0.f);
     }
@@ -66,7 +71,7 @@ PNR_HD V3 pnr_axis(const PnrParams& p, int j) {
 // axis . v,  axis * s,  v x (axis * s),  I axis (a column),  H^T axis (a row): single components when the axis is known
 template <int CHAIN>
 PNR_HD float pnr_axis_dot(const PnrParams& p, int j, V3 v) {
-    if (CHAIN == PNR_CHAIN_PIONEER) {
+    if (CHAIN != PNR_CHAIN_GENERIC) {
         const int c = pnr_code<CHAIN>(p, j);
         return c == PNR_AXIS_X ? v.x : (c == PNR_AXIS_Y ? v.y : v.z);
     }
@@ -74,7 +79,7 @@ PNR_HD float pnr_axis_dot(const PnrParams& p, int j, V3 v) {
 }
 template <int CHAIN>
 PNR_HD V3 pnr_axis_scaled(const PnrParams& p, int j, float s) {
-    if (CHAIN == PNR_CHAIN_PIONEER) {
+    if (CHAIN != PNR_CHAIN_GENERIC) {
         const int c = pnr_code<CHAIN>(p, j);
         return v3(c == PNR_AXIS_X ? s : 0.f, c == PNR_AXIS_Y ? s : 0.f, c == PNR_AXIS_Z ? s : 0.f);
     }
@@ -82,7 +87,7 @@ PNR_HD V3 pnr_axis_scaled(const PnrParams& p, int j, float s) {
 }
 template <int CHAIN>
 PNR_HD V3 pnr_cross_axis(const PnrParams& p, int j, V3 a, float s) {     // a x (axis * s)
-    if (CHAIN == PNR_CHAIN_PIONEER) {
+    if (CHAIN != PNR_CHAIN_GENERIC) {
         const int c = pnr_code<CHAIN>(p, j);
         if (c == PNR_AXIS_X) return v3(0.f, a.z * s, -a.y * s);
         if (c == PNR_AXIS_Y) return v3(-a.z * s, 0.f, a.x * s);
@@ -92,7 +97,7 @@ PNR_HD V3 pnr_cross_axis(const PnrParams& p, int j, V3 a, float s) {     // a x 
 }
 template <int CHAIN>
 PNR_HD V3 pnr_sym_axis(const PnrParams& p, int j, const Sym3& m) {        // m * axis
-    if (CHAIN == PNR_CHAIN_PIONEER) {
+    if (CHAIN != PNR_CHAIN_GENERIC) {
         const int c = pnr_code<CHAIN>(p, j);
         if (c == PNR_AXIS_X) return v3(m.xx, m.xy, m.xz);
         if (c == PNR_AXIS_Y) return v3(m.xy, m.yy, m.yz);
@@ -102,7 +107,7 @@ PNR_HD V3 pnr_sym_axis(const PnrParams& p, int j, const Sym3& m) {        // m *
 }
 template <int CHAIN>
 PNR_HD V3 pnr_matT_axis(const PnrParams& p, int j, const Mat3& a) {       // a^T * axis
-    if (CHAIN == PNR_CHAIN_PIONEER) {
+    if (CHAIN != PNR_CHAIN_GENERIC) {
         const int c = pnr_code<CHAIN>(p, j);
         return v3(a.m[3 * c + 0], a.m[3 * c + 1], a.m[3 * c + 2]);
     }
@@ -113,7 +118,7 @@ PNR_HD V3 pnr_matT_axis(const PnrParams& p, int j, const Mat3& a) {       // a^T
 // 1 and 2: along z, 3: along y, 4: along x; pioneer_knm_6dof.urdf:209-264), so the cross product is two multiplies.
 template <int CHAIN>
 PNR_HD V3 pnr_origin_cross(const PnrParams& p, int j, V3 v) {
-    if (CHAIN == PNR_CHAIN_PIONEER) {
+    if (CHAIN != PNR_CHAIN_GENERIC) {
         if (j == 0 || j == 5) return v3(0.f, 0.f, 0.f);
         if (j == 1 || j == 2) { const float z = p.origin_xyz[j][2]; return v3(-z * v.y, z * v.x, 0.f); }
         if (j == 3) { const float y = p.origin_xyz[j][1]; return v3(y * v.z, 0.f, -y * v.x); }
@@ -127,7 +132,7 @@ PNR_HD V3 pnr_origin_cross(const PnrParams& p, int j, V3 v) {
 template <int CHAIN>
 PNR_HD V3 pnr_axis_rot(const PnrParams& p, int j, float s, float c, V3 v) {
     const int code = pnr_code<CHAIN>(p, j);
-    if (CHAIN != PNR_CHAIN_PIONEER) s *= p.axis_sign[j];
+    if (CHAIN == PNR_CHAIN_GENERIC) s *= p.axis_sign[j];
     if (code == PNR_AXIS_X) return v3(v.x, fmaf(c, v.y, -s * v.z), fmaf(s, v.y, c * v.z));
     if (code == PNR_AXIS_Y) return v3(fmaf(c, v.x, s * v.z), v.y, fmaf(-s, v.x, c * v.z));
     if (code == PNR_AXIS_Z) return v3(fmaf(c, v.x, -s * v.y), fmaf(s, v.x, c * v.y), v.z);
@@ -142,7 +147,7 @@ PNR_HD V3 pnr_axis_rot(const PnrParams& p, int j, float s, float c, V3 v) {
 template <int CHAIN>
 PNR_HD V3 pnr_rot(const PnrParams& p, int j, float s, float c, V3 v) {
     V3 r = pnr_axis_rot<CHAIN>(p, j, s, c, v);
-    if (CHAIN != PNR_CHAIN_PIONEER && p.origin_has_rot[j]) {
+    if (CHAIN == PNR_CHAIN_GENERIC && p.origin_has_rot[j]) {
         const float* O = p.origin_rot[j];
         r = v3(O[0] * r.x + O[1] * r.y + O[2] * r.z, O[3] * r.x + O[4] * r.y + O[5] * r.z, O[6] * r.x + O[7] * r.y + O[8] * r.z);
     }
@@ -152,7 +157,7 @@ PNR_HD V3 pnr_rot(const PnrParams& p, int j, float s, float c, V3 v) {
 // parent -> child coordinates: R_j^T v
 template <int CHAIN>
 PNR_HD V3 pnr_rot_t(const PnrParams& p, int j, float s, float c, V3 v) {
-    if (CHAIN != PNR_CHAIN_PIONEER && p.origin_has_rot[j]) {
+    if (CHAIN == PNR_CHAIN_GENERIC && p.origin_has_rot[j]) {
         const float* O = p.origin_rot[j];
         v = v3(O[0] * v.x + O[3] * v.y + O[6] * v.z, O[1] * v.x + O[4] * v.y + O[7] * v.z, O[2] * v.x + O[5] * v.y + O[8] * v.z);
     }
@@ -469,6 +474,7 @@ PNR_HD void pnr_shift_ek(int k, float pk, Sym3& I, Mat3& H, const Sym3& M) {
     sset(I, b, k, fmaf(pk, h_ka, sget(I, b, k)));
 }
 
+template <bool ISO>
 PNR_HD void pnr_aba_pioneer(const PnrParams& p, const float (&q)[PNR_DOF], const float (&qd)[PNR_DOF],
                             const float (&tau)[PNR_DOF], float (&qdd)[PNR_DOF]) {
     PnrDynWork w;
@@ -480,15 +486,18 @@ PNR_HD void pnr_aba_pioneer(const PnrParams& p, const float (&q)[PNR_DOF], const
         pnr_sincos_bounded(q[i], w.sn[i], w.cs[i]);                    // chain_kind 1 implies joint limits within +-64 rad
         const Sym3 Io = {p.dyn_io[i][0], p.dyn_io[i][1], p.dyn_io[i][2], p.dyn_io[i][3], p.dyn_io[i][4], p.dyn_io[i][5]};
         const V3 mc = v3(p.dyn_mc[i][0], p.dyn_mc[i][1], p.dyn_mc[i][2]);
+        const bool iso = ISO && i < PNR_DOF - 1;                       // bias force (0, m om x vl)
         if (i == 0) {
             // fixed base: om = e_k qd, vl = 0, c = 0;  n = Io om,  f = -mc x om,  p = (om x n, om x f)
             const float wq = qd[0];
-            V3 n = v3(sget(Io, 0, k) * wq, sget(Io, 1, k) * wq, sget(Io, 2, k) * wq);
-            V3 f = v3(0.f, 0.f, 0.f);
-            vset(f, a, -vget(mc, b) * wq);
-            vset(f, b, vget(mc, a) * wq);
-            w.p_ang[0] = pnr_ek_cross(k, wq, n);
-            w.p_lin[0] = pnr_ek_cross(k, wq, f);
+            if (!iso) {
+                V3 n = v3(sget(Io, 0, k) * wq, sget(Io, 1, k) * wq, sget(Io, 2, k) * wq);
+                V3 f = v3(0.f, 0.f, 0.f);
+                vset(f, a, -vget(mc, b) * wq);
+                vset(f, b, vget(mc, a) * wq);
+                w.p_ang[0] = pnr_ek_cross(k, wq, n);
+                w.p_lin[0] = pnr_ek_cross(k, wq, f);
+            }
             om = v3(0.f, 0.f, 0.f);
             vset(om, k, wq);
         } else {
@@ -497,10 +506,14 @@ PNR_HD void pnr_aba_pioneer(const PnrParams& p, const float (&q)[PNR_DOF], const
             vl = pnr_rotk(k, -w.sn[i], w.cs[i], t);
             w.c_ang[i] = pnr_cross_ek(k, om, qd[i]);
             w.c_lin[i] = pnr_cross_ek(k, vl, qd[i]);
-            const V3 n = symmul(Io, om) + cross(mc, vl);
-            const V3 f = vl * p.dyn_mass[i] - cross(mc, om);
-            w.p_ang[i] = cross(om, n) + cross(vl, f);
-            w.p_lin[i] = cross(om, f);
+            if (iso) {
+                w.p_lin[i] = cross(om, vl) * p.dyn_mass[i];
+            } else {
+                const V3 n = symmul(Io, om) + cross(mc, vl);
+                const V3 f = vl * p.dyn_mass[i] - cross(mc, om);
+                w.p_ang[i] = cross(om, n) + cross(vl, f);
+                w.p_lin[i] = cross(om, f);
+            }
         }
     }
     // ---- pass 2 (tip -> base): articulated inertias and bias forces
@@ -523,14 +536,20 @@ PNR_HD void pnr_aba_pioneer(const PnrParams& p, const float (&q)[PNR_DOF], const
             Ul = v3(p.dyn_tip_ul[0], p.dyn_tip_ul[1], p.dyn_tip_ul[2]);
             dinv = p.dyn_tip_dinv;
         } else {                                                        // own rigid body + what the child handed up
-            const V3 mc = v3(p.dyn_mc[i][0], p.dyn_mc[i][1], p.dyn_mc[i][2]);
             const float m = p.dyn_mass[i];
-            I.xx += p.dyn_io[i][0]; I.xy += p.dyn_io[i][1]; I.xz += p.dyn_io[i][2];
-            I.yy += p.dyn_io[i][3]; I.yz += p.dyn_io[i][4]; I.zz += p.dyn_io[i][5];
-            H.m[1] -= mc.z; H.m[2] += mc.y; H.m[3] += mc.z; H.m[5] -= mc.x; H.m[6] -= mc.y; H.m[7] += mc.x;
+            if (ISO) {                                                  // centre of mass on the origin, inertia iota * 1
+                const float iota = p.dyn_io[i][0];
+                I.xx += iota; I.yy += iota; I.zz += iota;
+                if (i > 0) pa_lin = pa_lin + w.p_lin[i];                // the base joint's own bias force is zero
+            } else {
+                const V3 mc = v3(p.dyn_mc[i][0], p.dyn_mc[i][1], p.dyn_mc[i][2]);
+                I.xx += p.dyn_io[i][0]; I.xy += p.dyn_io[i][1]; I.xz += p.dyn_io[i][2];
+                I.yy += p.dyn_io[i][3]; I.yz += p.dyn_io[i][4]; I.zz += p.dyn_io[i][5];
+                H.m[1] -= mc.z; H.m[2] += mc.y; H.m[3] += mc.z; H.m[5] -= mc.x; H.m[6] -= mc.y; H.m[7] += mc.x;
+                pa_ang = pa_ang + w.p_ang[i];
+                pa_lin = pa_lin + w.p_lin[i];
+            }
             M.xx += m; M.yy += m; M.zz += m;
-            pa_ang = pa_ang + w.p_ang[i];
-            pa_lin = pa_lin + w.p_lin[i];
             Ua = v3(sget(I, 0, k), sget(I, 1, k), sget(I, 2, k));       // I e_k
             Ul = v3(H.m[3 * k], H.m[3 * k + 1], H.m[3 * k + 2]);        // H^T e_k
             dinv = 1.f / vget(Ua, k);
@@ -607,7 +626,8 @@ PNR_HD void pnr_aba(const PnrParams& p, const float (&q)[PNR_DOF], const float (
 #ifdef PNR_ABA_BASELINE                                 // A/B builds: the first specialisation
     pnr_aba_general<CHAIN>(p, q, qd, tau, qdd);
 #else
-    if (CHAIN == PNR_CHAIN_PIONEER) pnr_aba_pioneer(p, q, qd, tau, qdd);
+    if (CHAIN == PNR_CHAIN_PIONEER_ISO) pnr_aba_pioneer<true>(p, q, qd, tau, qdd);
+    else if (CHAIN != PNR_CHAIN_GENERIC) pnr_aba_pioneer<false>(p, q, qd, tau, qdd);
     else pnr_aba_general<CHAIN>(p, q, qd, tau, qdd);
 #endif
 }

@@ -164,3 +164,30 @@ def test_generic_chain_kernel_against_the_oracle(tmp_path):
     for k in range(0, n, 8):
         assert np.abs(o[k, 126:129] - fk_pointer(kin, q0[k])).max() <= 2e-4
     kenv.close()
+
+
+@pytest.mark.parametrize("chain", [0, 1])
+def test_less_specialised_kernels_agree_with_the_shipped_one(monkeypatch, chain):
+    """The shipped URDF runs pnr_step_dynamic_kernel<..., PIONEER_ISO>.  PNR_DYN_CHAIN forces the PIONEER (axis structure
+    only) and GENERIC (run-time axis codes) instantiations on the same robot: one env step from identical states must
+    land within the float32-vs-float64 bar of each other (all three are checked against the oracle on the CPU in
+    tests/test_dynamics_host.py)."""
+    n = 2048
+    kw = dict(gravity=9.81, kp=800.0, kd=200.0, torque_scale=1e4)
+    rng = np.random.default_rng(21)
+    ref_env = make(n, seed=5, **kw)
+    q0 = rng.uniform(ref_env.r_lo * 0.9, ref_env.r_hi * 0.9, size=(n, 6)).astype(np.float32)
+    qd0 = (rng.normal(size=(n, 6)) * 0.5).astype(np.float32)
+    act = torch.as_tensor(rng.uniform(ref_env.r_lo, ref_env.r_hi, size=(n, 6)).astype(np.float32)).cuda()
+    ref_env.set_state(r=q0, v=qd0)
+    ref_env.step_tensor(act)
+    ref = ref_env.state()
+    monkeypatch.setenv("PNR_DYN_CHAIN", str(chain))
+    env = make(n, seed=5, **kw)
+    env.set_state(r=q0, v=qd0)
+    env.step_tensor(act)
+    got = env.state()
+    monkeypatch.delenv("PNR_DYN_CHAIN")
+    assert (got["r"] - ref["r"]).abs().max().item() <= 2e-5
+    assert (got["v"] - ref["v"]).abs().max().item() <= 2e-4
+    ref_env.close(); env.close()
