@@ -40,11 +40,12 @@ BYTES_PER_ENV_STEP = BYTES_IO + BYTES_STATE          # 761
 FRAME_SKIP = 10
 FALLBACK_HBM_GBS = 6650.0                            # /opt/skills/guides/B200_PROFILING.md fallback
 L2_FLUSH_BYTES = 512 << 20                           # > 4x the 126 MB L2
-# Tier-B dynamic kernel, from the committed ncu capture (profiles/r01_dyn_v3_step_dynamic_65536.md): FFMA 8,056 +
-# FMUL 4,734 + FADD 3,733 thread instructions per env-step (10 ABA substeps) = 24,579 flop; FP32 FMA peak measured on
-# this pool's B200 with tools/fma_peak.py = 72.6 TFLOP/s (nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)
-DYN_FLOP_PER_ENV_STEP = 2 * 8056 + 4734 + 3733
-DYN_FP_INSTR_PER_ENV_STEP = 8056 + 4734 + 3733
+# Tier-B dynamic kernel, from the committed ncu capture (profiles/r01_dyn_v4_step_dynamic_65536.md): 10,397,696 FFMA +
+# 5,847,040 FMUL + 3,362,816 FADD warp instructions per 2,048-tile launch = FFMA 5,077 + FMUL 2,855 + FADD 1,642 thread
+# instructions per env-step (10 ABA substeps) = 14,651 flop; FP32 FMA peak measured on this pool's B200 with
+# tools/fma_peak.py = 72.6 TFLOP/s (nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)
+DYN_FLOP_PER_ENV_STEP = 2 * 5077 + 2855 + 1642
+DYN_FP_INSTR_PER_ENV_STEP = 5077 + 2855 + 1642
 FP32_PEAK_TFLOPS = 72.6
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of pnr_step_kernel from the committed `ncu --set full`
 # captures (profiles/r01_v5_step_65536.md, profiles/r01_v5_step_1m.md).  At 65,536 envs most of the 36 MB of
@@ -288,52 +289,6 @@ def time_device_steps(torch, env, actions, obs_ring, reward, flags, steps, warmu
     return sum(per), per
 
 
-def time_device_steps_graph(torch, env, actions, obs_ring, reward, flags, steps, flush, chunk=50, floor=False):
-    """The same measurement with the host taken out of the loop: [L2 flush, event, step kernel, event] x chunk is
-    captured into ONE CUDA graph (the events as external event-record nodes) and replayed until `steps` steps are
-    timed.  Every step is still bracketed by its own event pair and preceded by an untimed flush; what changes is
-    that the kernel is launched by the graph executor instead of the stream front-end, whose launch + event cost is
-    a fixed ~6 us per pair (timing_floor_ms).  floor=True times the library's 1-thread statistics kernel instead.
-    Returns (sum of per-step ms, list of per-step ms)."""
-    n_act, n_obs = actions.shape[0], obs_ring.shape[0]
-    per = []
-
-    def body(k):
-        if floor:
-            env.episode_stats_tensor()
-        else:
-            env.step_tensor(actions[k % n_act], out=(obs_ring[k % n_obs], reward, flags))
-
-    def build(count):
-        starts = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(count)]
-        stops = [torch.cuda.Event(enable_timing=True, external=True) for _ in range(count)]
-        g = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(g):
-            for k in range(count):
-                flush()
-                starts[k].record()
-                body(k)
-                stops[k].record()
-        return g, starts, stops
-
-    body(0)                                              # one-time kernel attribute setup outside the capture
-    torch.cuda.synchronize()
-    done = 0
-    graphs = {}
-    while done < steps:
-        count = min(chunk, steps - done)
-        if count not in graphs:
-            graphs[count] = build(count)
-            graphs[count][0].replay()                    # untimed first replay (graph upload)
-            torch.cuda.synchronize()
-        g, starts, stops = graphs[count]
-        g.replay()
-        torch.cuda.synchronize()
-        per.extend(s.elapsed_time(e) for s, e in zip(starts, stops))
-        done += count
-    return sum(per), per
-
-
 def time_back_to_back(torch, env, actions, obs_ring, reward, flags, steps):
     n_act, n_obs = actions.shape[0], obs_ring.shape[0]
     s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -484,23 +439,6 @@ def ours_arm(args):
     graph_ms = max_over_ranks(graph_ms)
     value_graph = total_envs * graph_steps / (graph_ms / 1e3)
     floor_ms = timing_floor(torch, env, flush)
-    # per-step event pairs again, launched by the graph executor instead of the stream front-end
-    graph_ev = None
-    if args.flush != "none":
-        try:
-            g_steps = min(args.steps, 1000)
-            g_ms, g_per = time_device_steps_graph(torch, env, actions, obs_ring, reward, flags, g_steps, flush)
-            _, g_floor = time_device_steps_graph(torch, env, actions, obs_ring, reward, flags, 200, flush, floor=True)
-            g_srt, f_srt = sorted(g_per), sorted(g_floor)
-            g_ms_max = max_over_ranks(g_ms)
-            graph_ev = {"ms_per_step": g_ms_max / g_steps, "value": total_envs * g_steps / (g_ms_max / 1e3), "steps": g_steps,
-                        "p50_ms": g_srt[len(g_srt) // 2], "timing_floor_ms": f_srt[len(f_srt) // 2],
-                        "achieved_gbs": BYTES_PER_ENV_STEP * n / (g_ms / g_steps / 1e3) / 1e9,
-                        "method": "[512 MiB flush, event, step kernel, event] x 50 captured in one CUDA graph "
-                                  "(external event-record nodes), replayed; same flush, same per-step event pairs, "
-                                  "no stream front-end launch cost inside the pair"}
-        except Exception as exc:  # noqa: BLE001
-            graph_ev = {"error": repr(exc)}
 
     # ---- end to end through the public host API: pinned host actions in, obs/reward/done out ------------
     e2e_steps = min(args.steps, 300)
@@ -536,7 +474,6 @@ def ours_arm(args):
                    "parallelism": f"env-sharded x{world}, no data-path collective; one stats all-reduce per iteration"},
         "substeps_per_sec": value * FRAME_SKIP,
         "timing_floor_ms": floor_ms,
-        "graph_launched_event_pairs": graph_ev,
         "value_l2_warm": value_l2_warm,
         "ms_per_step_l2_warm": warm_ms / args.steps,
         "value_l2_warm_cuda_graph": value_graph,
@@ -603,7 +540,7 @@ def ours_arm(args):
                          "frac": dyn_tflops / FP32_PEAK_TFLOPS, "flop_per_env_step": DYN_FLOP_PER_ENV_STEP,
                          "fp32_issue_frac": dyn_value * DYN_FP_INSTR_PER_ENV_STEP / (FP32_PEAK_TFLOPS / 2 * 1e12),
                          "peak_source": "tools/fma_peak.py on this pool's B200 (FMA = 2 flop)",
-                         "kernel": "pnr_step_dynamic_kernel<TERMINAL,false,PIONEER>"}}
+                         "kernel": "pnr_step_dynamic_kernel<TERMINAL,false,PIONEER_ISO>"}}
         e.close()
         del a, o, r, f
 
