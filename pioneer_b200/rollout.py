@@ -22,23 +22,37 @@ from .obs_filter import MeanStdObsFilter
 
 
 class GaussianMlpPolicy(nn.Module):
-    """137 -> 256 -> 256 -> 12 (mean, log_std), tanh: the launcher's `fcnet_hiddens` / `fcnet_activation`."""
+    """137 -> 256 -> 256 -> 12 (mean, log_std), tanh: the launcher's `fcnet_hiddens` / `fcnet_activation`.
+
+    The input is zero-padded to 144 columns and the head to 16 outputs: cuBLAS picks its 16-byte-aligned bf16 kernels
+    only when K and N are multiples of 8 (with K = 137 the first layer ran a legacy align1 kernel, 112 us per
+    131,072-row call against 16 us padded; profiles/r01_rollout_launches.md).  The padding columns of the first weight
+    multiply zeros and the padding outputs are dropped, so the function is the 137 -> 12 network."""
+
+    IN_PAD = (OBS_DIM + 7) // 8 * 8           # 144
+    OUT_PAD = (2 * DOF + 7) // 8 * 8          # 16
 
     def __init__(self, hiddens=(256, 256), dtype=torch.float32):
         super().__init__()
-        layers, d = [], OBS_DIM
+        layers, d = [], self.IN_PAD
         for h in hiddens:
             layers += [nn.Linear(d, h), nn.Tanh()]
             d = h
-        layers.append(nn.Linear(d, 2 * DOF))
+        layers.append(nn.Linear(d, self.OUT_PAD))
         self.net = nn.Sequential(*layers).to(dtype)
         with torch.no_grad():
+            self.net[0].weight[:, OBS_DIM:].zero_()
             self.net[-1].weight.mul_(0.01)
             self.net[-1].bias.zero_()
+        self._x: Optional[torch.Tensor] = None
 
     def forward(self, obs: torch.Tensor):
-        out = self.net(obs.to(self.net[0].weight.dtype)).float()
-        return out[:, :DOF], out[:, DOF:].clamp(-5.0, 2.0)
+        w = self.net[0].weight
+        if self._x is None or self._x.shape[0] != obs.shape[0] or self._x.device != obs.device or self._x.dtype != w.dtype:
+            self._x = torch.zeros((obs.shape[0], self.IN_PAD), dtype=w.dtype, device=obs.device)
+        self._x[:, :OBS_DIM].copy_(obs)                                # cast + pad in one strided copy
+        out = self.net(self._x).float()
+        return out[:, :DOF], out[:, DOF:2 * DOF].clamp(-5.0, 2.0)
 
 
 class RolloutWorker:
