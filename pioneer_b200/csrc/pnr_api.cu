@@ -38,7 +38,7 @@ struct pnr_handle {
     int64_t launches = 0;
     float a_max[PNR_DOF];
     // observation normaliser (pnr_filter_*): device accumulator, applied statistics, host-side running statistics
-    double* filt_delta = nullptr;        // device double[PNR_FILTER_DELTA_LEN]
+    double* filt_delta = nullptr;        // device double[PNR_FILTER_SLOTS][PNR_FILTER_DELTA_LEN]; copy 0 is what is read
     float* filt_applied = nullptr;       // device float[2 * PNR_OBS_DIM]: mean, 1 / (std + 1e-8)
     double filt_count = 0.0;
     double filt_mean[PNR_OBS_DIM] = {}, filt_m2[PNR_OBS_DIM] = {};
@@ -517,9 +517,9 @@ static int pnr_filter_upload_applied(pnr_handle* h, cudaStream_t stream) {
 
 static int pnr_filter_ensure(pnr_handle* h, cudaStream_t stream) {
     if (h->filt_delta) return PNR_OK;
-    PNR_CUDA(cudaMalloc(&h->filt_delta, sizeof(double) * PNR_FILTER_DELTA_LEN));
+    PNR_CUDA(cudaMalloc(&h->filt_delta, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN));
     PNR_CUDA(cudaMalloc(&h->filt_applied, sizeof(float) * 2 * PNR_OBS_DIM));
-    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_DELTA_LEN, stream));
+    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN, stream));
     return pnr_filter_upload_applied(h, stream);
 }
 
@@ -530,7 +530,7 @@ extern "C" int pnr_filter_configure(pnr_handle* h, double clip, int demean, int 
     int rc = pnr_filter_ensure(h, nullptr);
     if (rc != PNR_OK) return rc;
     // the accumulator is relative to the applied mean: rows pushed under the old setting are dropped
-    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_DELTA_LEN, nullptr));
+    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN, nullptr));
     return pnr_filter_upload_applied(h, nullptr);
 }
 
@@ -568,6 +568,7 @@ extern "C" int pnr_filter_delta_device(pnr_handle* h, double* out_device, void* 
     PnrDeviceGuard guard(h->device);
     int rc = pnr_filter_ensure(h, (cudaStream_t)stream);
     if (rc != PNR_OK) return rc;
+    PNR_CUDA(pnr_launch_filter_fold(h->filt_delta, (cudaStream_t)stream));
     PNR_CUDA(cudaMemcpyAsync(out_device, h->filt_delta, sizeof(double) * PNR_FILTER_DELTA_LEN, cudaMemcpyDeviceToDevice,
                              (cudaStream_t)stream));
     return PNR_OK;
@@ -584,6 +585,7 @@ extern "C" int pnr_filter_sync(pnr_handle* h, const double* merged, void* stream
         std::memcpy(d, merged, sizeof(d));
         PNR_CUDA(cudaStreamSynchronize(s));
     } else {
+        PNR_CUDA(pnr_launch_filter_fold(h->filt_delta, s));
         PNR_CUDA(cudaMemcpyAsync(d, h->filt_delta, sizeof(d), cudaMemcpyDeviceToHost, s));
         PNR_CUDA(cudaStreamSynchronize(s));
     }
@@ -601,7 +603,7 @@ extern "C" int pnr_filter_sync(pnr_handle* h, const double* merged, void* stream
         }
         h->filt_count = n;
     }
-    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_DELTA_LEN, s));
+    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN, s));
     return pnr_filter_upload_applied(h, s);
 }
 
@@ -625,6 +627,6 @@ extern "C" int pnr_filter_set(pnr_handle* h, double count, const double* mean, c
         h->filt_mean[c] = mean[c];
         h->filt_m2[c] = count > 1.0 ? var[c] * (count - 1.0) : 0.0;
     }
-    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_DELTA_LEN, (cudaStream_t)stream));
+    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN, (cudaStream_t)stream));
     return pnr_filter_upload_applied(h, (cudaStream_t)stream);
 }

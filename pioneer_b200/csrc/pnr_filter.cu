@@ -112,11 +112,29 @@ pnr_filter_kernel(const float* __restrict__ in, float* __restrict__ out, int64_t
         }
         __syncthreads();                                        // the tile may be overwritten
     }
+    double* slot = delta + (size_t)(blockIdx.x & (PNR_FILTER_SLOTS - 1)) * PNR_FILTER_DELTA_LEN;
     if (update && col_ok) {
-        atomicAdd(&delta[1 + tid], acc_s);
-        atomicAdd(&delta[1 + PNR_OBS_DIM + tid], acc_q);
+        atomicAdd(&slot[1 + tid], acc_s);
+        atomicAdd(&slot[1 + PNR_OBS_DIM + tid], acc_q);
     }
     if (update && blockIdx.x == 0 && tid == 0) atomicAdd(&delta[0], (double)n_rows);
+}
+
+// copy 0 += copies 1 .. SLOTS-1, which are cleared (see pnr_launch.h)
+__global__ void pnr_filter_fold_kernel(double* __restrict__ slots) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= PNR_FILTER_DELTA_LEN) return;
+    double acc = slots[c];
+    for (int s = 1; s < PNR_FILTER_SLOTS; ++s) {
+        acc += slots[(size_t)s * PNR_FILTER_DELTA_LEN + c];
+        slots[(size_t)s * PNR_FILTER_DELTA_LEN + c] = 0.0;
+    }
+    slots[c] = acc;
+}
+
+cudaError_t pnr_launch_filter_fold(double* delta_slots, cudaStream_t stream) {
+    pnr_filter_fold_kernel<<<(PNR_FILTER_DELTA_LEN + 127) / 128, 128, 0, stream>>>(delta_slots);
+    return cudaGetLastError();
 }
 
 cudaError_t pnr_launch_filter(int device, const float* in, float* out, int64_t n_rows, const float* applied,

@@ -333,11 +333,12 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         rowj = row + j0;
         if (FILTER) srow = scratch + buf * PNR_FSCRATCH_FLOATS + lane * PNR_FSCRATCH_STRIDE;
     }
-    if (FILTER && f_delta != nullptr) {                       // column statistics of this CTA's rows
+    if (FILTER && f_delta != nullptr) {                       // column statistics of this CTA's rows, into copy blockIdx % SLOTS
+        double* f_slot = f_delta + (size_t)(blockIdx.x & (PNR_FILTER_SLOTS - 1)) * PNR_FILTER_DELTA_LEN;
         if (part < 3) {
             if (lane < 30) {
-                atomicAdd(&f_delta[1 + f_col], f_sum);
-                atomicAdd(&f_delta[1 + PNR_OBS_DIM + f_col], f_sq);
+                atomicAdd(&f_slot[1 + f_col], f_sum);
+                atomicAdd(&f_slot[1 + PNR_OBS_DIM + f_col], f_sq);
             }
             if (blockIdx.x == 0 && lane < 12) {                // the constant columns of all N rows, analytically
                 const int g = lane >> 1, j = j0 + (lane & 1), c = 18 + 6 * g + j;
@@ -357,8 +358,8 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                     b += __shfl_xor_sync(PNR_FULL_MASK, b, ofs);
                 }
                 if (lane == 0) {
-                    atomicAdd(&f_delta[1 + 126 + i], (double)a);
-                    atomicAdd(&f_delta[1 + PNR_OBS_DIM + 126 + i], (double)b);
+                    atomicAdd(&f_slot[1 + 126 + i], (double)a);
+                    atomicAdd(&f_slot[1 + PNR_OBS_DIM + 126 + i], (double)b);
                 }
             }
             if (blockIdx.x == 0 && lane == 0) atomicAdd(&f_delta[0], (double)N);

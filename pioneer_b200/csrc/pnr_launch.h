@@ -9,7 +9,9 @@
 #define PNR_STEP_MIN_CTAS 6                                                  // 24 warps / SM, <= 85 registers: no spills (8 CTAs spill)
 #endif
 #define PNR_STEP_BUFS 2                                                      // observation tile buffers per CTA (producer / consumer pipeline)
+#ifndef PNR_STEP_MIN_CTAS_FILTER
 #define PNR_STEP_MIN_CTAS_FILTER 4                                           // fused normaliser: 39.9 KB of shared memory per CTA, <= 128 registers
+#endif
 #define PNR_FSCRATCH_STRIDE 19                                               // raw r | cos r | sin r per env (18 floats, odd stride)
 #define PNR_FSCRATCH_FLOATS (32 * PNR_FSCRATCH_STRIDE)
 #define PNR_STEP_SMEM_FILTER (PNR_STEP_SMEM + PNR_STEP_BUFS * PNR_FSCRATCH_FLOATS * sizeof(float))
@@ -19,6 +21,11 @@
 #define PNR_STEP_SMEM (PNR_STEP_BUFS * 32 * PNR_OBS_DIM * sizeof(float))     // step kernel: 17,536 B per tile buffer
 #define PNR_RO_SMEM (PNR_STEP_WARPS * 32 * PNR_OBS_DIM * sizeof(float))      // reset/observe: one tile per warp
 #define PNR_MAX_DEVICES 16
+// The statistics accumulator of the normaliser is PNR_FILTER_SLOTS copies of double[PNR_FILTER_DELTA_LEN]; a CTA adds its
+// partial sums to copy blockIdx % SLOTS.  With one copy the ~900 CTAs of a 65,536-env step queued ~900 float64 atomics on
+// each of 274 addresses and the kernel's tail took 13 us (tools/fuse_probe.py: 18.5 us without statistics, 31.7 us with).
+// pnr_launch_filter_fold adds copies 1.. into copy 0 (what the host and the all-reduce read) and clears them.
+#define PNR_FILTER_SLOTS 64
 
 // f_applied != NULL selects the fused-normaliser instantiation (float32, terminal observations only); f_delta may be NULL
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions,
@@ -33,5 +40,6 @@ cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, f
 cudaError_t pnr_launch_state_io(bool set, float4* state, int64_t N, float* r, float* v, float* a, float* potential,
                                 float* target, int32_t* t, float* ep_return, cudaStream_t stream);
 cudaError_t pnr_launch_stats_snapshot(PnrStats* stats, double env_steps, double* out, int clear, cudaStream_t stream);
+cudaError_t pnr_launch_filter_fold(double* delta_slots, cudaStream_t stream);
 cudaError_t pnr_launch_filter(int device, const float* in, float* out, int64_t n_rows, const float* applied,
                               double* delta, float clip, int update, int normalize, cudaStream_t stream);
