@@ -189,7 +189,7 @@ int pnr_filter_apply(pnr_handle* h, const float* obs_in, float* obs_out, int64_t
                      void* stream);
 /* Fuse the normaliser into pnr_step: with `on`, the observations pnr_step writes are already normalised and (with
  * `update`) their raw values have entered the statistics -- no second pass over the 548 B/env observation.  Kinematic
- * mode, PNR_ARITH_F32 and PNR_OBS_TERMINAL only (PNR_ERR_UNSUPPORTED otherwise). */
+ * mode: PNR_ARITH_F32 and PNR_OBS_TERMINAL only (PNR_ERR_UNSUPPORTED otherwise); dynamic mode: both observation modes. */
 int pnr_filter_fuse(pnr_handle* h, int on, int update);
 /* Copy the statistics accumulated since the last sync to a caller-owned DEVICE double[PNR_FILTER_DELTA_LEN]
  * (not synchronised): sum it over the ranks with one NCCL all-reduce, then hand it to pnr_filter_sync on every rank. */

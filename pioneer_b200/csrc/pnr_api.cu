@@ -407,7 +407,9 @@ extern "C" int pnr_step(pnr_handle* h, const float* actions, float* obs, float* 
     PnrDeviceGuard guard(h->device);
     if (h->cfg.mode == PNR_MODE_DYNAMIC)
         PNR_CUDA(pnr_launch_step_dynamic(h->params, h->device, h->cfg.obs_mode, h->state, actions, obs, reward, done,
-                                         h->stats, h->tick, (cudaStream_t)stream));
+                                         h->stats, h->tick, h->filt_fused ? h->filt_applied : nullptr,
+                                         (h->filt_fused && h->filt_fused_update) ? h->filt_delta : nullptr,
+                                         (float)h->filt_clip, (cudaStream_t)stream));
     else
         PNR_CUDA(pnr_launch_step(h->params, h->device, h->cfg.arith, h->cfg.obs_mode, h->state, actions, obs, reward, done,
                                  h->stats, h->tick, h->filt_fused ? h->filt_applied : nullptr,
@@ -536,8 +538,8 @@ extern "C" int pnr_filter_configure(pnr_handle* h, double clip, int demean, int 
 
 extern "C" int pnr_filter_fuse(pnr_handle* h, int on, int update) {
     if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_fuse: null handle");
-    if (on && (h->cfg.mode != PNR_MODE_KINEMATIC || h->cfg.arith != PNR_ARITH_F32 || h->cfg.obs_mode != PNR_OBS_TERMINAL))
-        return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_filter_fuse: the fused normaliser is built for the kinematic mode, float32 "
+    if (on && h->cfg.mode == PNR_MODE_KINEMATIC && (h->cfg.arith != PNR_ARITH_F32 || h->cfg.obs_mode != PNR_OBS_TERMINAL))
+        return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_filter_fuse: in the kinematic mode the fused normaliser is built for float32 "
                                              "arithmetic and terminal observations; use pnr_filter_apply otherwise");
     PnrDeviceGuard guard(h->device);
     if (on) {

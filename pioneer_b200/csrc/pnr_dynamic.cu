@@ -18,7 +18,8 @@ template <int OBS_MODE, bool OBSTACLES, int CHAIN>
 __global__ void __launch_bounds__(PNR_STEP_THREADS, PNR_DYN_MIN_CTAS)
 pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                         float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
-                        PnrStats* __restrict__ stats, uint32_t tick) {
+                        PnrStats* __restrict__ stats, uint32_t tick, const float* __restrict__ f_applied,
+                        double* __restrict__ f_delta, float f_clip) {
     extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float* tile = smem + warp * PNR_TILE_FLOATS;
@@ -27,6 +28,15 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
     const int64_t n_tiles = (N + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
     bool tile_busy = false;
     pnr_pack_obs_const(p, row);
+    // fused observation normaliser (pnr_filter_fuse; warp-uniform run-time switch): this warp owns the whole tile, so
+    // after the rows are packed it runs the column pass of pnr_filter_kernel on the 101 changing columns (lane = column,
+    // four passes) and pushes the tile's float64 column sums to accumulator copy blockIdx % SLOTS.  The 36 constant
+    // columns are normalised here, once, and their statistics added analytically by one thread of the grid.
+    const bool filt = f_applied != nullptr;
+    if (filt) {
+#pragma unroll
+        for (int c = 18; c < 54; ++c) row[c] = pnr_normalise(row[c], f_applied[c], f_applied[PNR_OBS_DIM + c], f_clip);
+    }
     for (int64_t t_idx = (int64_t)blockIdx.x * PNR_STEP_WARPS + warp; t_idx < n_tiles;
          t_idx += (int64_t)gridDim.x * PNR_STEP_WARPS) {
         const int64_t env_raw = t_idx * PNR_TILE_ENVS + lane;
@@ -88,9 +98,54 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         }
         if (active) pnr_store_env(state, N, env, s);
         const int64_t rows_left = N - t_idx * PNR_TILE_ENVS;
-        pnr_emit_tile(tile, obs + t_idx * (int64_t)PNR_TILE_FLOATS,
-                      rows_left < PNR_TILE_ENVS ? (int)rows_left : PNR_TILE_ENVS, lane);
+        const int rows_valid = rows_left < PNR_TILE_ENVS ? (int)rows_left : PNR_TILE_ENVS;
+        if (filt) {
+            __syncwarp();
+            double* f_slot = f_delta ? f_delta + (size_t)(blockIdx.x & (PNR_FILTER_SLOTS - 1)) * PNR_FILTER_DELTA_LEN : nullptr;
+#pragma unroll 1
+            for (int pass = 0; pass < 4; ++pass) {
+                const int cc = pass * 32 + lane;                   // index among the 101 changing columns
+                if (cc < PNR_OBS_DIM - 36) {
+                    const int c = cc < 18 ? cc : cc + 36;
+                    const float mean = f_applied[c], inv = f_applied[PNR_OBS_DIM + c];
+                    float* colp = tile + c;
+                    double s0 = 0.0, q0 = 0.0, s1 = 0.0, q1 = 0.0;
+                    int r = 0;
+#pragma unroll 4
+                    for (; r + 1 < rows_valid; r += 2) {
+                        const float d0 = colp[r * PNR_OBS_DIM] - mean, d1 = colp[(r + 1) * PNR_OBS_DIM] - mean;
+                        const double e0 = (double)d0, e1 = (double)d1;
+                        s0 += e0; q0 = fma(e0, e0, q0);
+                        s1 += e1; q1 = fma(e1, e1, q1);
+                        colp[r * PNR_OBS_DIM] = fminf(fmaxf(d0 * inv, -f_clip), f_clip);
+                        colp[(r + 1) * PNR_OBS_DIM] = fminf(fmaxf(d1 * inv, -f_clip), f_clip);
+                    }
+                    if (r < rows_valid) {
+                        const float d0 = colp[r * PNR_OBS_DIM] - mean;
+                        const double e0 = (double)d0;
+                        s0 += e0; q0 = fma(e0, e0, q0);
+                        colp[r * PNR_OBS_DIM] = fminf(fmaxf(d0 * inv, -f_clip), f_clip);
+                    }
+                    if (f_slot) {
+                        atomicAdd(&f_slot[1 + c], s0 + s1);
+                        atomicAdd(&f_slot[1 + PNR_OBS_DIM + c], q0 + q1);
+                    }
+                }
+            }
+        }
+        pnr_emit_tile(tile, obs + t_idx * (int64_t)PNR_TILE_FLOATS, rows_valid, lane);
         tile_busy = true;
+    }
+    if (filt && f_delta && blockIdx.x == 0 && warp == 0) {         // rows pushed + the constant columns of all N rows
+        if (lane == 0) atomicAdd(&f_delta[0], (double)N);
+        for (int c = 18 + lane; c < 54; c += 32) {
+            const int g = (c - 18) / PNR_DOF, j = (c - 18) % PNR_DOF;
+            const float x = g == 0 ? p.r_lo[j] : g == 1 ? p.cos_r_lo[j] : g == 2 ? p.sin_r_lo[j]
+                          : g == 3 ? p.r_hi[j] : g == 4 ? p.cos_r_hi[j] : p.sin_r_hi[j];
+            const double d = (double)(x - f_applied[c]);
+            atomicAdd(&f_delta[1 + c], (double)N * d);
+            atomicAdd(&f_delta[1 + PNR_OBS_DIM + c], (double)N * d * d);
+        }
     }
     if (lane == 0) pnr_bulk_wait_read<0>();
 }
@@ -105,8 +160,9 @@ static int pnr_dyn_resident(const void* fn) {
 
 cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode, float4* state, const float* actions,
                                     float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick,
-                                    cudaStream_t stream) {
-    typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t);
+                                    const float* f_applied, double* f_delta, float f_clip, cudaStream_t stream) {
+    typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, const float*,
+                         double*, float);
 #define PNR_DYN_ROW(CH) \
     {{pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, false, CH>, pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, true, CH>}, \
      {pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, false, CH>, pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, true, CH>}}
@@ -127,6 +183,7 @@ cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode
     int64_t grid = (p.n_envs + per_cta - 1) / per_cta;
     if (grid > resident) grid = resident;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, PNR_STEP_THREADS, PNR_RO_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick);
+    kern<<<(unsigned)grid, PNR_STEP_THREADS, PNR_RO_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick, f_applied,
+                                                                        f_delta, f_clip);
     return cudaGetLastError();
 }

@@ -26,7 +26,7 @@ class MeanStdObsFilter:
         """``fused=True``: the env's step kernel itself normalises the observations it writes and pushes their raw values
         into the statistics (pnr_filter_fuse) -- ``env.step_tensor`` then returns normalised observations and this
         object is only needed for ``sync()``; the first observations of a run (``env.reset()``) still go through
-        ``__call__``.  Kinematic mode, float32 arithmetic, terminal observations only."""
+        ``__call__``.  Kinematic mode: float32 arithmetic and terminal observations only; dynamic mode: both observation modes."""
         self.env = env
         self._lib, self._h = env._lib, env._h
         self.clip, self.demean, self.destd, self.fused = float(clip), bool(demean), bool(destd), bool(fused)

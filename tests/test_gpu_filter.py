@@ -118,3 +118,40 @@ def test_fused_step_normaliser_equals_the_two_pass_path(n):
         MeanStdObsFilter(c, fused=True)
     for e in (a, b, c):
         e.close()
+
+
+@pytest.mark.parametrize("obs_mode", ["terminal", "autoreset"])
+def test_fused_normaliser_in_the_dynamic_kernel_equals_the_two_pass_path(obs_mode):
+    """Dynamic mode (ABA kernel): the warp that owns a tile normalises it before the bulk store.  Same numbers as the
+    plain dynamic step followed by pnr_filter_apply -- bit for bit under the same applied statistics -- in both
+    observation modes (the auto-reset rows are normalised like any other), ragged last tile included."""
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv, SimulationConfig
+    from pioneer_b200.obs_filter import MeanStdObsFilter
+    n = 4096 + 13
+
+    def make():
+        return BatchedPioneerEnv(n, seed=9, simulation_config=SimulationConfig(gravity=9.81),
+                                 batch_config=BatchConfig(mode="dynamic", kp=800.0, kd=200.0, torque_scale=1e4,
+                                                          max_episode_steps=3, obs_mode=obs_mode))
+    a, b = make(), make()
+    fa, fb = MeanStdObsFilter(a), MeanStdObsFilter(b, fused=True)
+    g = torch.Generator(device="cuda").manual_seed(2)
+    lo, hi = torch.as_tensor(a.r_lo).cuda(), torch.as_tensor(a.r_hi).cuda()
+    for it in range(3):
+        for t in range(4):
+            act = torch.rand((n, 6), device="cuda", generator=g) * (hi - lo) + lo
+            oa, ra, fl_a = a.step_tensor(act)
+            ya = fa(oa.clone())
+            ob, rb, fl_b = b.step_tensor(act)
+            assert torch.equal(ra, rb) and torch.equal(fl_a, fl_b)
+            if it == 0:
+                assert torch.equal(ya, ob), (t, float((ya - ob).abs().max()))
+            else:
+                assert torch.allclose(ya, ob, rtol=0, atol=2e-5), (it, t, float((ya - ob).abs().max()))
+        fa.sync(); fb.sync()
+        assert fa.n == fb.n == n * 4 * (it + 1)
+        np.testing.assert_allclose(fb.mean, fa.mean, rtol=1e-5, atol=1e-6)
+        np.testing.assert_allclose(fb.var, fa.var, rtol=1e-4, atol=1e-8)
+    sa, sb = a.state(), b.state()
+    assert torch.equal(sa["r"], sb["r"]) and torch.equal(sa["v"], sb["v"])
+    a.close(); b.close()

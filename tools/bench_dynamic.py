@@ -14,10 +14,14 @@ def main():
     ap.add_argument("--envs", type=int, default=65536)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--obstacles", action="store_true")
+    ap.add_argument("--fused-filter", action="store_true", help="normalise the observations inside the step kernel")
     a = ap.parse_args()
     bc = BatchConfig(mode="dynamic", kp=2000.0, kd=500.0, torque_scale=1e5, max_episode_steps=500,
                      obstacles=demo_obstacles() if a.obstacles else [], contact_penalty=0.5 if a.obstacles else 0.0)
     env = BatchedPioneerEnv(a.envs, seed=0, simulation_config=SimulationConfig(gravity=9.81), batch_config=bc)
+    if a.fused_filter:
+        from pioneer_b200.obs_filter import MeanStdObsFilter
+        flt = MeanStdObsFilter(env, fused=True)                     # noqa: F841 (keeps the fused mode on)
     lo, hi = torch.as_tensor(env.r_lo).cuda(), torch.as_tensor(env.r_hi).cuda()
     g = torch.Generator(device="cuda").manual_seed(0)
     acts = torch.rand((8, a.envs, 6), device="cuda", generator=g) * (hi - lo) + lo
@@ -31,7 +35,7 @@ def main():
     e.record()
     torch.cuda.synchronize()
     ms = s.elapsed_time(e) / a.steps
-    print(f"dynamic mode: {a.envs} envs, {ms * 1e3:.1f} us/step, {a.envs / ms * 1e3:.3e} env-steps/s, "
+    print(f"dynamic mode{' + fused normaliser' if a.fused_filter else ''}: {a.envs} envs, {ms * 1e3:.1f} us/step, {a.envs / ms * 1e3:.3e} env-steps/s, "
           f"{10 * a.envs / ms * 1e3:.3e} substeps/s")
     env.close()
 
