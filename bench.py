@@ -521,28 +521,28 @@ def ours_arm(args):
     # ---- Tier-B dynamic mode (ABA + PD control, 10 substeps per env step), reported separately ---------------
     if world == 1 and not args.no_sweep:
         from pioneer_b200 import SimulationConfig
-        m = args.envs_per_gpu
-        e = BatchedPioneerEnv(m, device=device, seed=0, simulation_config=SimulationConfig(gravity=9.81),
-                              batch_config=BatchConfig(mode="dynamic", kp=2000.0, kd=500.0, torque_scale=1e5,
-                                                       max_episode_steps=500))
-        a, o, r, f = make_buffers(torch, e, m, device, seed=2)
-        lo, hi = torch.as_tensor(e.r_lo, device=device), torch.as_tensor(e.r_hi, device=device)
-        a = (a / torch.as_tensor(e.a_max, device=device)) * 0.5 * (hi - lo) + 0.5 * (hi + lo)   # desired joint positions
-        k_steps = min(args.steps, 300)
-        ms, _ = time_device_steps(torch, e, a.contiguous(), o, r, f, k_steps, 10, flush)
-        dyn_value = m * k_steps / (ms / 1e3)
-        dyn_tflops = dyn_value * DYN_FLOP_PER_ENV_STEP / 1e12
-        line["dynamic_mode"] = {
-            "workload": f"{m} envs, gravity 9.81, PD position control (kp 2000, kd 500), {FRAME_SKIP} ABA substeps per env step",
-            "ms_per_step": ms / k_steps, "value": dyn_value, "unit": UNIT,
-            "substeps_per_sec": FRAME_SKIP * dyn_value, "parity": "float64 oracle, unpinned vs PyBullet",
-            "roofline": {"bound": "fp32", "achieved": dyn_tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
-                         "frac": dyn_tflops / FP32_PEAK_TFLOPS, "flop_per_env_step": DYN_FLOP_PER_ENV_STEP,
-                         "fp32_issue_frac": dyn_value * DYN_FP_INSTR_PER_ENV_STEP / (FP32_PEAK_TFLOPS / 2 * 1e12),
-                         "peak_source": "tools/fma_peak.py on this pool's B200 (FMA = 2 flop)",
-                         "kernel": "pnr_step_dynamic_kernel<TERMINAL,false,PIONEER_ISO>"}}
-        e.close()
-        del a, o, r, f
+        for key, m in (("dynamic_mode", args.envs_per_gpu), ("dynamic_mode_large_batch", 1048576)):
+            e = BatchedPioneerEnv(m, device=device, seed=0, simulation_config=SimulationConfig(gravity=9.81),
+                                  batch_config=BatchConfig(mode="dynamic", kp=2000.0, kd=500.0, torque_scale=1e5,
+                                                           max_episode_steps=500))
+            a, o, r, f = make_buffers(torch, e, m, device, seed=2)
+            lo, hi = torch.as_tensor(e.r_lo, device=device), torch.as_tensor(e.r_hi, device=device)
+            a = (a / torch.as_tensor(e.a_max, device=device)) * 0.5 * (hi - lo) + 0.5 * (hi + lo)   # desired joint positions
+            k_steps = min(args.steps, 300 if m <= 131072 else 100)
+            ms, _ = time_device_steps(torch, e, a.contiguous(), o, r, f, k_steps, 10, flush)
+            dyn_value = m * k_steps / (ms / 1e3)
+            dyn_tflops = dyn_value * DYN_FLOP_PER_ENV_STEP / 1e12
+            line[key] = {
+                "workload": f"{m} envs, gravity 9.81, PD position control (kp 2000, kd 500), {FRAME_SKIP} ABA substeps per env step",
+                "ms_per_step": ms / k_steps, "value": dyn_value, "unit": UNIT,
+                "substeps_per_sec": FRAME_SKIP * dyn_value, "parity": "float64 oracle, unpinned vs PyBullet",
+                "roofline": {"bound": "fp32", "achieved": dyn_tflops, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
+                             "frac": dyn_tflops / FP32_PEAK_TFLOPS, "flop_per_env_step": DYN_FLOP_PER_ENV_STEP,
+                             "fp32_issue_frac": dyn_value * DYN_FP_INSTR_PER_ENV_STEP / (FP32_PEAK_TFLOPS / 2 * 1e12),
+                             "peak_source": "tools/fma_peak.py on this pool's B200 (FMA = 2 flop)",
+                             "kernel": "pnr_step_dynamic_kernel<TERMINAL,false,PIONEER_ISO>"}}
+            e.close()
+            del a, o, r, f
 
     # ---- N2: fused observation normaliser (one pass: push statistics + normalise in place) -------------------------
     if world == 1 and not args.no_sweep:
