@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PNR_ABI_VERSION 2
+#define PNR_ABI_VERSION 3
 #define PNR_DOF 6                 /* revolute joints of the Pioneer arm (pioneer_knm_env.py:213-215) */
 #define PNR_OBS_DIM 137           /* 21*dof + 11 (pioneer_knm_env.py:194-211)                          */
 #define PNR_MAX_CAPSULES 8
@@ -167,6 +167,11 @@ int pnr_set_state(pnr_handle* h, const float* r, const float* v, const float* a,
  * reset generator (one per reset / step call), `env_steps` feeds pnr_stats.  (The reference env has no state
  * save / restore of its own -- it is re-created from constructor arguments, pioneer_knm_env.py:38,51.) */
 int pnr_get_counters(const pnr_handle* h, uint32_t* tick, double* env_steps, uint64_t* seed);
+/* Advance the reset generator's counter by `n` ON THE DEVICE (a one-thread kernel on `stream`).  The host counter that
+ * pnr_step passes to its kernel is frozen into a captured CUDA graph; capture this call as the first node of a graph of
+ * `n` steps and every replay draws fresh reset states (BatchedPioneerEnv.capture_rollout does).  pnr_get_counters reports
+ * host counter + device advance; pnr_set_counters clears the device part. */
+int pnr_tick_advance(pnr_handle* h, uint32_t n, void* stream);
 int pnr_set_counters(pnr_handle* h, uint32_t tick, double env_steps);
 
 /* Episode statistics accumulated on the device since the last clear (the columns cli.py:32-38 prints):

@@ -11,7 +11,7 @@ from typing import Optional
 
 from . import build as _build
 
-PNR_ABI_VERSION = 2
+PNR_ABI_VERSION = 3
 PNR_DOF = 6
 PNR_OBS_DIM = 137
 PNR_MAX_CAPSULES = 8
@@ -79,6 +79,7 @@ SIGNATURES = {
     "pnr_seed": (C.c_int, [_H, C.c_uint64]),
     "pnr_get_counters": (C.c_int, [_H, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "pnr_set_counters": (C.c_int, [_H, C.c_uint32, C.c_double]),
+    "pnr_tick_advance": (C.c_int, [_H, C.c_uint32, _S]),
     "pnr_reset": (C.c_int, [_H, _P, C.c_int64, _P, _P, _P, _S]),
     "pnr_step": (C.c_int, [_H, _P, _P, _P, _P, _S]),
     "pnr_step_host": (C.c_int, [_H, _P, _P, _P, _P]),

@@ -202,8 +202,9 @@ class BatchedPioneerEnv:
         ``flags`` [T,N] (caller-owned device tensors, re-read / re-written on every replay).  Replaying the graph
         costs one launch for T fused kernels, which removes the host's per-step launch cost from a rollout
         fragment whose actions are produced on the device.  Returns the torch.cuda.CUDAGraph; ``graph.replay()``
-        advances every env by T steps.  Note: the reset generator's call counter is frozen into the graph, so
-        replays re-use the same T reset ticks (episodes still differ: draws are keyed on the env id as well)."""
+        advances every env by T steps.  The host-side call counter that keys the reset generator is frozen into the
+        graph, so the graph's first node advances a device-side counter by T (pnr_tick_advance): every replay draws
+        fresh reset states."""
         T = actions.shape[0]
         assert actions.shape == (T, self.n_envs, DOF) and obs.shape == (T, self.n_envs, OBS_DIM)
         assert reward.shape == (T, self.n_envs) and flags.shape == (T, self.n_envs)
@@ -215,9 +216,16 @@ class BatchedPioneerEnv:
             torch.cuda.synchronize(self.device)
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
+                _cabi.check(self._lib.pnr_tick_advance(self._h, T, self._stream()), "pnr_tick_advance")
                 for t in range(T):
                     self.step_tensor(actions[t], out=(obs[t], reward[t], flags[t]))
         return graph
+
+    def advance_reset_counter(self, n: int) -> None:
+        """Advance the reset generator's counter by ``n`` on the device (pnr_tick_advance); what a captured rollout
+        graph does as its first node."""
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.pnr_tick_advance(self._h, int(n), self._stream()), "pnr_tick_advance")
 
     def step(self, actions):
         """BulletEnv.step through gym TimeLimit (bullet_env.py:192-197, pioneer_knm_train.py:27) for every env:

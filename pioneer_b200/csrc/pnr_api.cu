@@ -1,6 +1,7 @@
 // C-ABI of pioneer_b200 (include/pioneer_b200.h): handle lifetime, parameter block, launches.
 // No torch types, no exceptions across the boundary, no CPU fallback.
 #include <cmath>
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -316,6 +317,7 @@ extern "C" int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t
     cudaError_t e;
     if ((e = cudaMalloc(&h->state, sizeof(float4) * 6 * (size_t)n_envs)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
     if ((e = cudaMalloc(&h->stats, sizeof(PnrStats))) != cudaSuccess) return bail(e, "cudaMalloc(stats)");
+    if ((e = cudaMemset(h->stats, 0, sizeof(PnrStats))) != cudaSuccess) return bail(e, "cudaMemset(stats)");
     if ((e = cudaMalloc(&h->stats_out, sizeof(double) * PNR_STATS_LEN)) != cudaSuccess) return bail(e, "cudaMalloc(stats_out)");
     if ((e = cudaMallocHost(&h->stats_host, sizeof(double) * PNR_STATS_LEN)) != cudaSuccess) return bail(e, "cudaMallocHost");
     // clear statistics, then reset every env (reset_world) with tick 0
@@ -356,9 +358,23 @@ extern "C" int pnr_get_bounds(const pnr_handle* h, float* r_lo, float* r_hi, flo
     return PNR_OK;
 }
 
+extern "C" int pnr_tick_advance(pnr_handle* h, uint32_t n, void* stream) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_tick_advance: null handle");
+    PnrDeviceGuard guard(h->device);
+    PNR_CUDA(pnr_launch_tick_advance(h->stats, n, 0, (cudaStream_t)stream));
+    h->launches += 1;
+    return PNR_OK;
+}
+
 extern "C" int pnr_get_counters(const pnr_handle* h, uint32_t* tick, double* env_steps, uint64_t* seed) {
     if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_get_counters: null handle");
-    if (tick) *tick = h->tick;
+    if (tick) {                                   // host call counter + what graph replays added on the device
+        PnrDeviceGuard guard(h->device);
+        uint32_t off = 0;
+        PNR_CUDA(cudaMemcpy(&off, reinterpret_cast<const char*>(h->stats) + offsetof(PnrStats, tick_offset), sizeof(off),
+                            cudaMemcpyDeviceToHost));
+        *tick = h->tick + off;
+    }
     if (env_steps) *env_steps = h->env_steps;
     if (seed) *seed = ((uint64_t)h->params.seed_hi << 32) | h->params.seed_lo;
     return PNR_OK;
@@ -366,6 +382,11 @@ extern "C" int pnr_get_counters(const pnr_handle* h, uint32_t* tick, double* env
 
 extern "C" int pnr_set_counters(pnr_handle* h, uint32_t tick, double env_steps) {
     if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_set_counters: null handle");
+    {
+        PnrDeviceGuard guard(h->device);
+        PNR_CUDA(pnr_launch_tick_advance(h->stats, 0, 1, nullptr));       // the device-side offset is folded into `tick`
+        PNR_CUDA(cudaStreamSynchronize(nullptr));
+    }
     h->tick = tick;
     h->env_steps = env_steps;
     return PNR_OK;

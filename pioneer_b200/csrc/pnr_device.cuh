@@ -181,4 +181,8 @@ __device__ __host__ __forceinline__ float pnr_ordered_to_float(uint32_t o) {
 struct PnrStats {
     double episodes, sum_return, sum_length, sum_return_sq, reached;
     uint32_t max_return_ord, min_return_ord;
+    // added to the host's call counter where a kernel keys the reset generator (in-kernel auto-reset).  The host counter
+    // is a kernel argument and therefore FROZEN into a captured CUDA graph; pnr_tick_advance bumps this one from inside
+    // the graph, so every replay draws fresh reset states.  0 unless pnr_tick_advance is used.
+    uint32_t tick_offset;
 };

@@ -85,7 +85,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         if (OBS_MODE == PNR_OBS_TERMINAL) pnr_pack_obs_dyn<true>(p, row, s, o, s.pot, slow);
         if (do_reset) {
             float q[PNR_DOF], tg[3];
-            pnr_reset_draws(p, p.env_id_base + env, tick, q, tg);
+            pnr_reset_draws(p, p.env_id_base + env, tick + stats->tick_offset, q, tg);
             pnr_reset_env(s, q, tg);
         }
         if (OBS_MODE == PNR_OBS_AUTORESET) {

@@ -303,7 +303,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
 
         if (part == 3) {
             if (__any_sync(PNR_FULL_MASK, do_reset)) {         // rare: auto-reset (reset_world, :76-105)
-                if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, tick, row);
+                if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, tick + stats->tick_offset, row);
                 pnr_fence_async_smem();
                 __syncwarp();
             }
@@ -553,6 +553,15 @@ cudaError_t pnr_launch_state_io(bool set, float4* state, int64_t N, float* r, fl
     const unsigned grid = (unsigned)((N + threads - 1) / threads);
     if (set) pnr_state_io_kernel<true><<<grid, threads, 0, stream>>>(state, N, r, v, a, potential, target, t, ep_return);
     else pnr_state_io_kernel<false><<<grid, threads, 0, stream>>>(state, N, r, v, a, potential, target, t, ep_return);
+    return cudaGetLastError();
+}
+
+__global__ void pnr_tick_advance_kernel(PnrStats* stats, uint32_t n, int absolute) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) stats->tick_offset = absolute ? n : stats->tick_offset + n;
+}
+
+cudaError_t pnr_launch_tick_advance(PnrStats* stats, uint32_t n, int absolute, cudaStream_t stream) {
+    pnr_tick_advance_kernel<<<1, 32, 0, stream>>>(stats, n, absolute);
     return cudaGetLastError();
 }
 

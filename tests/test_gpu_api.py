@@ -133,13 +133,39 @@ def test_cuda_graph_rollout_equals_stepping():
     b.step_tensor(actions[0])
     graph.replay()
     torch.cuda.synchronize()
+    b.advance_reset_counter(T)                 # the graph's first node: the reset counter moves on by T per replay
     for t in range(T):
         o, r, f = b.step_tensor(actions[t])
         assert torch.equal(r, rew[t]) and torch.equal(f, flg[t]), t
-        # reset draws are keyed on the call counter, which the graph froze at capture time: compare non-reset rows
-        keep = ~(f & 1).bool()
-        assert torch.equal(o[keep], obs[t][keep])
+        assert torch.equal(o, obs[t])
+    sa, sb = a.state(), b.state()              # including the envs that restarted inside the graph
+    assert torch.equal(sa["r"], sb["r"]) and torch.equal(sa["target"], sb["target"])
     a.close(); b.close()
+
+
+def test_graph_replays_draw_fresh_reset_states():
+    """The host call counter that keys the Philox reset draws is a kernel argument, frozen at capture time; the graph
+    advances a device-side counter instead (pnr_tick_advance), so an env that restarts in replay k does not restart
+    from the state it restarted from in replay k-1.  Checkpoints fold the device-side part into the counter."""
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    n, T = 512, 2
+    env = BatchedPioneerEnv(n, seed=8, batch_config=BatchConfig(max_episode_steps=1))     # every step ends an episode
+    actions = torch.zeros((T, n, 6), device="cuda")
+    obs = torch.zeros((T, n, 137), device="cuda")
+    rew = torch.zeros((T, n), device="cuda")
+    flg = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+    graph = env.capture_rollout(actions, obs, rew, flg)
+    tick0 = env.state_dict()["tick"]
+    graph.replay(); torch.cuda.synchronize()
+    first = env.state()["r"].clone()
+    graph.replay(); torch.cuda.synchronize()
+    second = env.state()["r"].clone()
+    assert (flg & 1).all()
+    assert not torch.equal(first, second) and (first != second).any(dim=1).float().mean() > 0.99
+    assert env.state_dict()["tick"] == tick0 + 2 * T
+    env.load_state_dict(env.state_dict())      # folds the device-side part into the host counter
+    assert env.state_dict()["tick"] == tick0 + 2 * T
+    env.close()
 
 
 def test_scene_mirrors_answer_from_device_state():
