@@ -163,8 +163,9 @@ int pnr_get_state(pnr_handle* h, float* r, float* v, float* a, float* potential,
 int pnr_set_state(pnr_handle* h, const float* r, const float* v, const float* a, const float* potential,
                   const float* target, const int32_t* t, const float* ep_return, void* stream);
 
-/* Host-side counters of the handle, for checkpoint / resume together with pnr_get_state / pnr_set_state: `tick` keys the
- * reset generator (one per reset / step call), `env_steps` feeds pnr_stats.  (The reference env has no state
+/* Counters of the handle, for checkpoint / resume together with pnr_get_state / pnr_set_state: `tick` keys the
+ * reset generator (one per reset / step call, plus what pnr_tick_advance added on the device), `env_steps` feeds
+ * pnr_stats (counted on the device by the step kernels, so CUDA-graph replays count).  Both calls synchronise.  (The reference env has no state
  * save / restore of its own -- it is re-created from constructor arguments, pioneer_knm_env.py:38,51.) */
 int pnr_get_counters(const pnr_handle* h, uint32_t* tick, double* env_steps, uint64_t* seed);
 /* Advance the reset generator's counter by `n` ON THE DEVICE (a one-thread kernel on `stream`).  The host counter that

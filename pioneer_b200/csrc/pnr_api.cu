@@ -35,7 +35,6 @@ struct pnr_handle {
     double* stats_out = nullptr;    // device double[8] snapshot
     double* stats_host = nullptr;   // pinned
     uint32_t tick = 0;              // keys the reset generator: one tick per reset/step call
-    double env_steps = 0.0;
     int64_t launches = 0;
     float a_max[PNR_DOF];
     // observation normaliser (pnr_filter_*): device accumulator, applied statistics, host-side running statistics
@@ -321,7 +320,7 @@ extern "C" int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t
     if ((e = cudaMalloc(&h->stats_out, sizeof(double) * PNR_STATS_LEN)) != cudaSuccess) return bail(e, "cudaMalloc(stats_out)");
     if ((e = cudaMallocHost(&h->stats_host, sizeof(double) * PNR_STATS_LEN)) != cudaSuccess) return bail(e, "cudaMallocHost");
     // clear statistics, then reset every env (reset_world) with tick 0
-    if ((e = pnr_launch_stats_snapshot(h->stats, 0.0, h->stats_out, 1, nullptr)) != cudaSuccess) return bail(e, "stats init");
+    if ((e = pnr_launch_stats_snapshot(h->stats, h->stats_out, 1, nullptr)) != cudaSuccess) return bail(e, "stats init");
     if ((e = pnr_launch_reset_observe(h->params, device, 0, h->state, nullptr, n_envs, nullptr, nullptr, nullptr,
                                       h->tick, nullptr)) != cudaSuccess) return bail(e, "initial reset");
     h->launches += 2;
@@ -375,7 +374,11 @@ extern "C" int pnr_get_counters(const pnr_handle* h, uint32_t* tick, double* env
                             cudaMemcpyDeviceToHost));
         *tick = h->tick + off;
     }
-    if (env_steps) *env_steps = h->env_steps;
+    if (env_steps) {                              // counted on the device by the step kernels
+        PnrDeviceGuard guard(h->device);
+        PNR_CUDA(cudaMemcpy(env_steps, reinterpret_cast<const char*>(h->stats) + offsetof(PnrStats, env_steps),
+                            sizeof(double), cudaMemcpyDeviceToHost));
+    }
     if (seed) *seed = ((uint64_t)h->params.seed_hi << 32) | h->params.seed_lo;
     return PNR_OK;
 }
@@ -385,10 +388,10 @@ extern "C" int pnr_set_counters(pnr_handle* h, uint32_t tick, double env_steps) 
     {
         PnrDeviceGuard guard(h->device);
         PNR_CUDA(pnr_launch_tick_advance(h->stats, 0, 1, nullptr));       // the device-side offset is folded into `tick`
+        PNR_CUDA(pnr_launch_env_steps_set(h->stats, env_steps, nullptr));
         PNR_CUDA(cudaStreamSynchronize(nullptr));
     }
     h->tick = tick;
-    h->env_steps = env_steps;
     return PNR_OK;
 }
 
@@ -437,7 +440,6 @@ extern "C" int pnr_step(pnr_handle* h, const float* actions, float* obs, float* 
                                  (h->filt_fused && h->filt_fused_update) ? h->filt_delta : nullptr, (float)h->filt_clip,
                                  (cudaStream_t)stream));
     h->tick += 1;
-    h->env_steps += (double)h->n_envs;
     h->launches += 1;
     return PNR_OK;
 }
@@ -504,8 +506,7 @@ extern "C" int pnr_set_state(pnr_handle* h, const float* r, const float* v, cons
 extern "C" int pnr_stats_device(pnr_handle* h, double* out_device, int clear, void* stream) {
     if (!h || !out_device) return pnr_fail(PNR_ERR_INVALID, "pnr_stats_device: null argument");
     PnrDeviceGuard guard(h->device);
-    PNR_CUDA(pnr_launch_stats_snapshot(h->stats, h->env_steps, out_device, clear, (cudaStream_t)stream));
-    if (clear) h->env_steps = 0.0;
+    PNR_CUDA(pnr_launch_stats_snapshot(h->stats, out_device, clear, (cudaStream_t)stream));
     h->launches += 1;
     return PNR_OK;
 }

@@ -180,6 +180,7 @@ __device__ __host__ __forceinline__ float pnr_ordered_to_float(uint32_t o) {
 // device-side episode statistics (one per handle)
 struct PnrStats {
     double episodes, sum_return, sum_length, sum_return_sq, reached;
+    double env_steps;               // env-steps since the last clear: counted by the step kernels, so graph replays count too
     uint32_t max_return_ord, min_return_ord;
     // added to the host's call counter where a kernel keys the reset generator (in-kernel auto-reset).  The host counter
     // is a kernel argument and therefore FROZEN into a captured CUDA graph; pnr_tick_advance bumps this one from inside

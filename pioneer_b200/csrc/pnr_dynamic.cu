@@ -147,6 +147,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
             atomicAdd(&f_delta[1 + PNR_OBS_DIM + c], (double)N * d * d);
         }
     }
+    if (blockIdx.x == 0 && warp == 0 && lane == 0) stats->env_steps += (double)N;   // one writer per launch
     if (lane == 0) pnr_bulk_wait_read<0>();
 }
 

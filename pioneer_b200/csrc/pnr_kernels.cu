@@ -365,6 +365,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             if (blockIdx.x == 0 && lane == 0) atomicAdd(&f_delta[0], (double)N);
         }
     }
+    if (part == 3 && lane == 0 && blockIdx.x == 0) stats->env_steps += (double)N;   // one writer per launch
     if (part == 3 && lane == 0) pnr_bulk_wait_read<0>();      // smem must outlive the copy engine's reads
 #ifdef PNR_TRACE
     trace_iter = 0;
@@ -449,15 +450,16 @@ __global__ void pnr_state_io_kernel(float4* __restrict__ state, int64_t N, float
     if (SET) pnr_store_env(state, N, e, s);
 }
 
-__global__ void pnr_stats_snapshot_kernel(PnrStats* stats, double env_steps, double* out, int clear) {
+__global__ void pnr_stats_snapshot_kernel(PnrStats* stats, double* out, int clear) {
     if (threadIdx.x == 0 && blockIdx.x == 0) {
         out[0] = stats->episodes; out[1] = stats->sum_return; out[2] = stats->sum_length;
         out[3] = stats->sum_return_sq;
         out[4] = (double)pnr_ordered_to_float(stats->max_return_ord);
         out[5] = (double)pnr_ordered_to_float(stats->min_return_ord);
-        out[6] = env_steps; out[7] = stats->reached;
+        out[6] = stats->env_steps; out[7] = stats->reached;
         if (clear) {
             stats->episodes = stats->sum_return = stats->sum_length = stats->sum_return_sq = stats->reached = 0.0;
+            stats->env_steps = 0.0;
             stats->max_return_ord = pnr_float_to_ordered(-INFINITY);
             stats->min_return_ord = pnr_float_to_ordered(INFINITY);
         }
@@ -559,13 +561,20 @@ cudaError_t pnr_launch_state_io(bool set, float4* state, int64_t N, float* r, fl
 __global__ void pnr_tick_advance_kernel(PnrStats* stats, uint32_t n, int absolute) {
     if (threadIdx.x == 0 && blockIdx.x == 0) stats->tick_offset = absolute ? n : stats->tick_offset + n;
 }
+__global__ void pnr_env_steps_set_kernel(PnrStats* stats, double env_steps) {
+    if (threadIdx.x == 0 && blockIdx.x == 0) stats->env_steps = env_steps;
+}
+cudaError_t pnr_launch_env_steps_set(PnrStats* stats, double env_steps, cudaStream_t stream) {
+    pnr_env_steps_set_kernel<<<1, 32, 0, stream>>>(stats, env_steps);
+    return cudaGetLastError();
+}
 
 cudaError_t pnr_launch_tick_advance(PnrStats* stats, uint32_t n, int absolute, cudaStream_t stream) {
     pnr_tick_advance_kernel<<<1, 32, 0, stream>>>(stats, n, absolute);
     return cudaGetLastError();
 }
 
-cudaError_t pnr_launch_stats_snapshot(PnrStats* stats, double env_steps, double* out, int clear, cudaStream_t stream) {
-    pnr_stats_snapshot_kernel<<<1, 32, 0, stream>>>(stats, env_steps, out, clear);
+cudaError_t pnr_launch_stats_snapshot(PnrStats* stats, double* out, int clear, cudaStream_t stream) {
+    pnr_stats_snapshot_kernel<<<1, 32, 0, stream>>>(stats, out, clear);
     return cudaGetLastError();
 }

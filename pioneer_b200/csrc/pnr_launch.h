@@ -41,7 +41,8 @@ cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, f
 cudaError_t pnr_launch_state_io(bool set, float4* state, int64_t N, float* r, float* v, float* a, float* potential,
                                 float* target, int32_t* t, float* ep_return, cudaStream_t stream);
 cudaError_t pnr_launch_tick_advance(PnrStats* stats, uint32_t n, int absolute, cudaStream_t stream);
-cudaError_t pnr_launch_stats_snapshot(PnrStats* stats, double env_steps, double* out, int clear, cudaStream_t stream);
+cudaError_t pnr_launch_env_steps_set(PnrStats* stats, double env_steps, cudaStream_t stream);
+cudaError_t pnr_launch_stats_snapshot(PnrStats* stats, double* out, int clear, cudaStream_t stream);
 cudaError_t pnr_launch_filter_fold(double* delta_slots, cudaStream_t stream);
 cudaError_t pnr_launch_filter(int device, const float* in, float* out, int64_t n_rows, const float* applied,
                               double* delta, float clip, int update, int normalize, cudaStream_t stream);

@@ -57,8 +57,14 @@ class GaussianMlpPolicy(nn.Module):
 
 class RolloutWorker:
     def __init__(self, env: BatchedPioneerEnv, fragment_length: int = 8, policy: Optional[nn.Module] = None,
-                 use_filter: bool = True, seed: int = 0, policy_dtype=torch.bfloat16, fused_filter: bool = True):
+                 use_filter: bool = True, seed: int = 0, policy_dtype=torch.bfloat16, fused_filter: bool = True,
+                 cuda_graph: bool = False):
+        """``cuda_graph=True``: the T steps of a fragment (policy, sampling, env step) are captured once and replayed,
+        which removes the ~25 launch gaps per env step; the noise then comes from the device's default generator
+        (graph-safe) and the env's reset counter advances on the device (pnr_tick_advance).  Needs the fused filter (or
+        none): a separate filter pass would be captured too, but its synchronisation is not."""
         self.env, self.T = env, int(fragment_length)
+        self.use_graph, self._graph = bool(cuda_graph), None
         dev, n = env.device, env.n_envs
         self.policy = (policy or GaussianMlpPolicy(dtype=policy_dtype)).to(dev)
         self.fused = bool(use_filter and fused_filter)          # the step kernel normalises and pushes statistics itself
@@ -74,26 +80,40 @@ class RolloutWorker:
         self.flags = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
         self._have_first = False
 
-    @torch.no_grad()
-    def collect(self) -> Dict[str, torch.Tensor]:
-        """T env steps of every env; returns views of the fragment buffers (valid until the next call)."""
+    def _steps(self) -> None:
         env = self.env
-        if not self._have_first:
-            self.obs[0].copy_(env.reset())
-            if self.filter is not None:
-                self.filter(self.obs[0])
-            self._have_first = True
-        else:
-            self.obs[0].copy_(self.obs[self.T])
+        self.obs[0].copy_(self.obs[self.T])
         for t in range(self.T):
             mean, log_std = self.policy(self.obs[t])
-            noise = torch.randn(mean.shape, device=mean.device, generator=self.gen)
+            noise = torch.randn(mean.shape, device=mean.device, generator=None if self.use_graph else self.gen)
             raw = mean + log_std.exp() * noise
             self.logp[t] = (-0.5 * noise.pow(2) - log_std).sum(-1)
             torch.mul(torch.tanh(raw), self.a_max, out=self.actions[t])          # squash into the action space
             env.step_tensor(self.actions[t], out=(self.obs[t + 1], self.reward[t], self.flags[t]))
             if self.filter is not None and not self.fused:
                 self.filter(self.obs[t + 1])                                      # push + normalise in place
+
+    @torch.no_grad()
+    def collect(self) -> Dict[str, torch.Tensor]:
+        """T env steps of every env; returns views of the fragment buffers (valid until the next call)."""
+        env = self.env
+        if not self._have_first:
+            self.obs[self.T].copy_(env.reset())
+            if self.filter is not None:
+                self.filter(self.obs[self.T])
+            self._have_first = True
+            if self.use_graph:
+                with torch.cuda.device(env.device):
+                    self._steps()                                                 # warm-up: allocations, kernel attributes
+                    torch.cuda.synchronize(env.device)
+                    self._graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(self._graph):
+                        env.advance_reset_counter(self.T)
+                        self._steps()
+        if self._graph is not None:
+            self._graph.replay()
+        else:
+            self._steps()
         return dict(obs=self.obs[:self.T], next_obs=self.obs[1:], actions=self.actions, logp=self.logp,
                     reward=self.reward, done=(self.flags & 1).bool(), truncated=(self.flags & 2).bool())
 

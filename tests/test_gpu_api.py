@@ -233,3 +233,30 @@ def test_facade_pickles_as_constructor_arguments():
     assert isinstance(clone, PioneerKinematicEnv) and clone.config.award_done == 7.5
     assert clone.reset().shape == (137,)
     env.close(); clone.close()
+
+
+def test_rollout_worker_replays_fragments_from_a_cuda_graph():
+    """cuda_graph=True: policy, sampling and env steps of a fragment are captured once and replayed; the statistics,
+    the fused normaliser and the reset counter keep advancing on the device."""
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    from pioneer_b200.rollout import RolloutWorker
+    n, T = 512, 5
+    env = BatchedPioneerEnv(n, seed=3, batch_config=BatchConfig(max_episode_steps=4))
+    w = RolloutWorker(env, fragment_length=T, policy_dtype=torch.float32, cuda_graph=True)
+    a_max = torch.as_tensor(env.a_max).cuda()
+    w.collect()                                # warm-up fragment + capture + first replay
+    w.sync()
+    seen = []
+    for it in range(3):
+        last = w.obs[T].clone()
+        b = w.collect()
+        assert torch.equal(b["obs"][0], last)                          # fragments chain
+        assert (b["actions"].abs() <= a_max).all() and torch.isfinite(b["obs"]).all() and torch.isfinite(b["logp"]).all()
+        assert float(b["obs"].abs().max()) <= 10.0
+        s = w.sync()
+        assert s["env_steps"] == n * T and s["episodes_total"] >= n    # TimeLimit 4 < T: every env finished an episode
+        seen.append((b["actions"].clone(), b["obs"][-1].clone()))
+    assert not torch.equal(seen[0][0], seen[1][0])                     # fresh noise on every replay
+    assert not torch.equal(seen[1][1], seen[2][1])
+    assert w.filter.n == n * (1 + 5 * T)                               # reset obs + warm-up + capture replay + 3 fragments
+    env.close()

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--fragment", type=int, default=8)
     ap.add_argument("--iters", type=int, default=10)
     ap.add_argument("--no-filter", action="store_true")
+    ap.add_argument("--graph", action="store_true", help="replay each fragment from a CUDA graph")
     a = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
     dev = torch.device("cuda", local)
@@ -33,7 +34,8 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n = a.envs_per_gpu
     env = BatchedPioneerEnv(n, device=dev, seed=0, env_id_base=rank * n, batch_config=BatchConfig(max_episode_steps=500))
-    worker = RolloutWorker(env, fragment_length=a.fragment, use_filter=not a.no_filter, seed=rank)
+    torch.cuda.manual_seed(1234 + rank)
+    worker = RolloutWorker(env, fragment_length=a.fragment, use_filter=not a.no_filter, seed=rank, cuda_graph=a.graph)
     for _ in range(3):
         worker.collect()
         worker.sync()
@@ -54,7 +56,7 @@ def main():
     line = {"metric": "rollout env-steps/sec (filter + 137-256-256-12 policy stub + env step, device resident)",
             "value": world * n * steps / (float(ms) / 1e3), "unit": "env-steps/s", "n_gpus": world, "envs_per_gpu": n,
             "total_envs": world * n, "fragment_length": a.fragment, "iterations": a.iters,
-            "ms_per_env_step_batch": float(ms) / steps, "filter": not a.no_filter,
+            "ms_per_env_step_batch": float(ms) / steps, "filter": not a.no_filter, "cuda_graph": a.graph,
             "batch_shapes": {k: list(v.shape) for k, v in batch.items()}, "episode_stats": summary}
     if rank == 0:
         print(json.dumps(line), flush=True)        # summarize() reports None (null), never NaN
