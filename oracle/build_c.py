@@ -17,13 +17,19 @@ FLAGS = ["-O2", "-std=c99", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-
 
 
 def build(force: bool = False) -> str:
+    """Built into a temporary file and renamed into place, so concurrent callers (pool workers of the CPU baseline)
+    never open a half-written library."""
     if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= os.path.getmtime(SRC):
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
-    cmd = [os.environ.get("CC", "gcc")] + FLAGS + [SRC, "-o", LIB_PATH, "-lm"]
+    tmp = f"{LIB_PATH}.tmp.{os.getpid()}"
+    cmd = [os.environ.get("CC", "gcc")] + FLAGS + [SRC, "-o", tmp, "-lm"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
+        if os.path.exists(tmp):
+            os.remove(tmp)
         raise RuntimeError("gcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+    os.replace(tmp, LIB_PATH)
     return LIB_PATH
 
 

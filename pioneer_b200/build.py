@@ -23,12 +23,26 @@ def _sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
+HASH_PATH = LIB_PATH + ".srchash"
+
+
+def _source_hash() -> str:
+    """Content hash of everything the library is built from (file times do not survive a snapshot copy to another box)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    deps = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC)) + [os.path.join(HERE, "..", "include", "pioneer_b200.h")]
+    for d in deps:
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH):
+    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
         return True
-    built = os.path.getmtime(LIB_PATH)
-    deps = [os.path.join(CSRC, f) for f in os.listdir(CSRC)] + [os.path.join(HERE, "..", "include", "pioneer_b200.h")]
-    return any(os.path.getmtime(d) > built for d in deps)
+    with open(HASH_PATH) as f:
+        return f.read().strip() != _source_hash()
 
 
 TRACE_LIB_PATH = os.path.join(LIB_DIR, "libpioneer_b200_trace.so")
@@ -36,22 +50,42 @@ TRACE_LIB_PATH = os.path.join(LIB_DIR, "libpioneer_b200_trace.so")
 
 def build(force: bool = False, verbose: bool = False, trace: bool = False) -> str:
     """trace=True: developer build with per-CTA phase timestamps (-DPNR_TRACE) next to the product library;
-    select it with PIONEER_B200_LIB=<path>."""
+    select it with PIONEER_B200_LIB=<path>.
+
+    Safe when several processes (the ranks of a torchrun job) import the package at once: one of them builds under a
+    file lock into a temporary file that is renamed into place, the others wait and find the library fresh."""
+    import fcntl
     out = TRACE_LIB_PATH if trace else LIB_PATH
     if not trace and not force and not _stale():
         return LIB_PATH
     os.makedirs(LIB_DIR, exist_ok=True)
-    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("PNR_EXTRA_NVCC_FLAGS", "").split()     # developer experiments (e.g. -DPNR_STEP_MIN_CTAS=6)
     if extra:
         out = os.environ.get("PNR_LIB_OUT", out)
-    cmd = [nvcc] + NVCC_FLAGS + extra + (["-DPNR_TRACE"] if trace else []) + (["-Xptxas", "-v"] if verbose else []) \
-        + _sources() + ["-o", out]
-    proc = subprocess.run(cmd, capture_output=True, text=True)
-    if proc.returncode != 0:
-        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
-    if verbose:
-        print(proc.stdout + proc.stderr)
+    product = (out == LIB_PATH)
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if product and not force and not _stale():             # another process built it while we waited
+                return LIB_PATH
+            nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+            tmp = f"{out}.tmp.{os.getpid()}"
+            cmd = [nvcc] + NVCC_FLAGS + extra + (["-DPNR_TRACE"] if trace else []) + (["-Xptxas", "-v"] if verbose else []) \
+                + _sources() + ["-o", tmp]
+            proc = subprocess.run(cmd, capture_output=True, text=True)
+            if proc.returncode != 0:
+                if os.path.exists(tmp):
+                    os.remove(tmp)
+                raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
+            os.replace(tmp, out)                                   # atomic: readers see the old or the new file, never a part
+            if product:
+                with open(HASH_PATH + ".tmp", "w") as f:
+                    f.write(_source_hash())
+                os.replace(HASH_PATH + ".tmp", HASH_PATH)
+            if verbose:
+                print(proc.stdout + proc.stderr)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
     return out
 
 

@@ -93,3 +93,17 @@ def test_product_package_never_imports_the_oracle():
     code = "import sys, pioneer_b200, pioneer_b200.batched_env, pioneer_b200.vector_env, pioneer_b200.launch; " \
            "assert not [m for m in sys.modules if m == 'oracle' or m.startswith('oracle.')]"
     subprocess.run([sys.executable, "-c", code], check=True, cwd=ROOT)
+
+
+def test_build_freshness_is_decided_by_content_not_by_file_times(tmp_path, monkeypatch):
+    """A snapshot copy to another box does not keep file times: the library is stale iff the hash of its sources
+    changed (pioneer_b200/build.py), so N ranks importing the package on a fresh box do not all start nvcc."""
+    from pioneer_b200 import build
+    build.build()
+    assert not build._stale()
+    src = os.path.join(build.CSRC, "pnr_launch.h")
+    os.utime(src, None)                                  # newer file time, same content
+    assert not build._stale()
+    h = build._source_hash()
+    monkeypatch.setattr(build, "NVCC_FLAGS", build.NVCC_FLAGS + ["-DX"])
+    assert build._source_hash() != h and build._stale()
