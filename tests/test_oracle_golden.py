@@ -113,3 +113,54 @@ def test_philox_known_answers():
     assert philox4x32_10((0xffffffff,) * 4, (0xffffffff,) * 2) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
     assert philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == \
         (0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+def test_fk_matches_the_product_of_exponentials_formulation():
+    """An independent route to the same forward kinematics (Lynch & Park, 'Modern Robotics', ch. 4): space-frame screw
+    axes read off the ZERO configuration straight from the URDF text (the shipped asset, whose kinematic tree is the
+    reference's pioneer_knm_6dof.urdf:204-275) -- joint origins summed along the chain, joint axes as written -- and T(q) = exp([S1] q1) ... exp([S6] q6) M with scipy's matrix exponential.  It
+    shares no code and no recursion with oracle.fk_pointer or the flattener (pioneer_b200/urdf.py)."""
+    import xml.etree.ElementTree as ET
+    from scipy.linalg import expm
+    from pioneer_b200.urdf import DEFAULT_URDF
+    root = ET.parse(DEFAULT_URDF).getroot()
+    joints = {j.find("child").get("link"): j for j in root.findall("joint")}
+    chain = []                                           # walk from the pointer up to the world link
+    link = "robot:pointer" if "robot:pointer" in joints else None
+    if link is None:                                     # link names may carry another prefix: take the leaf
+        parents = {j.find("parent").get("link") for j in root.findall("joint")}
+        link = next(c for c in joints if c not in parents)
+    while link in joints:
+        chain.append(joints[link])
+        link = joints[link].find("parent").get("link")
+    chain.reverse()
+    vec = lambda s: np.array([float(x) for x in s.split()])
+    pos = np.zeros(3)
+    screws = []
+    for j in chain:                                      # the shipped URDF has no rpy on any joint origin
+        origin = j.find("origin")
+        assert origin is None or origin.get("rpy") in (None, "0 0 0")
+        pos = pos + (vec(origin.get("xyz")) if origin is not None and origin.get("xyz") else np.zeros(3))
+        if j.get("type") == "revolute":
+            w = vec(j.find("axis").get("xyz"))
+            screws.append(np.concatenate([w, -np.cross(w, pos)]))
+        else:
+            assert j.get("type") == "fixed"
+    assert len(screws) == 6
+    home = pos                                           # pointer position at q = 0
+
+    def twist(S):
+        w, v = S[:3], S[3:]
+        m = np.zeros((4, 4))
+        m[:3, :3] = [[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]]
+        m[:3, 3] = v
+        return m
+
+    rng = np.random.default_rng(5)
+    for _ in range(200):
+        q = rng.uniform(-3.1416, 3.1416, size=6)
+        T = np.eye(4)
+        for S, qi in zip(screws, q):
+            T = T @ expm(twist(S) * qi)
+        want = (T @ np.append(home, 1.0))[:3]
+        np.testing.assert_allclose(fk_pointer(CHAIN, q), want, atol=1e-10)
