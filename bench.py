@@ -491,7 +491,11 @@ def ours_arm(args):
                 "timer": "host perf_counter around synchronous calls, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": NCU_TRAFFIC_BYTES.get(n), "kernel": "pnr_step_kernel<F32,TERMINAL>",
-                     "bytes_per_env_step": BYTES_PER_ENV_STEP, "units_per_launch": n, "peak_source": peak_src},
+                     "bytes_per_env_step": BYTES_PER_ENV_STEP, "units_per_launch": n, "peak_source": peak_src,
+                     # context, not the roofline claim: the same bytes over (event-pair time - timing_floor_ms), i.e.
+                     # without the fixed ~6.2 us an event pair reads around an EMPTY kernel after the same flush
+                     # (tools/csrc/launch_floor.cu: independent of parameter size, grid and shared memory)
+                     "frac_net_of_event_floor": (BYTES_PER_ENV_STEP * n / (max(avg_ms - floor_ms, 1e-6) / 1e3) / 1e9) / peak},
     }
     env.close()
     del obs_ring, actions
