@@ -27,6 +27,9 @@ def main():
     ap.add_argument("--graph", action="store_true", help="replay each fragment from a CUDA graph")
     a = ap.parse_args()
     world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    sys.stdout.flush()
+    json_fd = os.dup(1)                 # stdout carries exactly one JSON line: NCCL prints its banner on fd 1
+    os.dup2(2, 1)
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
@@ -59,7 +62,7 @@ def main():
             "ms_per_env_step_batch": float(ms) / steps, "filter": not a.no_filter, "cuda_graph": a.graph,
             "batch_shapes": {k: list(v.shape) for k, v in batch.items()}, "episode_stats": summary}
     if rank == 0:
-        print(json.dumps(line), flush=True)        # summarize() reports None (null), never NaN
+        os.write(json_fd, (json.dumps(line) + "\n").encode())        # summarize() reports None (null), never NaN
     env.close()
     if world > 1:
         dist.destroy_process_group()
