@@ -203,6 +203,10 @@ int pnr_filter_delta_device(pnr_handle* h, double* out_device, void* stream);
 /* Merge a delta (HOST double[PNR_FILTER_DELTA_LEN], or NULL = this handle's own) into the running statistics, refresh the
  * mean / std used by pnr_filter_apply, clear the accumulator.  Synchronises `stream`. */
 int pnr_filter_sync(pnr_handle* h, const double* merged_delta_host, void* stream);
+/* The same merge with the (all-reduced) delta still on the DEVICE, or NULL = this handle's own accumulator: one small
+ * kernel on `stream`, no host round trip -- the running count / mean / M2 live on the device, so a rollout loop can
+ * synchronise its filter once per iteration without stalling the stream.  pnr_filter_sync is this call after an H2D copy. */
+int pnr_filter_sync_device(pnr_handle* h, const double* merged_device, void* stream);
 /* Running statistics: HOST count[1], mean[137], var[137] (var = M2 / (count - 1), or mean^2 while count < 2, as
  * RLlib's RunningStat reports it). */
 int pnr_filter_get(pnr_handle* h, double* count, double* mean, double* var);

@@ -93,6 +93,7 @@ SIGNATURES = {
     "pnr_filter_fuse": (C.c_int, [_H, C.c_int, C.c_int]),
     "pnr_filter_delta_device": (C.c_int, [_H, _P, _S]),
     "pnr_filter_sync": (C.c_int, [_H, C.POINTER(C.c_double), _S]),
+    "pnr_filter_sync_device": (C.c_int, [_H, _P, _S]),
     "pnr_filter_get": (C.c_int, [_H, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "pnr_filter_set": (C.c_int, [_H, C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double), _S]),
     "pnr_launch_count": (C.c_int64, [_H]),

@@ -40,8 +40,8 @@ struct pnr_handle {
     // observation normaliser (pnr_filter_*): device accumulator, applied statistics, host-side running statistics
     double* filt_delta = nullptr;        // device double[PNR_FILTER_SLOTS][PNR_FILTER_DELTA_LEN]; copy 0 is what is read
     float* filt_applied = nullptr;       // device float[2 * PNR_OBS_DIM]: mean, 1 / (std + 1e-8)
-    double filt_count = 0.0;
-    double filt_mean[PNR_OBS_DIM] = {}, filt_m2[PNR_OBS_DIM] = {};
+    double* filt_state = nullptr;        // device double[PNR_FILTER_DELTA_LEN]: running count, mean[137], M2[137]
+    double* filt_merged = nullptr;       // device staging for a merged delta handed in from the host
     double filt_clip = 10.0;
     int filt_demean = 1, filt_destd = 1;
     int filt_fused = 0, filt_fused_update = 1;   // pnr_filter_fuse: the step kernel normalises and pushes statistics
@@ -337,7 +337,7 @@ extern "C" void pnr_destroy(pnr_handle* h) {
     if (h->host_stream2) { cudaStreamSynchronize(h->host_stream2); cudaStreamDestroy(h->host_stream2); }
     if (h->host_event) cudaEventDestroy(h->host_event);
     cudaFree(h->state); cudaFree(h->stats); cudaFree(h->stats_out);
-    cudaFree(h->filt_delta); cudaFree(h->filt_applied);
+    cudaFree(h->filt_delta); cudaFree(h->filt_applied); cudaFree(h->filt_state); cudaFree(h->filt_merged);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_done);
     if (h->stats_host) cudaFreeHost(h->stats_host);
     delete h;
@@ -526,16 +526,10 @@ extern "C" int pnr_stats(pnr_handle* h, double* out, int clear, void* stream) {
 // ---------------------------------------------------------------------------------------------------------------
 // observation normaliser
 // ---------------------------------------------------------------------------------------------------------------
-static int pnr_filter_upload_applied(pnr_handle* h, cudaStream_t stream) {
-    float host[2 * PNR_OBS_DIM];
-    for (int c = 0; c < PNR_OBS_DIM; ++c) {
-        // RunningStat.var: S / (n - 1) if n > 1 else mean^2 (RLlib, restated); std = sqrt(var)
-        const double var = h->filt_count > 1.0 ? h->filt_m2[c] / (h->filt_count - 1.0) : h->filt_mean[c] * h->filt_mean[c];
-        host[c] = h->filt_demean ? (float)h->filt_mean[c] : 0.f;
-        host[PNR_OBS_DIM + c] = h->filt_destd ? (float)(1.0 / (std::sqrt(var) + 1e-8)) : 1.f;
-    }
-    PNR_CUDA(cudaMemcpyAsync(h->filt_applied, host, sizeof(host), cudaMemcpyHostToDevice, stream));
-    PNR_CUDA(cudaStreamSynchronize(stream));                    // `host` is a stack buffer
+// The running statistics live on the device (filt_state); the applied statistics (what the kernels subtract / scale by)
+// are derived from them by a kernel, so a synchronisation never leaves the stream.
+static int pnr_filter_refresh(pnr_handle* h, cudaStream_t stream) {
+    PNR_CUDA(pnr_launch_filter_refresh(h->filt_state, h->filt_applied, h->filt_demean, h->filt_destd, stream));
     return PNR_OK;
 }
 
@@ -543,8 +537,11 @@ static int pnr_filter_ensure(pnr_handle* h, cudaStream_t stream) {
     if (h->filt_delta) return PNR_OK;
     PNR_CUDA(cudaMalloc(&h->filt_delta, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN));
     PNR_CUDA(cudaMalloc(&h->filt_applied, sizeof(float) * 2 * PNR_OBS_DIM));
+    PNR_CUDA(cudaMalloc(&h->filt_state, sizeof(double) * PNR_FILTER_DELTA_LEN));
+    PNR_CUDA(cudaMalloc(&h->filt_merged, sizeof(double) * PNR_FILTER_DELTA_LEN));
     PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN, stream));
-    return pnr_filter_upload_applied(h, stream);
+    PNR_CUDA(cudaMemsetAsync(h->filt_state, 0, sizeof(double) * PNR_FILTER_DELTA_LEN, stream));
+    return pnr_filter_refresh(h, stream);
 }
 
 extern "C" int pnr_filter_configure(pnr_handle* h, double clip, int demean, int destd) {
@@ -555,7 +552,7 @@ extern "C" int pnr_filter_configure(pnr_handle* h, double clip, int demean, int 
     if (rc != PNR_OK) return rc;
     // the accumulator is relative to the applied mean: rows pushed under the old setting are dropped
     PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN, nullptr));
-    return pnr_filter_upload_applied(h, nullptr);
+    return pnr_filter_refresh(h, nullptr);
 }
 
 extern "C" int pnr_filter_fuse(pnr_handle* h, int on, int update) {
@@ -598,45 +595,43 @@ extern "C" int pnr_filter_delta_device(pnr_handle* h, double* out_device, void* 
     return PNR_OK;
 }
 
+extern "C" int pnr_filter_sync_device(pnr_handle* h, const double* merged_device, void* stream) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_sync_device: null handle");
+    PnrDeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = pnr_filter_ensure(h, s);
+    if (rc != PNR_OK) return rc;
+    PNR_CUDA(pnr_launch_filter_sync(h->filt_delta, merged_device, h->filt_state, h->filt_applied, h->filt_demean,
+                                    h->filt_destd, s));
+    h->launches += 1;
+    return PNR_OK;
+}
+
 extern "C" int pnr_filter_sync(pnr_handle* h, const double* merged, void* stream) {
     if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_sync: null handle");
     PnrDeviceGuard guard(h->device);
     cudaStream_t s = (cudaStream_t)stream;
     int rc = pnr_filter_ensure(h, s);
     if (rc != PNR_OK) return rc;
-    double d[PNR_FILTER_DELTA_LEN];
-    if (merged) {
-        std::memcpy(d, merged, sizeof(d));
-        PNR_CUDA(cudaStreamSynchronize(s));
-    } else {
-        PNR_CUDA(pnr_launch_filter_fold(h->filt_delta, s));
-        PNR_CUDA(cudaMemcpyAsync(d, h->filt_delta, sizeof(d), cudaMemcpyDeviceToHost, s));
-        PNR_CUDA(cudaStreamSynchronize(s));
+    if (merged) {                                 // pageable source: the copy is staged before the call returns
+        PNR_CUDA(cudaMemcpyAsync(h->filt_merged, merged, sizeof(double) * PNR_FILTER_DELTA_LEN, cudaMemcpyHostToDevice, s));
+        return pnr_filter_sync_device(h, h->filt_merged, stream);
     }
-    const double nb = d[0];
-    if (nb > 0.0) {
-        // the batch statistics are relative to the APPLIED mean (what the kernel subtracted); Chan et al. merge
-        const double na = h->filt_count, n = na + nb;
-        for (int c = 0; c < PNR_OBS_DIM; ++c) {
-            const double applied_mean = h->filt_demean ? (double)(float)h->filt_mean[c] : 0.0;
-            const double mean_b = applied_mean + d[1 + c] / nb;
-            const double m2_b = d[1 + PNR_OBS_DIM + c] - d[1 + c] * d[1 + c] / nb;
-            const double delta = mean_b - h->filt_mean[c];
-            h->filt_m2[c] = h->filt_m2[c] + (m2_b > 0.0 ? m2_b : 0.0) + delta * delta * na * nb / n;
-            h->filt_mean[c] = h->filt_mean[c] + delta * nb / n;
-        }
-        h->filt_count = n;
-    }
-    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN, s));
-    return pnr_filter_upload_applied(h, s);
+    return pnr_filter_sync_device(h, nullptr, stream);
 }
 
 extern "C" int pnr_filter_get(pnr_handle* h, double* count, double* mean, double* var) {
     if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_get: null handle");
-    if (count) *count = h->filt_count;
+    PnrDeviceGuard guard(h->device);
+    double st[PNR_FILTER_DELTA_LEN] = {};
+    if (h->filt_state) {
+        PNR_CUDA(cudaDeviceSynchronize());        // whatever stream the last synchronisation ran on
+        PNR_CUDA(cudaMemcpy(st, h->filt_state, sizeof(st), cudaMemcpyDeviceToHost));
+    }
+    if (count) *count = st[0];
     for (int c = 0; c < PNR_OBS_DIM; ++c) {
-        if (mean) mean[c] = h->filt_mean[c];
-        if (var) var[c] = h->filt_count > 1.0 ? h->filt_m2[c] / (h->filt_count - 1.0) : h->filt_mean[c] * h->filt_mean[c];
+        if (mean) mean[c] = st[1 + c];
+        if (var) var[c] = st[0] > 1.0 ? st[1 + PNR_OBS_DIM + c] / (st[0] - 1.0) : st[1 + c] * st[1 + c];
     }
     return PNR_OK;
 }
@@ -644,13 +639,17 @@ extern "C" int pnr_filter_get(pnr_handle* h, double* count, double* mean, double
 extern "C" int pnr_filter_set(pnr_handle* h, double count, const double* mean, const double* var, void* stream) {
     if (!h || !mean || !var || count < 0.0) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_set: bad argument");
     PnrDeviceGuard guard(h->device);
-    int rc = pnr_filter_ensure(h, (cudaStream_t)stream);
+    cudaStream_t s = (cudaStream_t)stream;
+    int rc = pnr_filter_ensure(h, s);
     if (rc != PNR_OK) return rc;
-    h->filt_count = count;
+    double st[PNR_FILTER_DELTA_LEN];
+    st[0] = count;
     for (int c = 0; c < PNR_OBS_DIM; ++c) {
-        h->filt_mean[c] = mean[c];
-        h->filt_m2[c] = count > 1.0 ? var[c] * (count - 1.0) : 0.0;
+        st[1 + c] = mean[c];
+        st[1 + PNR_OBS_DIM + c] = count > 1.0 ? var[c] * (count - 1.0) : 0.0;
     }
-    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN, (cudaStream_t)stream));
-    return pnr_filter_upload_applied(h, (cudaStream_t)stream);
+    PNR_CUDA(cudaMemcpyAsync(h->filt_state, st, sizeof(st), cudaMemcpyHostToDevice, s));
+    PNR_CUDA(cudaStreamSynchronize(s));           // `st` is a stack buffer
+    PNR_CUDA(cudaMemsetAsync(h->filt_delta, 0, sizeof(double) * PNR_FILTER_SLOTS * PNR_FILTER_DELTA_LEN, s));
+    return pnr_filter_refresh(h, s);
 }

@@ -132,6 +132,76 @@ __global__ void pnr_filter_fold_kernel(double* __restrict__ slots) {
     slots[c] = acc;
 }
 
+// applied statistics from the running ones: mean (float) and 1 / (std + 1e-8); RunningStat.var = S / (n - 1) if n > 1 else
+// mean^2 (RLlib, restated in oracle/filter_oracle.py)
+__device__ __forceinline__ void pnr_filter_refresh_column(double count, double mean, double m2, float* applied, int c,
+                                                          int demean, int destd) {
+    const double var = count > 1.0 ? m2 / (count - 1.0) : mean * mean;
+    applied[c] = demean ? (float)mean : 0.f;
+    applied[PNR_OBS_DIM + c] = destd ? (float)(1.0 / (sqrt(var) + 1e-8)) : 1.f;
+}
+
+__global__ void pnr_filter_refresh_kernel(const double* state, float* applied, int demean, int destd) {
+    const int c = threadIdx.x;
+    if (c < PNR_OBS_DIM) pnr_filter_refresh_column(state[0], state[1 + c], state[1 + PNR_OBS_DIM + c], applied, c, demean, destd);
+}
+
+// Once per iteration, entirely on the device (one CTA, thread = column): fold the accumulator copies (or take `merged`,
+// the all-reduced delta of all ranks), merge into the running count / mean / M2 (Chan et al.; the batch sums are relative
+// to the APPLIED mean, i.e. what the kernels subtracted), refresh the applied statistics, clear the accumulator.
+__global__ void __launch_bounds__(PNR_FILTER_THREADS)
+pnr_filter_sync_kernel(double* slots, const double* merged, double* state, float* applied, int demean, int destd) {
+    // no __restrict__ here: the count is written by one thread and every thread carries its own copy of the new value
+    const int c = threadIdx.x;
+    const bool col_ok = c < PNR_OBS_DIM;
+    double nb, sum_d = 0.0, sum_q = 0.0;
+    if (merged) {
+        nb = merged[0];
+        if (col_ok) { sum_d = merged[1 + c]; sum_q = merged[1 + PNR_OBS_DIM + c]; }
+    } else {
+        nb = 0.0;
+        for (int k = 0; k < PNR_FILTER_SLOTS; ++k) {
+            const double* sl = slots + (size_t)k * PNR_FILTER_DELTA_LEN;
+            nb += sl[0];
+            if (col_ok) { sum_d += sl[1 + c]; sum_q += sl[1 + PNR_OBS_DIM + c]; }
+        }
+    }
+    const double na = state[0];
+    const double n = nb > 0.0 ? na + nb : na;
+    __syncthreads();                                            // everybody has read the old count and the accumulator
+    if (col_ok) {
+        double mean = state[1 + c], m2 = state[1 + PNR_OBS_DIM + c];
+        if (nb > 0.0) {
+            const double applied_mean = demean ? (double)applied[c] : 0.0;
+            const double mean_b = applied_mean + sum_d / nb;
+            const double m2_b = sum_q - sum_d * sum_d / nb;
+            const double delta = mean_b - mean;
+            m2 += (m2_b > 0.0 ? m2_b : 0.0) + delta * delta * na * nb / n;
+            mean += delta * nb / n;
+            state[1 + c] = mean;
+            state[1 + PNR_OBS_DIM + c] = m2;
+        }
+        pnr_filter_refresh_column(n, mean, m2, applied, c, demean, destd);
+    }
+    if (c == 0) state[0] = n;
+    for (int k = 0; k < PNR_FILTER_SLOTS; ++k) {                // clear the accumulator
+        double* sl = slots + (size_t)k * PNR_FILTER_DELTA_LEN;
+        if (c == 0) sl[0] = 0.0;
+        if (col_ok) { sl[1 + c] = 0.0; sl[1 + PNR_OBS_DIM + c] = 0.0; }
+    }
+}
+
+cudaError_t pnr_launch_filter_refresh(const double* state, float* applied, int demean, int destd, cudaStream_t stream) {
+    pnr_filter_refresh_kernel<<<1, PNR_FILTER_THREADS, 0, stream>>>(state, applied, demean, destd);
+    return cudaGetLastError();
+}
+
+cudaError_t pnr_launch_filter_sync(double* slots, const double* merged, double* state, float* applied, int demean, int destd,
+                                   cudaStream_t stream) {
+    pnr_filter_sync_kernel<<<1, PNR_FILTER_THREADS, 0, stream>>>(slots, merged, state, applied, demean, destd);
+    return cudaGetLastError();
+}
+
 cudaError_t pnr_launch_filter_fold(double* delta_slots, cudaStream_t stream) {
     pnr_filter_fold_kernel<<<(PNR_FILTER_DELTA_LEN + 127) / 128, 128, 0, stream>>>(delta_slots);
     return cudaGetLastError();

@@ -44,5 +44,8 @@ cudaError_t pnr_launch_tick_advance(PnrStats* stats, uint32_t n, int absolute, c
 cudaError_t pnr_launch_env_steps_set(PnrStats* stats, double env_steps, cudaStream_t stream);
 cudaError_t pnr_launch_stats_snapshot(PnrStats* stats, double* out, int clear, cudaStream_t stream);
 cudaError_t pnr_launch_filter_fold(double* delta_slots, cudaStream_t stream);
+cudaError_t pnr_launch_filter_refresh(const double* state, float* applied, int demean, int destd, cudaStream_t stream);
+cudaError_t pnr_launch_filter_sync(double* slots, const double* merged, double* state, float* applied, int demean, int destd,
+                                   cudaStream_t stream);
 cudaError_t pnr_launch_filter(int device, const float* in, float* out, int64_t n_rows, const float* applied,
                               double* delta, float clip, int update, int normalize, cudaStream_t stream);

@@ -57,18 +57,20 @@ class MeanStdObsFilter:
                                                    1, 0, self.env._stream()), "pnr_filter_apply")
 
     def sync(self, group: Optional[dist.ProcessGroup] = None) -> None:
-        """Merge the rows pushed since the last sync (of ALL ranks) into the running statistics."""
+        """Merge the rows pushed since the last sync (of ALL ranks) into the running statistics.  Stays on the device:
+        one small kernel (after one all-reduce when distributed), no host round trip; ``n`` / ``mean`` / ``var`` read the
+        result back on demand."""
         with torch.cuda.device(self.env.device):
             if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
                 delta = torch.empty(_cabi.PNR_FILTER_DELTA_LEN, dtype=torch.float64, device=self.env.device)
                 _cabi.check(self._lib.pnr_filter_delta_device(self._h, delta.data_ptr(), self.env._stream()),
                             "pnr_filter_delta_device")
                 dist.all_reduce(delta, op=dist.ReduceOp.SUM, group=group)
-                host = delta.cpu().numpy()
-                _cabi.check(self._lib.pnr_filter_sync(self._h, host.ctypes.data_as(C.POINTER(C.c_double)),
-                                                      self.env._stream()), "pnr_filter_sync")
+                _cabi.check(self._lib.pnr_filter_sync_device(self._h, delta.data_ptr(), self.env._stream()),
+                            "pnr_filter_sync_device")
+                self._keep = delta                      # the kernel reads it asynchronously
             else:
-                _cabi.check(self._lib.pnr_filter_sync(self._h, None, self.env._stream()), "pnr_filter_sync")
+                _cabi.check(self._lib.pnr_filter_sync_device(self._h, None, self.env._stream()), "pnr_filter_sync_device")
 
     def _get(self):
         n = C.c_double()

@@ -117,9 +117,11 @@ class RolloutWorker:
         return dict(obs=self.obs[:self.T], next_obs=self.obs[1:], actions=self.actions, logp=self.logp,
                     reward=self.reward, done=(self.flags & 1).bool(), truncated=(self.flags & 2).bool())
 
-    def sync(self, group=None) -> Dict[str, float]:
-        """Once per training iteration: episode statistics and filter statistics of all ranks."""
+    def sync(self, group=None, summary: bool = True):
+        """Once per training iteration: episode statistics and filter statistics of all ranks.  ``summary=False`` returns
+        the reduced float64[8] statistics tensor without reading it back, so the loop never waits for the GPU (the filter
+        synchronisation stays on the device as well)."""
         stats = reduce_episode_stats(self.env.episode_stats_tensor(clear=True), group)
         if self.filter is not None:
             self.filter.sync(group)
-        return summarize(stats)
+        return summarize(stats) if summary else stats

@@ -49,9 +49,11 @@ def main():
     s.record()
     for _ in range(a.iters):
         batch = worker.collect()
-        summary = worker.sync()
+        stats = worker.sync(summary=False)         # stays on the device: the loop never waits for the GPU
     e.record()
     torch.cuda.synchronize()
+    from pioneer_b200.distributed import summarize
+    summary = summarize(stats)
     ms = torch.tensor([s.elapsed_time(e)], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
