@@ -70,6 +70,24 @@ def reduce_episode_stats(local: torch.Tensor, group: Optional[dist.ProcessGroup]
     return out
 
 
+def reduce_packed(stats_local: torch.Tensor, extra_local: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+    """ONE collective for everything a rollout worker exchanges per iteration: the float64[8] episode statistics (SUM /
+    MAX slots) and an additive float64 vector (the observation filter's delta) are packed, all-gathered, and reduced
+    locally.  Returns (stats, extra) like reduce_episode_stats + a SUM all-reduce would."""
+    assert stats_local.dtype == torch.float64 and extra_local.dtype == torch.float64
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats_local.clone(), extra_local.clone()
+    world = dist.get_world_size(group)
+    packed = torch.cat([stats_local, extra_local])
+    gathered = torch.empty((world, packed.numel()), dtype=torch.float64, device=packed.device)
+    dist.all_gather(list(gathered.unbind(0)), packed, group=group)       # (works on gloo as well as on NCCL)
+    k = len(STATS_FIELDS)
+    stats = gathered[:, :k].sum(0)
+    stats[4] = gathered[:, 4].max()
+    stats[5] = gathered[:, 5].min()
+    return stats, gathered[:, k:].sum(0).contiguous()
+
+
 def summarize(stats: torch.Tensor) -> Dict[str, float]:
     """episode_reward_max/min/mean, episode_len_mean, episodes_total (cli.py:32-38) from the packed vector."""
     s = [float(x) for x in stats.tolist()]

@@ -72,6 +72,24 @@ class MeanStdObsFilter:
             else:
                 _cabi.check(self._lib.pnr_filter_sync_device(self._h, None, self.env._stream()), "pnr_filter_sync_device")
 
+    def delta(self) -> torch.Tensor:
+        """The statistics pushed on THIS rank since the last sync: float64[1 + 2 * 137] on the device (rows, sum(x - mean),
+        sum((x - mean)^2)); additive over ranks."""
+        with torch.cuda.device(self.env.device):
+            out = torch.empty(_cabi.PNR_FILTER_DELTA_LEN, dtype=torch.float64, device=self.env.device)
+            _cabi.check(self._lib.pnr_filter_delta_device(self._h, out.data_ptr(), self.env._stream()),
+                        "pnr_filter_delta_device")
+        return out
+
+    def apply_merged(self, merged: torch.Tensor) -> None:
+        """Finish a synchronisation with a delta that was summed over the ranks elsewhere (e.g. packed into the
+        rollout worker's one collective per iteration)."""
+        assert merged.dtype == torch.float64 and merged.numel() == _cabi.PNR_FILTER_DELTA_LEN and merged.is_contiguous()
+        with torch.cuda.device(self.env.device):
+            _cabi.check(self._lib.pnr_filter_sync_device(self._h, merged.data_ptr(), self.env._stream()),
+                        "pnr_filter_sync_device")
+        self._keep = merged
+
     def _get(self):
         n = C.c_double()
         mean = (C.c_double * OBS_DIM)()

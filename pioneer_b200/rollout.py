@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from .batched_env import DOF, OBS_DIM, BatchedPioneerEnv
-from .distributed import reduce_episode_stats, summarize
+from .distributed import reduce_episode_stats, reduce_packed, summarize
 from .obs_filter import MeanStdObsFilter
 
 
@@ -121,7 +121,10 @@ class RolloutWorker:
         """Once per training iteration: episode statistics and filter statistics of all ranks.  ``summary=False`` returns
         the reduced float64[8] statistics tensor without reading it back, so the loop never waits for the GPU (the filter
         synchronisation stays on the device as well)."""
-        stats = reduce_episode_stats(self.env.episode_stats_tensor(clear=True), group)
-        if self.filter is not None:
-            self.filter.sync(group)
+        local = self.env.episode_stats_tensor(clear=True)
+        if self.filter is not None:                       # one collective for both (all-gather + local reduction)
+            stats, merged = reduce_packed(local, self.filter.delta(), group)
+            self.filter.apply_merged(merged)
+        else:
+            stats = reduce_episode_stats(local, group)
         return summarize(stats) if summary else stats

@@ -59,6 +59,11 @@ def _worker(rank, world, port, out):
         idle = torch.tensor([0, 0, 0, 0, -np.inf, np.inf, 10, 0], dtype=torch.float64)
         mixed = reduce_episode_stats(local if rank == 0 else idle)
         out.put((rank + 10, mixed.tolist()))
+        # the rollout worker's ONE collective per iteration: statistics + an additive vector, all-gathered and reduced locally
+        from pioneer_b200.distributed import reduce_packed
+        extra = torch.arange(5, dtype=torch.float64) * (rank + 1)
+        st, ex = reduce_packed(local, extra)
+        out.put((rank + 20, st.tolist() + ex.tolist()))
     finally:
         dist.destroy_process_group()
 
@@ -70,7 +75,7 @@ def test_reduce_episode_stats_gloo_world2():
     procs = [ctx.Process(target=_worker, args=(r, 2, port, out)) for r in range(2)]
     for p in procs:
         p.start()
-    got = dict(out.get(timeout=120) for _ in range(4))
+    got = dict(out.get(timeout=120) for _ in range(6))
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
@@ -78,6 +83,8 @@ def test_reduce_episode_stats_gloo_world2():
     assert got[0] == want and got[1] == want                      # SUM over counters, MAX / MIN over returns
     want_mixed = [3, 30.0, 900, 350.0, 15.0, 5.0, 4106, 1]
     assert got[10] == want_mixed and got[11] == want_mixed
+    want_packed = want + [0.0, 3.0, 6.0, 9.0, 12.0]
+    assert got[20] == want_packed and got[21] == want_packed      # the packed all-gather gives the same statistics
     s = summarize(torch.tensor(got[0], dtype=torch.float64))
     assert s["episodes_total"] == 8 and s["episode_reward_mean"] == 110.0 / 8
 
