@@ -204,7 +204,7 @@ PNR_HD void pnr_aba_general(const PnrParams& p, const float (&q)[PNR_DOF], const
     PnrDynWork w;
     // ---- pass 1 (base -> tip): velocities, velocity-product accelerations, bias forces
     V3 om = v3(0.f, 0.f, 0.f), vl = v3(0.f, 0.f, 0.f);
-#pragma unroll
+#pragma unroll (CHAIN == 0 ? 1 : 6)   // GENERIC: rolled joint loops (the unrolled body does not fit the instruction cache)
     for (int i = 0; i < PNR_DOF; ++i) {
         pnr_sincos_fast(q[i], w.sn[i], w.cs[i]);                       // q is inside the joint limits
         const V3 t = vl - pnr_origin_cross<CHAIN>(p, i, om);
@@ -224,7 +224,7 @@ PNR_HD void pnr_aba_general(const PnrParams& p, const float (&q)[PNR_DOF], const
     Sym3 I, M;
     Mat3 H;
     V3 pa_ang, pa_lin;
-#pragma unroll
+#pragma unroll (CHAIN == 0 ? 1 : 6)   // GENERIC: rolled joint loops (the unrolled body does not fit the instruction cache)
     for (int i = PNR_DOF - 1; i >= 0; --i) {
         const Sym3 Io = {p.dyn_io[i][0], p.dyn_io[i][1], p.dyn_io[i][2], p.dyn_io[i][3], p.dyn_io[i][4], p.dyn_io[i][5]};
         const V3 mc = v3(p.dyn_mc[i][0], p.dyn_mc[i][1], p.dyn_mc[i][2]);
@@ -301,7 +301,7 @@ PNR_HD void pnr_aba_general(const PnrParams& p, const float (&q)[PNR_DOF], const
     }
     // ---- pass 3 (base -> tip): accelerations.  The base "accelerates" by -g: a_lin = (0, 0, +gravity)
     V3 aa = v3(0.f, 0.f, 0.f), al = v3(0.f, 0.f, p.dyn_gravity);
-#pragma unroll
+#pragma unroll (CHAIN == 0 ? 1 : 6)   // GENERIC: rolled joint loops (the unrolled body does not fit the instruction cache)
     for (int i = 0; i < PNR_DOF; ++i) {
         const V3 t = al - pnr_origin_cross<CHAIN>(p, i, aa);
         aa = pnr_rot_t<CHAIN>(p, i, w.sn[i], w.cs[i], aa) + w.c_ang[i];
