@@ -40,12 +40,12 @@ BYTES_PER_ENV_STEP = BYTES_IO + BYTES_STATE          # 761
 FRAME_SKIP = 10
 FALLBACK_HBM_GBS = 6650.0                            # /opt/skills/guides/B200_PROFILING.md fallback
 L2_FLUSH_BYTES = 512 << 20                           # > 4x the 126 MB L2
-# Tier-B dynamic kernel, from the committed ncu capture (profiles/r01_dyn_v4_step_dynamic_65536.md): 10,397,696 FFMA +
-# 5,847,040 FMUL + 3,362,816 FADD warp instructions per 2,048-tile launch = FFMA 5,077 + FMUL 2,855 + FADD 1,642 thread
-# instructions per env-step (10 ABA substeps) = 14,651 flop; FP32 FMA peak measured on this pool's B200 with
+# Tier-B dynamic kernel, from the committed ncu capture (profiles/r01_dyn_v5_step_dynamic_65536.md): 11,094,016 FFMA +
+# 5,150,720 FMUL + 2,359,296 FADD warp instructions per 2,048-tile launch = FFMA 5,417 + FMUL 2,515 + FADD 1,152 thread
+# instructions per env-step (10 ABA substeps) = 14,501 flop; FP32 FMA peak measured on this pool's B200 with
 # tools/fma_peak.py = 72.6 TFLOP/s (nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)
-DYN_FLOP_PER_ENV_STEP = 2 * 5077 + 2855 + 1642
-DYN_FP_INSTR_PER_ENV_STEP = 5077 + 2855 + 1642
+DYN_FLOP_PER_ENV_STEP = 2 * 5417 + 2515 + 1152
+DYN_FP_INSTR_PER_ENV_STEP = 5417 + 2515 + 1152
 FP32_PEAK_TFLOPS = 72.6
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of pnr_step_kernel from the committed `ncu --set full`
 # captures (profiles/r01_v5_step_65536.md, profiles/r01_v5_step_1m.md).  At 65,536 envs most of the 36 MB of

@@ -325,6 +325,16 @@ PNR_HD void pnr_aba_general(const PnrParams& p, const float (&q)[PNR_DOF], const
 //     host in float64 (PnrParams::dyn_tip_*, pnr_build_params);
 //   * joint 0 sits on the fixed base: its velocity is e_k qd and its acceleration bias is zero.
 // ---------------------------------------------------------------------------------------------------------------
+// 1 / x for a well-scaled positive x: the hardware reciprocal (MUFU.RCP, <= 1 ulp) without the IEEE fix-up sequence and
+// its slow-path call (5 per substep); the host build (tests/csrc/aba_check.cu) divides
+PNR_HD float pnr_rcp_fast(float x) {
+#ifdef __CUDA_ARCH__
+    return __fdividef(1.f, x);
+#else
+    return 1.f / x;
+#endif
+}
+
 PNR_HD int pnr_pio_code(int i) { return i == 0 ? PNR_AXIS_Z : ((i == 3 || i == 5) ? PNR_AXIS_X : PNR_AXIS_Y); }
 PNR_HD int pnr_pio_ocode(int i) { return (i == 0 || i == 5) ? -1 : (i == 3 ? 1 : (i == 4 ? 0 : 2)); }   // axis the origin lies on
 PNR_HD int pnr_nxt(int k) { return k == 2 ? 0 : k + 1; }       // a: the component after k, cyclic
@@ -507,7 +517,7 @@ PNR_HD void pnr_aba_pioneer(const PnrParams& p, const float (&q)[PNR_DOF], const
             w.c_ang[i] = pnr_cross_ek(k, om, qd[i]);
             w.c_lin[i] = pnr_cross_ek(k, vl, qd[i]);
             if (iso) {
-                w.p_lin[i] = cross(om, vl) * p.dyn_mass[i];
+                w.p_lin[i] = cross(om, vl);                             // the mass is applied where it is accumulated (pass 2)
             } else {
                 const V3 n = symmul(Io, om) + cross(mc, vl);
                 const V3 f = vl * p.dyn_mass[i] - cross(mc, om);
@@ -540,7 +550,9 @@ PNR_HD void pnr_aba_pioneer(const PnrParams& p, const float (&q)[PNR_DOF], const
             if (ISO) {                                                  // centre of mass on the origin, inertia iota * 1
                 const float iota = p.dyn_io[i][0];
                 I.xx += iota; I.yy += iota; I.zz += iota;
-                if (i > 0) pa_lin = pa_lin + w.p_lin[i];                // the base joint's own bias force is zero
+                if (i > 0) {                                            // + m om x vl; the base joint's own bias force is zero
+                    pa_lin = v3(fmaf(m, w.p_lin[i].x, pa_lin.x), fmaf(m, w.p_lin[i].y, pa_lin.y), fmaf(m, w.p_lin[i].z, pa_lin.z));
+                }
             } else {
                 const V3 mc = v3(p.dyn_mc[i][0], p.dyn_mc[i][1], p.dyn_mc[i][2]);
                 I.xx += p.dyn_io[i][0]; I.xy += p.dyn_io[i][1]; I.xz += p.dyn_io[i][2];
@@ -552,7 +564,7 @@ PNR_HD void pnr_aba_pioneer(const PnrParams& p, const float (&q)[PNR_DOF], const
             M.xx += m; M.yy += m; M.zz += m;
             Ua = v3(sget(I, 0, k), sget(I, 1, k), sget(I, 2, k));       // I e_k
             Ul = v3(H.m[3 * k], H.m[3 * k + 1], H.m[3 * k + 2]);        // H^T e_k
-            dinv = 1.f / vget(Ua, k);
+            dinv = pnr_rcp_fast(vget(Ua, k));                           // d = S^T I^A S >= the body's own inertia about the axis
         }
         const float u = tau[i] - vget(pa_ang, k);
         w.u_ang[i] = Ua; w.u_lin[i] = Ul; w.dinv[i] = dinv; w.u[i] = u;
@@ -580,12 +592,16 @@ PNR_HD void pnr_aba_pioneer(const PnrParams& p, const float (&q)[PNR_DOF], const
             const float ud = u * dinv;
             const float ca_a = vget(w.c_ang[i], a), ca_b = vget(w.c_ang[i], b);
             const float cl_a = vget(w.c_lin[i], a), cl_b = vget(w.c_lin[i], b);
-            vset(pa_ang, a, vget(pa_ang, a) + fmaf(sget(I, a, a), ca_a, fmaf(sget(I, a, b), ca_b,
-                            fmaf(H.m[3 * a + a], cl_a, fmaf(H.m[3 * a + b], cl_b, vget(Ua, a) * ud)))));
-            vset(pa_ang, b, vget(pa_ang, b) + fmaf(sget(I, a, b), ca_a, fmaf(sget(I, b, b), ca_b,
-                            fmaf(H.m[3 * b + a], cl_a, fmaf(H.m[3 * b + b], cl_b, vget(Ua, b) * ud)))));
+            // every term is folded into one FMA chain per component that ends in the accumulator (no separate adds)
+            vset(pa_ang, a, fmaf(sget(I, a, a), ca_a, fmaf(sget(I, a, b), ca_b, fmaf(H.m[3 * a + a], cl_a,
+                            fmaf(H.m[3 * a + b], cl_b, fmaf(vget(Ua, a), ud, vget(pa_ang, a)))))));
+            vset(pa_ang, b, fmaf(sget(I, a, b), ca_a, fmaf(sget(I, b, b), ca_b, fmaf(H.m[3 * b + a], cl_a,
+                            fmaf(H.m[3 * b + b], cl_b, fmaf(vget(Ua, b), ud, vget(pa_ang, b)))))));
             vset(pa_ang, k, fmaf(vget(Ua, k), ud, vget(pa_ang, k)));
-            pa_lin = pa_lin + pnr_matTmul_z(k, H, w.c_ang[i]) + pnr_symmul_z(k, M, w.c_lin[i]) + Ul * ud;
+#pragma unroll
+            for (int j = 0; j < 3; ++j)                                 // H^T c_ang + M c_lin + Ul u / d
+                vset(pa_lin, j, fmaf(H.m[3 * a + j], ca_a, fmaf(H.m[3 * b + j], ca_b, fmaf(sget(M, j, a), cl_a,
+                                fmaf(sget(M, j, b), cl_b, fmaf(vget(Ul, j), ud, vget(pa_lin, j)))))));
             // hand I^a, p^a up to the parent: rotate by Rot(e_k, q_i), then move the reference point by p_i
             const PnrRot2 r = pnr_rot2(w.sn[i], w.cs[i]);
             const float pk = ok >= 0 ? p.origin_xyz[i][ok] : 0.f;
@@ -614,7 +630,10 @@ PNR_HD void pnr_aba_pioneer(const PnrParams& p, const float (&q)[PNR_DOF], const
             const int a = pnr_nxt(k), b = pnr_prv(k);                   // c_ang, c_lin have a zero k-component
             vset(aa, a, vget(aa, a) + vget(w.c_ang[i], a)); vset(aa, b, vget(aa, b) + vget(w.c_ang[i], b));
             vset(al, a, vget(al, a) + vget(w.c_lin[i], a)); vset(al, b, vget(al, b) + vget(w.c_lin[i], b));
-            qdd[i] = (w.u[i] - dot(w.u_ang[i], aa) - dot(w.u_lin[i], al)) * w.dinv[i];
+            float acc = w.u[i];                                         // u - U . a as one FMA chain
+            acc = fmaf(-w.u_ang[i].x, aa.x, acc); acc = fmaf(-w.u_ang[i].y, aa.y, acc); acc = fmaf(-w.u_ang[i].z, aa.z, acc);
+            acc = fmaf(-w.u_lin[i].x, al.x, acc); acc = fmaf(-w.u_lin[i].y, al.y, acc); acc = fmaf(-w.u_lin[i].z, al.z, acc);
+            qdd[i] = acc * w.dinv[i];
             aa = pnr_add_ek(k, aa, qdd[i]);
         }
     }
