@@ -10,7 +10,7 @@ happens in libpioneer_b200.so through the C-ABI (include/pioneer_b200.h).  There
 from __future__ import annotations
 
 import ctypes as C
-from typing import Dict, Optional, Sequence, Tuple
+from typing import Dict, Optional, Tuple
 
 import numpy as np
 import torch

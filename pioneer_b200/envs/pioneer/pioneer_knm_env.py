@@ -11,7 +11,7 @@ from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
-from ...batched_env import OBS_DIM, BatchedPioneerEnv
+from ...batched_env import BatchedPioneerEnv
 from ...config import BatchConfig, PioneerKinematicConfig, RenderConfig, SimulationConfig
 from ...spaces import Box
 from ...urdf import DEFAULT_URDF

@@ -1,6 +1,6 @@
 import sys, os; sys.path.insert(0, os.getcwd())
 import torch
-from pioneer_b200 import BatchedPioneerEnv, BatchConfig, _cabi
+from pioneer_b200 import BatchedPioneerEnv, BatchConfig
 from pioneer_b200.obs_filter import MeanStdObsFilter
 for n in (65536, 1048576):
     env = BatchedPioneerEnv(n, seed=0, batch_config=BatchConfig(max_episode_steps=500))
