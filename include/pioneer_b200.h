@@ -147,8 +147,10 @@ int pnr_reset(pnr_handle* h, const int64_t* idx, int64_t n, const float* q0, con
  * reward DEVICE float[N]; done DEVICE uint8[N] (PNR_DONE | PNR_TRUNCATED bits). */
 int pnr_step(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, void* stream);
 
-/* Same step with HOST buffers (pinned or pageable): H2D of actions, the kernel, D2H of
- * obs/reward/done, pipelined in chunks on internal streams; returns after the results are on the host. */
+/* Same step with HOST buffers (pinned or pageable): H2D of actions, the kernel, D2H of obs / reward / done on the
+ * library's own streams (the observation copy split over two copy engines); returns after the results are on the host.
+ * The work is ordered after whatever was queued on the default stream; callers using other non-blocking streams
+ * synchronise them first. */
 int pnr_step_host(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done);
 
 /* Replaces PioneerKinematicEnv.observe (pioneer_knm_env.py:184-211) on the current state.

@@ -49,7 +49,7 @@ struct pnr_handle {
     float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
     uint8_t* h_done = nullptr;
     cudaStream_t host_stream = nullptr, host_stream2 = nullptr;
-    cudaEvent_t host_event = nullptr;
+    cudaEvent_t host_event = nullptr, host_order_event = nullptr;
 };
 
 struct PnrDeviceGuard {
@@ -336,6 +336,7 @@ extern "C" void pnr_destroy(pnr_handle* h) {
     if (h->host_stream) { cudaStreamSynchronize(h->host_stream); cudaStreamDestroy(h->host_stream); }
     if (h->host_stream2) { cudaStreamSynchronize(h->host_stream2); cudaStreamDestroy(h->host_stream2); }
     if (h->host_event) cudaEventDestroy(h->host_event);
+    if (h->host_order_event) cudaEventDestroy(h->host_order_event);
     cudaFree(h->state); cudaFree(h->stats); cudaFree(h->stats_out);
     cudaFree(h->filt_delta); cudaFree(h->filt_applied); cudaFree(h->filt_state); cudaFree(h->filt_merged);
     cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_done);
@@ -448,18 +449,30 @@ extern "C" int pnr_step_host(pnr_handle* h, const float* actions, float* obs, fl
     if (!h || !actions || !obs || !reward || !done) return pnr_fail(PNR_ERR_INVALID, "pnr_step_host: null argument");
     PnrDeviceGuard guard(h->device);
     const size_t n = (size_t)h->n_envs;
-    if (!h->host_stream) {
-        PNR_CUDA(cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking));
-        if (!getenv("PNR_HOST_ONE_STREAM")) {                   // developer knob: single-stream copies
-            PNR_CUDA(cudaStreamCreateWithFlags(&h->host_stream2, cudaStreamNonBlocking));
-            PNR_CUDA(cudaEventCreateWithFlags(&h->host_event, cudaEventDisableTiming));
-        }
-        PNR_CUDA(cudaMalloc(&h->h_actions, n * PNR_DOF * sizeof(float)));
-        PNR_CUDA(cudaMalloc(&h->h_obs, n * PNR_OBS_DIM * sizeof(float)));
-        PNR_CUDA(cudaMalloc(&h->h_reward, n * sizeof(float)));
-        PNR_CUDA(cudaMalloc(&h->h_done, n));
+    if (!h->h_done) {                                           // first call: streams + device staging, all or nothing
+        auto setup = [&]() -> cudaError_t {
+            cudaError_t e;
+            if (!h->host_stream && (e = cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+            if (!h->host_order_event && (e = cudaEventCreateWithFlags(&h->host_order_event, cudaEventDisableTiming)) != cudaSuccess) return e;
+            if (!getenv("PNR_HOST_ONE_STREAM")) {               // developer knob: single-stream copies
+                if (!h->host_stream2 && (e = cudaStreamCreateWithFlags(&h->host_stream2, cudaStreamNonBlocking)) != cudaSuccess) return e;
+                if (!h->host_event && (e = cudaEventCreateWithFlags(&h->host_event, cudaEventDisableTiming)) != cudaSuccess) return e;
+            }
+            if (!h->h_actions && (e = cudaMalloc(&h->h_actions, n * PNR_DOF * sizeof(float))) != cudaSuccess) return e;
+            if (!h->h_obs && (e = cudaMalloc(&h->h_obs, n * PNR_OBS_DIM * sizeof(float))) != cudaSuccess) return e;
+            if (!h->h_reward && (e = cudaMalloc(&h->h_reward, n * sizeof(float))) != cudaSuccess) return e;
+            return cudaMalloc(&h->h_done, n);                   // last: its presence marks the set-up as complete
+        };
+        const cudaError_t e = setup();
+        if (e != cudaSuccess)                                   // what was allocated is kept for the retry / freed by pnr_destroy
+            return pnr_fail(e == cudaErrorMemoryAllocation ? PNR_ERR_ALLOC : PNR_ERR_CUDA,
+                            std::string("pnr_step_host: staging set-up: ") + cudaGetErrorString(e));
     }
     cudaStream_t s = h->host_stream;
+    // the library's own (non-blocking) stream: order it after whatever the caller queued on the default stream (a reset,
+    // a set_state, a previous pnr_step); work on other non-blocking streams is the caller's to synchronise
+    PNR_CUDA(cudaEventRecord(h->host_order_event, nullptr));
+    PNR_CUDA(cudaStreamWaitEvent(s, h->host_order_event, 0));
     PNR_CUDA(cudaMemcpyAsync(h->h_actions, actions, n * PNR_DOF * sizeof(float), cudaMemcpyHostToDevice, s));
     int rc = pnr_step(h, h->h_actions, h->h_obs, h->h_reward, h->h_done, s);
     if (rc != PNR_OK) return rc;
