@@ -41,12 +41,12 @@ def harness(tmp_path_factory):
     return lib
 
 
-def params_blob(harness, gravity=9.81, kp=0.0, kd=0.0, torque_scale=1.0):
+def params_blob(harness, gravity=9.81, kp=0.0, kd=0.0, torque_scale=1.0, chain=None):
     lib = _cabi.load()
     lib.pnr_debug_build_params.restype = C.c_int64
     lib.pnr_debug_build_params.argtypes = [C.POINTER(_cabi.pnr_model), C.POINTER(_cabi.pnr_config), C.c_int64,
                                            C.c_void_p, C.c_int64]
-    chain = flatten_urdf()
+    chain = chain or flatten_urdf()
     model = _cabi.model_from_chain(chain)
     cfg = _cabi.pnr_config()
     lib.pnr_default_config(C.byref(cfg))
@@ -128,3 +128,49 @@ def test_one_env_step_of_substeps_against_the_oracle(harness, kp, kd, scale):
         assert harness.aba_substeps(blob, pioneer_chain, n, fp(q1), fp(qd1), fp(act)) == 0
         assert np.abs(q1 - ref_q).max() <= 2e-5, (pioneer_chain, np.abs(q1 - ref_q).max())
         assert np.abs(qd1 - ref_qd).max() <= 2e-4, (pioneer_chain, np.abs(qd1 - ref_qd).max())
+
+
+def test_general_inertials_take_the_non_isotropic_specialisation(harness):
+    """The shipped URDF's links have stub inertials (centre of mass on the frame origin, isotropic), which hides every
+    term that multiplies a centre-of-mass offset or an off-diagonal inertia.  Same kinematic structure with random
+    full inertias and centre-of-mass offsets on ALL six composite bodies: the generic chain, the first specialisation and
+    pnr_aba_pioneer<false> must still agree with the float64 oracle; the isotropic variant must be refused."""
+    import copy
+    rng = np.random.default_rng(11)
+    chain = copy.deepcopy(flatten_urdf())
+    com, inertia = [], []
+    for j in range(6):
+        a = rng.normal(size=(3, 3))
+        inertia.append((a @ a.T + 2.0 * np.eye(3)) * float(chain.body_mass[j]))       # symmetric positive definite
+        com.append(rng.uniform(-1.5, 1.5, size=3))
+    chain.body_com = np.array(com)
+    chain.body_inertia = np.array(inertia)
+    gravity = 9.81
+    chain_out, blob = params_blob(harness, gravity=gravity, chain=chain)
+    dyn = DynChain.from_model(chain_out)
+    n = 300
+    rng2, q, qd = states(chain_out, n, seed=12)
+    tau = (rng2.normal(size=(n, 6)) * 300.0).astype(np.float32)
+    ref = np.stack([aba(dyn, q[e].astype(np.float64), qd[e].astype(np.float64), tau[e].astype(np.float64), gravity)
+                    for e in range(n)])
+    scale = np.abs(ref).max(axis=0) + 1e-9
+    for variant in (0, 1, 2):
+        out = np.empty((n, 6), np.float32)
+        assert harness.aba_check(blob, variant, n, fp(q), fp(qd), fp(tau), fp(out)) == 0
+        err = np.abs(out - ref) / scale
+        assert err.max() < 2e-5, (variant, err.max())
+    out = np.empty((n, 6), np.float32)
+    assert harness.aba_check(blob, 3, n, fp(q), fp(qd), fp(tau), fp(out)) == -1       # dyn_iso_links is off for this model
+    # one env step of substeps through the kernel's own driver, chain kinds 0 and 1
+    cfg = DynConfig(gravity=gravity, kp=0.0, kd=0.0, torque_scale=50.0)
+    _, blob2 = params_blob(harness, gravity=gravity, torque_scale=50.0, chain=chain)
+    lo32, hi32 = np.asarray(chain_out.lower, np.float32), np.asarray(chain_out.upper, np.float32)
+    q0, qd0 = (q[:100] * 0.8).astype(np.float32), (qd[:100] * 0.3).astype(np.float32)
+    act = (rng2.normal(size=(100, 6)) * 50.0).astype(np.float32)
+    want = [dynamic_substeps(dyn, cfg, q0[e].astype(np.float64), qd0[e].astype(np.float64), act[e].astype(np.float64),
+                             lo32.astype(np.float64), hi32.astype(np.float64)) for e in range(100)]
+    for kind in (0, 1):
+        q1, qd1 = q0.copy(), qd0.copy()
+        assert harness.aba_substeps(blob2, kind, 100, fp(q1), fp(qd1), fp(act)) == 0
+        assert max(np.abs(q1[e] - want[e][0]).max() for e in range(100)) <= 2e-5
+        assert max(np.abs(qd1[e] - want[e][1]).max() for e in range(100)) <= 2e-4
