@@ -2,7 +2,7 @@
 // [PD / torque control -> Featherstone ABA -> semi-implicit Euler -> limit stops] with the joint state in
 // registers, then the same task code as the kinematic env (pioneer_knm_env.py:151-211): forward kinematics of
 // the pointer, reward, done, TimeLimit, statistics, auto-reset, 137-float observation staged per warp in shared
-// memory and stored with one TMA bulk copy.  Bound: FP32 pipe (10 x ~2 kflop per env-step against 761 B).
+// memory and stored with one TMA bulk copy.  Bound: FP32 pipe (10 x ~1.45 kflop per env-step against 761 B).
 #include <cstdlib>
 #include "pnr_kernels.cuh"
 #include "pnr_dynamics.cuh"
