@@ -23,7 +23,7 @@ def _sources():
     return [os.path.join(CSRC, s) for s in SOURCES if os.path.exists(os.path.join(CSRC, s))]
 
 
-HASH_PATH = LIB_PATH + ".srchash"
+HASH_MARKER = b"PNR_SRC_HASH:"
 
 
 def _source_hash() -> str:
@@ -38,11 +38,19 @@ def _source_hash() -> str:
     return h.hexdigest()
 
 
+def _built_hash(path: str) -> str:
+    """The hash the library carries inside itself (pnr_source_hash() in pnr_api.cu), read from the file without loading it."""
+    try:
+        with open(path, "rb") as f:
+            blob = f.read()
+    except OSError:
+        return ""
+    i = blob.find(HASH_MARKER)
+    return blob[i + len(HASH_MARKER):i + len(HASH_MARKER) + 64].decode("ascii", "replace") if i >= 0 else ""
+
+
 def _stale() -> bool:
-    if not os.path.exists(LIB_PATH) or not os.path.exists(HASH_PATH):
-        return True
-    with open(HASH_PATH) as f:
-        return f.read().strip() != _source_hash()
+    return _built_hash(LIB_PATH) != _source_hash()
 
 
 TRACE_LIB_PATH = os.path.join(LIB_DIR, "libpioneer_b200_trace.so")
@@ -71,17 +79,13 @@ def build(force: bool = False, verbose: bool = False, trace: bool = False) -> st
             nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
             tmp = f"{out}.tmp.{os.getpid()}"
             cmd = [nvcc] + NVCC_FLAGS + extra + (["-DPNR_TRACE"] if trace else []) + (["-Xptxas", "-v"] if verbose else []) \
-                + _sources() + ["-o", tmp]
+                + [f'-DPNR_SRC_HASH="{_source_hash()}"'] + _sources() + ["-o", tmp]
             proc = subprocess.run(cmd, capture_output=True, text=True)
             if proc.returncode != 0:
                 if os.path.exists(tmp):
                     os.remove(tmp)
                 raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + proc.stdout + proc.stderr)
             os.replace(tmp, out)                                   # atomic: readers see the old or the new file, never a part
-            if product:
-                with open(HASH_PATH + ".tmp", "w") as f:
-                    f.write(_source_hash())
-                os.replace(HASH_PATH + ".tmp", HASH_PATH)
             if verbose:
                 print(proc.stdout + proc.stderr)
         finally:

@@ -62,6 +62,13 @@ struct PnrDeviceGuard {
     ~PnrDeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
 };
 
+// Build stamp: the content hash of the sources this library was built from (pioneer_b200/build.py looks for the marker
+// in the file to decide whether the library is stale -- file times do not survive a snapshot copy to another box).
+#ifndef PNR_SRC_HASH
+#define PNR_SRC_HASH "unknown"
+#endif
+extern "C" const char* pnr_source_hash(void) { return "PNR_SRC_HASH:" PNR_SRC_HASH; }
+
 extern "C" int pnr_abi_version(void) { return PNR_ABI_VERSION; }
 extern "C" const char* pnr_last_error(void) { return g_last_error.c_str(); }
 

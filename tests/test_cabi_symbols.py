@@ -100,7 +100,7 @@ def test_build_freshness_is_decided_by_content_not_by_file_times(tmp_path, monke
     changed (pioneer_b200/build.py), so N ranks importing the package on a fresh box do not all start nvcc."""
     from pioneer_b200 import build
     build.build()
-    assert not build._stale()
+    assert not build._stale() and build._built_hash(build.LIB_PATH) == build._source_hash()    # the stamp is inside the .so
     src = os.path.join(build.CSRC, "pnr_launch.h")
     os.utime(src, None)                                  # newer file time, same content
     assert not build._stale()
