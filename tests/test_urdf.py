@@ -96,3 +96,92 @@ def test_rpy_convention():
     R = rpy_to_matrix((0.1, 0.2, 0.3))
     want = axis_angle_matrix((0, 0, 1), 0.3) @ axis_angle_matrix((0, 1, 0), 0.2) @ axis_angle_matrix((1, 0, 0), 0.1)
     np.testing.assert_allclose(R, want, atol=1e-15)
+
+
+def _random_urdf(rng, path):
+    """Six revolute joints with random axes, fixed joints (with rotations) in between, every link with a random mass,
+    inertial origin (xyz + rpy) and full inertia tensor; the tracked tip hangs off the last link by a fixed joint."""
+    def f(v):
+        return " ".join(f"{x:.9f}" for x in v)
+
+    def link(name):
+        a = rng.normal(size=(3, 3))
+        I = a @ a.T + np.eye(3)
+        return (f'<link name="{name}"><inertial><mass value="{rng.uniform(0.5, 3.0):.9f}"/>'
+                f'<origin xyz="{f(rng.uniform(-0.5, 0.5, 3))}" rpy="{f(rng.uniform(-1, 1, 3))}"/>'
+                f'<inertia ixx="{I[0, 0]:.9f}" ixy="{I[0, 1]:.9f}" ixz="{I[0, 2]:.9f}" iyy="{I[1, 1]:.9f}" iyz="{I[1, 2]:.9f}" '
+                f'izz="{I[2, 2]:.9f}"/></inertial></link>')
+
+    def joint(name, kind, parent, child):
+        body = (f'<joint name="{name}" type="{kind}"><parent link="{parent}"/><child link="{child}"/>'
+                f'<origin xyz="{f(rng.uniform(-2, 2, 3))}" rpy="{f(rng.uniform(-1, 1, 3))}"/>')
+        if kind == "revolute":
+            body += f'<axis xyz="{f(rng.normal(size=3))}"/><limit lower="-2.5" upper="2.5" effort="10" velocity="5"/>'
+        return body + "</joint>"
+
+    parts, prev = ['<link name="world"/>'], "world"
+    n = 0
+    for r in range(6):
+        for _ in range(int(rng.integers(0, 3))):              # 0..2 fixed joints before every revolute one
+            n += 1
+            parts += [link(f"f{n}"), joint(f"jf{n}", "fixed", prev, f"f{n}")]
+            prev = f"f{n}"
+        parts += [link(f"m{r}"), joint(f"jr{r}", "revolute", prev, f"m{r}")]
+        prev = f"m{r}"
+    parts += [link("tip"), joint("jtip", "fixed", prev, "tip")]
+    path.write_text('<robot name="random">' + "".join(parts) + "</robot>")
+
+
+def _link_frames(path, q):
+    """World transform of every link, straight from the parsed XML (no folding)."""
+    _, links, raw = parse_urdf(path)
+    rev = [j["name"] for j in raw if j["type"] == "revolute"]
+    T = {"world": np.eye(4)}
+    todo = list(raw)
+    while todo:
+        for j in list(todo):
+            if j["parent"] in T:
+                A = np.eye(4)
+                A[:3, :3], A[:3, 3] = j["rot"], j["xyz"]
+                if j["type"] == "revolute":
+                    R = np.eye(4)
+                    R[:3, :3] = axis_angle_matrix(j["axis"] / np.linalg.norm(j["axis"]), q[rev.index(j["name"])])
+                    A = A @ R
+                T[j["child"]] = T[j["parent"]] @ A
+                todo.remove(j)
+    return links, T
+
+
+def test_folded_composite_bodies_carry_the_kinetic_energy_of_the_unfolded_links(tmp_path):
+    """Fixed joints (with rotations) are folded into composite bodies: mass, centre of mass and inertia about it.  The
+    kinetic energy of the UNFOLDED links -- from finite differences of every link's world pose, nothing else -- must equal
+    1/2 qd^T M(q) qd with the joint-space inertia M of the FOLDED chain (oracle CRBA).  Also: the tracked point."""
+    from oracle.dynamics_oracle import DynChain, crba
+    rng = np.random.default_rng(17)
+    for case in range(3):
+        path = tmp_path / f"random{case}.urdf"
+        _random_urdf(rng, path)
+        m = flatten_urdf(str(path), tip_link="tip")
+        assert m.dof == 6
+        ch = DynChain.from_model(m)
+        for _ in range(3):
+            q, qd = rng.uniform(-2.0, 2.0, 6), rng.normal(size=6)
+            h = 1e-6
+            links, Tp = _link_frames(str(path), q + h * qd)
+            _, Tm = _link_frames(str(path), q - h * qd)
+            _, T0 = _link_frames(str(path), q)
+            ke = 0.0
+            for name, ln in links.items():
+                if ln.mass <= 0.0:
+                    continue
+                cp = (Tp[name] @ np.append(ln.com_xyz, 1.0))[:3]
+                cm = (Tm[name] @ np.append(ln.com_xyz, 1.0))[:3]
+                v = (cp - cm) / (2 * h)
+                W = (Tp[name][:3, :3] @ Tm[name][:3, :3].T - np.eye(3)) / (2 * h)          # ~ [omega]x
+                om = 0.5 * np.array([W[2, 1] - W[1, 2], W[0, 2] - W[2, 0], W[1, 0] - W[0, 1]])
+                Rw = T0[name][:3, :3] @ ln.com_rot
+                ke += 0.5 * ln.mass * v @ v + 0.5 * om @ (Rw @ ln.inertia @ Rw.T) @ om
+            want = 0.5 * qd @ crba(ch, q) @ qd
+            assert abs(ke - want) <= 1e-6 * max(1.0, abs(want)), (case, ke, want)
+            # getLinkState(...)[0] is the world position of the link's CENTRE OF MASS (bullet_bindings.py:38-45)
+            np.testing.assert_allclose(m.tip_position(q), (T0["tip"] @ np.append(links["tip"].com_xyz, 1.0))[:3], atol=1e-9)
