@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define PNR_ABI_VERSION 3
+#define PNR_ABI_VERSION 4
 #define PNR_DOF 6                 /* revolute joints of the Pioneer arm (pioneer_knm_env.py:213-215) */
 #define PNR_OBS_DIM 137           /* 21*dof + 11 (pioneer_knm_env.py:194-211)                          */
 #define PNR_MAX_CAPSULES 8
@@ -52,6 +52,20 @@ typedef enum pnr_status {
 
 #define PNR_MODE_KINEMATIC 0      /* the reference env: act() integrator + teleport (pioneer_knm_env.py:111-148) */
 #define PNR_MODE_DYNAMIC 1        /* ABA forward dynamics + PD torque + semi-implicit Euler substeps   */
+
+/* substep of the dynamic mode */
+#define PNR_STEPPING_EXPLICIT 0   /* tau = clamp(kp (u - q) - kd qd) - damping qd; qd += qdd dt; q += qd dt              */
+#define PNR_STEPPING_BULLET 1     /* opt-in Bullet-like substep: per-link damping, +-max_velocity clamp, POSITION_CONTROL as
+                                   * a velocity-level motor constraint with impulse clamp force * dt (Joint.control_position,
+                                   * bullet_scene.py:123-142; btMultiBody semantics restated from memory, unpinned)       */
+
+/* row layout of the HOST observation buffer of pnr_step_host_begin */
+#define PNR_HOST_FULL 0           /* float[N,137], the reference's observe() row (pioneer_knm_env.py:184-211)            */
+#define PNR_HOST_COMPACT 1        /* float[N,101]: columns 0:18 and 54:137; the 36 columns 18:54 (r_lo, r_hi and their
+                                   * cos / sin) never change and are delivered once by pnr_get_obs_constants             */
+#define PNR_OBS_COMPACT_DIM 101
+#define PNR_OBS_CONST_BEGIN 18
+#define PNR_OBS_CONST_END 54
 
 /* bits of the per-env `done` byte */
 #define PNR_DONE 1                /* episode over (distance < done_distance, or time limit)            */
@@ -106,6 +120,17 @@ typedef struct pnr_config {
     double obstacle_p[PNR_MAX_OBSTACLES][3];
     double obstacle_e[PNR_MAX_OBSTACLES][3];
     double contact_penalty;               /* reward -= contact_penalty * sum(penetration depth)         */
+    /* per-env random box (the legacy randomizer, pioneer/temp/pioneer_env.py:169-192): with random_box != 0 the FIRST box
+     * among the obstacles is redrawn at every reset of an env: half extents ~ U(box_size_lo, box_size_hi), centre =
+     * (U(box_pos_lo, box_pos_hi), half height) -- the box stands on z = 0 */
+    int32_t random_box;
+    double box_pos_lo[2], box_pos_hi[2], box_size_lo[3], box_size_hi[3];
+    /* dynamic mode, PNR_STEPPING_BULLET only */
+    int32_t stepping;                     /* PNR_STEPPING_*                                             */
+    double link_damping;                  /* Bullet's linear = angular link damping, 0.04               */
+    double max_velocity;                  /* joint velocity clamp, 100 rad/s                            */
+    double motor_kp, motor_kd;            /* setJointMotorControl2 positionGain 0.1 / velocityGain 1.0  */
+    double motor_max_force;               /* `force`: impulse clamp force * dt per substep; 0 = motors off */
 } pnr_config;
 
 typedef struct pnr_handle pnr_handle;
@@ -131,7 +156,12 @@ void pnr_destroy(pnr_handle* h);
 int64_t pnr_num_envs(const pnr_handle* h);
 /* derived bounds (pioneer_knm_env.py:56-58): each out pointer is HOST float[PNR_DOF] or NULL */
 int pnr_get_bounds(const pnr_handle* h, float* r_lo, float* r_hi, float* v_max, float* a_max);
-/* re-seed the reset generator (PioneerKinematicEnv.seed, pioneer_knm_env.py:107-109) */
+/* obs[18:54] of every observation row (r_lo, cos r_lo, sin r_lo, r_hi, cos r_hi, sin r_hi; pioneer_knm_env.py:196-197)
+ * exactly as the kernels write them: HOST float[36].  With these a PNR_HOST_COMPACT row re-expands to the 137-column row
+ * bit for bit (pnr_expand_obs_host). */
+int pnr_get_obs_constants(const pnr_handle* h, float* out36);
+/* re-seed the reset generator (PioneerKinematicEnv.seed, pioneer_knm_env.py:107-109).  The key lives in device memory, so
+ * steps already captured into a CUDA graph see the new seed too.  Synchronises the device. */
 int pnr_seed(pnr_handle* h, uint64_t seed);
 
 /* Replaces BulletEnv.reset / reset_world(joint_positions, target_position) (bullet_env.py:187-190,
@@ -153,9 +183,28 @@ int pnr_step(pnr_handle* h, const float* actions, float* obs, float* reward, uin
  * synchronise them first. */
 int pnr_step_host(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done);
 
+/* The same step, asynchronous and double-buffered: _begin queues H2D of the actions, the kernel and the D2H of the results
+ * into the caller's HOST buffers (pinned memory for real overlap) and returns at once; _end blocks until the results of the
+ * OLDEST step begun have landed.  At most two steps may be in flight (begin, begin, end, begin, end, ...): the D2H of step
+ * k then overlaps H2D + kernel of step k + 1 -- for callers whose next action does not depend on the observation still in
+ * flight.  layout = PNR_HOST_FULL: obs is float[N,137]; PNR_HOST_COMPACT: obs is float[N,101] (26 % fewer bytes over PCIe;
+ * a small gather kernel runs after the step).  pnr_step_host is _begin(FULL) + _end. */
+int pnr_step_host_begin(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int layout);
+int pnr_step_host_end(pnr_handle* h);
+/* HOST helper (plain memory formatting, no device work): compact float[n_rows,101] -> full float[n_rows,137]. */
+int pnr_expand_obs_host(const pnr_handle* h, const float* compact, float* full, int64_t n_rows);
+
 /* Replaces PioneerKinematicEnv.observe (pioneer_knm_env.py:184-211) on the current state.
  * idx DEVICE int64[n] or NULL = all. */
 int pnr_observe(pnr_handle* h, const int64_t* idx, int64_t n, float* obs_out, void* stream);
+
+/* What RLlib's sampler does after a done: reset_at(i) and feed the policy the RESET observation (bullet_env.py:187-190;
+ * VectorEnv.reset_at).  With auto_reset the envs flagged in `done` (the DEVICE uint8[N] pnr_step wrote) are already in
+ * their new episode; this call overwrites their rows of obs DEVICE float[N,137] (PNR_OBS_TERMINAL content) with the first
+ * observation of the new episode -- normalised and pushed into the statistics like the step's output when the filter is
+ * fused -- after copying the terminal rows to terminal_obs DEVICE float[N,137] (or NULL; only done rows are written).
+ * Fixed launch shape: capturable in a CUDA graph. */
+int pnr_observe_done(pnr_handle* h, const uint8_t* done, float* obs, float* terminal_obs, void* stream);
 
 /* Replaces Joint.position()/velocity() and the env attributes a, v, r, potential (bullet_scene.py:115-121,
  * pioneer_knm_env.py:63-66).  All DEVICE, any may be NULL: r,v,a float[N,6]; potential float[N];
@@ -164,11 +213,19 @@ int pnr_get_state(pnr_handle* h, float* r, float* v, float* a, float* potential,
                   int32_t* t, float* ep_return, void* stream);
 int pnr_set_state(pnr_handle* h, const float* r, const float* v, const float* a, const float* potential,
                   const float* target, const int32_t* t, const float* ep_return, void* stream);
+/* The per-env random box of the obstacle variant (cfg->random_box): DEVICE float[N,6] = centre xyz, half extents xyz.
+ * PNR_ERR_UNSUPPORTED without random_box. */
+int pnr_get_boxes(pnr_handle* h, float* box, void* stream);
+int pnr_set_boxes(pnr_handle* h, const float* box, void* stream);
 
 /* Counters of the handle, for checkpoint / resume together with pnr_get_state / pnr_set_state: `tick` keys the
  * reset generator (one per reset / step call, plus what pnr_tick_advance added on the device), `env_steps` feeds
- * pnr_stats (counted on the device by the step kernels, so CUDA-graph replays count).  Both calls synchronise.  (The reference env has no state
- * save / restore of its own -- it is re-created from constructor arguments, pioneer_knm_env.py:38,51.) */
+ * pnr_stats (counted on the device by the step kernels, so CUDA-graph replays count).  Both calls synchronise the DEVICE (every
+ * stream), so the values are current whatever stream the steps ran on.  (The reference env has no state
+ * save / restore of its own -- it is re-created from constructor arguments, pioneer_knm_env.py:38,51.)
+ * Reset keys never repeat: eager launches draw with (tick = host call counter, domain 0); launches captured into the g-th
+ * CUDA graph of this handle draw with (tick = captured counter + device-side advance, domain g), so eager steps and graph
+ * replays may be interleaved freely. */
 int pnr_get_counters(const pnr_handle* h, uint32_t* tick, double* env_steps, uint64_t* seed);
 /* Advance the reset generator's counter by `n` ON THE DEVICE (a one-thread kernel on `stream`).  The host counter that
  * pnr_step passes to its kernel is frozen into a captured CUDA graph; capture this call as the first node of a graph of
@@ -184,13 +241,16 @@ int pnr_stats(pnr_handle* h, double* out, int clear, void* stream);
 /* Same 8 numbers written to a caller-owned DEVICE double[8] without synchronising, for an NCCL
  * all-reduce on the same stream (SUM over {0,1,2,3,6,7}, MAX over {4, -5}). */
 int pnr_stats_device(pnr_handle* h, double* out_device, int clear, void* stream);
+/* Restore the statistics window from HOST double[8] (what pnr_stats returned): checkpoint / resume.  Synchronises. */
+int pnr_set_stats(pnr_handle* h, const double* in8);
 
-/* ---- observation normaliser: the 'MeanStdFilter' observation_filter of the reference launcher
- * (pioneer/launch/pioneer_knm_train.py:66; the filter itself is RLlib's, third party) --------------------------------
+/* ---- observation normaliser: the 'ConcurrentMeanStdFilter' observation_filter of the reference launcher
+ * (pioneer/launch/pioneer_knm_train.py:66; the filter is RLlib's MeanStdFilter behind a lock, third party) -----------
  * pnr_filter_apply: ONE pass over obs_in DEVICE float[n_rows,137]: if `update`, the rows enter the statistics
  * accumulated since the last pnr_filter_sync; if `normalize`, obs_out = clip((obs_in - mean) / (std + 1e-8), +-clip)
  * with the mean / std of the last synchronisation (obs_out may alias obs_in; with normalize = 0 and obs_out == obs_in
- * nothing is written).  Defaults: clip = 10, demean and destd on (RLlib's MeanStdFilter). */
+ * nothing is written).  Defaults: clip = 10, demean and destd on (RLlib's MeanStdFilter).  Before the first synchronisation
+ * that has seen a row the filter is the identity (mean 0, scale 1). */
 #define PNR_FILTER_DELTA_LEN (1 + 2 * PNR_OBS_DIM)   /* rows, sum(x - mean)[137], sum((x - mean)^2)[137] */
 int pnr_filter_configure(pnr_handle* h, double clip, int demean, int destd);
 int pnr_filter_apply(pnr_handle* h, const float* obs_in, float* obs_out, int64_t n_rows, int update, int normalize,

@@ -1,4 +1,4 @@
-"""Build the C restatement of the oracle (test infrastructure): gcc -> oracle/_build/libreach_oracle.so.
+"""Build the C restatements of the oracle (test infrastructure): gcc reach_oracle.c dynamics_oracle.c -> oracle/_build/libreach_oracle.so.
 
     python -m oracle.build_c [--force]
 
@@ -10,20 +10,23 @@ import subprocess
 import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-SRC = os.path.join(HERE, "reach_oracle.c")
+SOURCES = [os.path.join(HERE, f) for f in ("reach_oracle.c", "dynamics_oracle.c")]
+HEADERS = [os.path.join(HERE, "contact.h")]
 OUT_DIR = os.path.join(HERE, "_build")
 LIB_PATH = os.path.join(OUT_DIR, "libreach_oracle.so")
-FLAGS = ["-O2", "-std=c99", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-Wall", "-Werror"]
+# -pthread: the dynamic-mode oracle steps its envs on plain pthreads (65,536 envs x 10 float64 ABA substeps per step)
+FLAGS = ["-O3", "-std=c99", "-fPIC", "-shared", "-ffp-contract=off", "-fno-fast-math", "-pthread", "-Wall", "-Werror"]
 
 
 def build(force: bool = False) -> str:
     """Built into a temporary file and renamed into place, so concurrent callers (pool workers of the CPU baseline)
     never open a half-written library."""
-    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= os.path.getmtime(SRC):
+    newest = max(os.path.getmtime(f) for f in SOURCES + HEADERS + [os.path.abspath(__file__)])
+    if not force and os.path.exists(LIB_PATH) and os.path.getmtime(LIB_PATH) >= newest:
         return LIB_PATH
     os.makedirs(OUT_DIR, exist_ok=True)
     tmp = f"{LIB_PATH}.tmp.{os.getpid()}"
-    cmd = [os.environ.get("CC", "gcc")] + FLAGS + [SRC, "-o", tmp, "-lm"]
+    cmd = [os.environ.get("CC", "gcc")] + FLAGS + SOURCES + ["-o", tmp, "-lm"]
     proc = subprocess.run(cmd, capture_output=True, text=True)
     if proc.returncode != 0:
         if os.path.exists(tmp):

@@ -11,6 +11,7 @@ from typing import Optional
 import numpy as np
 
 from . import build_c
+from .c_dyn_oracle import fill_contact, orc_contact
 from .reach_oracle import DOF, OBS_DIM, OracleChain, OracleConfig
 
 _d3, _d9 = C.c_double * 3, C.c_double * 9
@@ -23,7 +24,7 @@ class orc_params(C.Structure):
                 ("award_max", C.c_double), ("award_done", C.c_double), ("award_potential_slope", C.c_double),
                 ("penalty_step", C.c_double), ("target_lo", _d3), ("target_hi", _d3), ("timestep", C.c_double),
                 ("frame_skip", C.c_int32), ("max_episode_steps", C.c_int32), ("legacy", C.c_int32),
-                ("auto_reset", C.c_int32), ("obs_autoreset", C.c_int32)]
+                ("auto_reset", C.c_int32), ("obs_autoreset", C.c_int32), ("contact", orc_contact)]
 
 
 _lib = None
@@ -43,6 +44,7 @@ def load():
         lib.orc_step.argtypes = [P, P, P, P, P]
         lib.orc_get_state.argtypes = [P, P, P, P, P, P, P, P]
         lib.orc_stats.argtypes = [P, P]
+        lib.orc_get_boxes.argtypes = [P, P]
         lib.orc_sizeof_params.restype = C.c_int64
         assert lib.orc_sizeof_params() == C.sizeof(orc_params), "orc_params layout mismatch"
         _lib = lib
@@ -73,6 +75,7 @@ class COracleBatch:
         _fill(p.target_lo, cfg.target_lo); _fill(p.target_hi, cfg.target_hi)
         p.timestep, p.frame_skip, p.max_episode_steps = cfg.timestep, cfg.frame_skip, cfg.max_episode_steps or 0
         p.legacy, p.auto_reset, p.obs_autoreset = int(arith == "legacy"), int(auto_reset), int(obs_mode == "autoreset")
+        fill_contact(p.contact, chain.capsules, cfg.obstacles, cfg.contact_penalty, getattr(cfg, "random_box", None))
         self.n = int(n_envs)
         self.h = self.lib.orc_create(C.byref(p), self.n, int(env_id_base), int(seed) & (2 ** 64 - 1))
         assert self.h, "orc_create failed"
@@ -114,6 +117,11 @@ class COracleBatch:
                  ep_return=np.zeros(n, np.float32))
         self.lib.orc_get_state(self.h, *[s[k].ctypes.data for k in ("r", "v", "a", "potential", "target", "t", "ep_return")])
         return s
+
+    def boxes(self):
+        out = np.zeros((self.n, 6), np.float64)
+        self.lib.orc_get_boxes(self.h, out.ctypes.data)
+        return out
 
     @property
     def stats(self):

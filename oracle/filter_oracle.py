@@ -49,7 +49,9 @@ class SequentialFilter:
 class BatchSyncFilter:
     def __init__(self, dim, clip=10.0):
         self.rs, self.clip = RunningStat(dim), clip
-        self.applied_mean, self.applied_std = np.zeros(dim), np.zeros(dim)
+        # before the first synchronisation nothing has been pushed: the filter is the identity (mean 0, scale 1), as an
+        # RLlib filter that has seen no sample never normalises anything
+        self.applied_mean, self.applied_std = np.zeros(dim), np.ones(dim) - 1e-8
         self.pending = []
 
     def __call__(self, batch, update=True):

@@ -25,6 +25,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include "contact.h"
+
 #define DOF 6
 #define OBS_DIM 137
 #define ORC_DONE 1
@@ -43,6 +45,7 @@ typedef struct {
     int32_t legacy;      /* 0 = 'np2' (float32 arithmetic), 1 = 'legacy' (NumPy 1.x promotion) */
     int32_t auto_reset;
     int32_t obs_autoreset; /* 0 = terminal observation, 1 = first observation of the next episode */
+    orc_contact contact;   /* obstacle variant (contact.h): reward -= contact_penalty * sum of capsule penetration depths */
 } orc_params;
 
 typedef struct {
@@ -51,6 +54,7 @@ typedef struct {
     double potential;
     int32_t elapsed;
     float ep_return;
+    double box_p[3], box_e[3];  /* the per-env random box of the obstacle variant (centre, half extents) */
 } orc_env;
 
 typedef struct {
@@ -79,13 +83,15 @@ static void philox4x32_10(const uint32_t ctr[4], uint32_t k0, uint32_t k1, uint3
 
 static float u01(uint32_t x) { return (float)(x >> 8) * 5.9604644775390625e-08f; }
 
-static void reset_draws(const orc_batch* b, int64_t global_env, uint32_t tick, float u[9]) {
-    uint32_t out[12];
-    for (uint32_t blk = 0; blk < 3; ++blk) {
+/* 6 joints, 3 target coordinates (reference draw order, pioneer_knm_env.py:80-90), then the per-env box of the obstacle
+ * variant: 3 half extents, 2 centre coordinates (pioneer/temp/pioneer_env.py:173-174) */
+static void reset_draws(const orc_batch* b, int64_t global_env, uint32_t tick, float u[16]) {
+    uint32_t out[16];
+    for (uint32_t blk = 0; blk < 4; ++blk) {
         const uint32_t ctr[4] = {(uint32_t)global_env, (uint32_t)((uint64_t)global_env >> 32), tick, blk};
         philox4x32_10(ctr, (uint32_t)b->seed, (uint32_t)(b->seed >> 32), out + 4 * blk);
     }
-    for (int i = 0; i < 9; ++i) u[i] = u01(out[i]);
+    for (int i = 0; i < 16; ++i) u[i] = u01(out[i]);
 }
 
 /* ---- forward kinematics of 'robot:pointer', float64, tip-to-base with Rodrigues' formula ---- */
@@ -158,8 +164,8 @@ static void integrate_joint(const orc_batch* b, int i, float a0, float v0, float
 
 static void reset_env(orc_batch* b, int64_t i, const float* q0, const float* target, uint32_t tick) {
     orc_env* e = &b->envs[i];
-    float u[9];
-    if (!q0 || !target) reset_draws(b, b->env_id_base + i, tick, u);
+    float u[16];
+    reset_draws(b, b->env_id_base + i, tick, u);
     for (int j = 0; j < DOF; ++j) {
         if (q0) e->r[j] = q0[j];
         else { const float span = b->r_hi[j] - b->r_lo[j]; const float m = span * u[j]; e->r[j] = b->r_lo[j] + m; }
@@ -172,6 +178,18 @@ static void reset_env(orc_batch* b, int64_t i, const float* q0, const float* tar
             const float span = hi - lo; const float m = span * u[6 + k];
             e->target[k] = (double)(float)(lo + m);
         }
+    }
+    if (b->p.contact.random_box >= 0) {
+        const orc_contact* c = &b->p.contact;
+        for (int k = 0; k < 3; ++k) {
+            const float lo = (float)c->box_size_lo[k], span = (float)c->box_size_hi[k] - lo; const float m = span * u[9 + k];
+            e->box_e[k] = (double)(float)(lo + m);
+        }
+        for (int k = 0; k < 2; ++k) {
+            const float lo = (float)c->box_pos_lo[k], span = (float)c->box_pos_hi[k] - lo; const float m = span * u[12 + k];
+            e->box_p[k] = (double)(float)(lo + m);
+        }
+        e->box_p[2] = e->box_e[2];                              /* the box stands on z = 0 */
     }
     e->potential = 0.0; e->elapsed = 0; e->ep_return = 0.f;
 }
@@ -261,7 +279,14 @@ void orc_step(orc_batch* b, const float* actions, double* obs, double* reward, u
         const double old_potential = e->potential;
         e->potential = potential_of(p, distance);
         int done = distance < p->done_distance;
-        const double rew = (e->potential - old_potential) + (-p->penalty_step) + (done ? p->award_done : 0.0);
+        double rew = (e->potential - old_potential) + (-p->penalty_step) + (done ? p->award_done : 0.0);
+        if (p->contact.n_obstacles > 0 && p->contact.contact_penalty != 0.0) {
+            double qd_[DOF];
+            for (int j = 0; j < DOF; ++j) qd_[j] = (double)e->r[j];
+            const int rb = p->contact.random_box >= 0;
+            rew -= p->contact.contact_penalty * orc_contact_depth(&p->contact, p->axis, p->origin_xyz, p->origin_rot, qd_,
+                                                                  rb ? e->box_p : NULL, rb ? e->box_e : NULL);
+        }
         if (obs) observe(b, e, obs + i * OBS_DIM);
         e->elapsed += 1;
         int truncated = 0;
@@ -300,6 +325,12 @@ void orc_get_state(const orc_batch* b, float* r, float* v, float* a, double* pot
         if (t) t[i] = e->elapsed;
         if (ep_return) ep_return[i] = e->ep_return;
     }
+}
+
+/* box float64 [n,6]: centre and half extents of every env's random box */
+void orc_get_boxes(const orc_batch* b, double* box) {
+    for (int64_t i = 0; i < b->n; ++i)
+        for (int k = 0; k < 3; ++k) { box[i * 6 + k] = b->envs[i].box_p[k]; box[i * 6 + 3 + k] = b->envs[i].box_e[k]; }
 }
 
 void orc_stats(const orc_batch* b, double* out8) { memcpy(out8, b->stats, sizeof b->stats); }

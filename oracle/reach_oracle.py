@@ -73,15 +73,16 @@ def _u01(x: int) -> np.float32:
     return f32(x >> 8) * f32(2.0 ** -24)
 
 
-def reset_draws(seed: int, global_env_id: int, tick: int):
-    """9 uniforms for one reset: 6 joints then 3 target coordinates (reference draw order,
-    pioneer_knm_env.py:80-90).  Counter = (env id lo, env id hi, tick, block), key = seed."""
+def reset_draws(seed: int, global_env_id: int, tick: int, n: int = 9):
+    """Uniforms for one reset: 6 joints then 3 target coordinates (reference draw order, pioneer_knm_env.py:80-90); with
+    ``n=14`` also the per-env box of the obstacle variant (3 half extents, 2 centre coordinates: the draw order of
+    pioneer/temp/pioneer_env.py:173-174).  Counter = (env id lo, env id hi, tick, block), key = seed."""
     key = (seed & _MASK, (seed >> 32) & _MASK)
     out: List[np.float32] = []
-    for block in range(3):
+    for block in range(4):
         out.extend(_u01(x) for x in philox4x32_10((global_env_id & _MASK, (global_env_id >> 32) & _MASK,
                                                    tick & _MASK, block), key))
-    return out[:9]
+    return out[:n]
 
 
 # --------------------------------------------------------------------------------------------
@@ -109,7 +110,9 @@ class OracleConfig:
     # plane in its GUI demo, pioneer_knm_env.py:249-261): list of (kind, position, extent), kind in plane/box/sphere
     obstacles: Tuple = ()
     contact_penalty: float = 0.0
-    box_samples: int = 8
+    # (pos_lo[2], pos_hi[2], size_lo[3], size_hi[3]): the first box among ``obstacles`` is redrawn at every reset, half
+    # extents ~ U(size), centre = (U(pos), half height) -- the legacy randomizer, pioneer/temp/pioneer_env.py:169-192
+    random_box: Optional[Tuple] = None
 
 
 @dataclass
@@ -156,14 +159,58 @@ def fk_point(chain: OracleChain, q, body: int, point) -> np.ndarray:
     return p
 
 
-def contact_depth(chain: OracleChain, q, obstacles, box_samples: int = 8) -> float:
-    """Sum over (link capsule, obstacle) pairs of the penetration depth max(0, radius - distance(segment, obstacle)).
-    plane : exact (signed distance is linear along the segment: the nearer end point decides)
-    sphere: exact (closest point of the segment to the centre)
-    box   : axis-aligned signed-distance function sampled at ``box_samples`` equally spaced points of the segment"""
+def box_sdf(x: np.ndarray, ext: np.ndarray) -> float:
+    """Signed distance of ``x`` (relative to the box centre) to the axis-aligned box with half extents ``ext``."""
+    qv = np.abs(x) - ext
+    return float(np.linalg.norm(np.maximum(qv, 0.0))) + min(float(qv.max()), 0.0)
+
+
+def segment_box_distance(a, b, centre, ext) -> float:
+    """EXACT minimum of the box signed-distance function over the segment [a, b].  The function is convex along the
+    segment and piecewise: the root of a quadratic between the parameters where a coordinate crosses a face plane, linear
+    inside the box between the parameters where the nearest face changes.  Every breakpoint is enumerated, every piece
+    minimised in closed form (same method as oracle/contact.h; the CUDA path bisects on the derivative instead)."""
+    a0 = np.array(a, f64) - np.array(centre, f64)
+    d = np.array(b, f64) - np.array(a, f64)
+    e = np.array(ext, f64)
+    ts = [0.0, 1.0]
+    for i in range(3):
+        if d[i] != 0.0:
+            ts += [(e[i] - a0[i]) / d[i], (-e[i] - a0[i]) / d[i], -a0[i] / d[i]]
+    for i in range(3):
+        for j in range(i + 1, 3):
+            for si in (-1.0, 1.0):
+                for sj in (-1.0, 1.0):
+                    den = si * d[i] - sj * d[j]
+                    if den != 0.0:
+                        ts.append((e[i] - e[j] - si * a0[i] + sj * a0[j]) / den)
+    ts = sorted(t for t in ts if 0.0 <= t <= 1.0)
+    best = min(box_sdf(a0 + t * d, e) for t in ts)
+    for t0, t1 in zip(ts[:-1], ts[1:]):
+        if t1 <= t0:
+            continue
+        x = a0 + 0.5 * (t0 + t1) * d
+        active = np.abs(x) - e > 0.0
+        if active.any():                                    # outside: f^2 = sum over the active axes of (u + t w)^2
+            sgn = np.where(x > 0.0, 1.0, -1.0)
+            u, w = (sgn * a0 - e)[active], (sgn * d)[active]
+            if float(w @ w) > 0.0:
+                tv = min(max(-float(u @ w) / float(w @ w), t0), t1)
+                best = min(best, box_sdf(a0 + tv * d, e))
+    return best
+
+
+def contact_depth(chain: OracleChain, q, obstacles, box=None) -> float:
+    """Sum over (link capsule, obstacle) pairs of the penetration depth max(0, radius - distance(segment, obstacle)),
+    distance = the minimum of the obstacle's signed-distance function over the capsule's axis segment, exact for all kinds:
+    plane : linear along the segment, the nearer end point decides
+    sphere: closest point of the segment to the centre
+    box   : segment_box_distance
+    ``box`` = (centre, half extents) replaces the first box among ``obstacles`` (the per-env random box)."""
     total = 0.0
     for body, radius, p0, p1 in chain.capsules:
         a, b = fk_point(chain, q, body, p0), fk_point(chain, q, body, p1)
+        first_box = True
         for kind, pos, ext in obstacles:
             pos, ext = np.array(pos, f64), np.array(ext, f64)
             if kind == "plane":
@@ -173,11 +220,10 @@ def contact_depth(chain: OracleChain, q, obstacles, box_samples: int = 8) -> flo
                 t = min(max(float((pos - a) @ ab) / max(float(ab @ ab), 1e-30), 0.0), 1.0)
                 d = float(np.linalg.norm(a + t * ab - pos)) - float(ext[0])
             elif kind == "box":
-                d = math.inf
-                for k in range(box_samples):
-                    x = a + (b - a) * (k / (box_samples - 1))
-                    qv = np.abs(x - pos) - ext
-                    d = min(d, float(np.linalg.norm(np.maximum(qv, 0.0))) + min(float(qv.max()), 0.0))
+                if first_box and box is not None:
+                    pos, ext = np.array(box[0], f64), np.array(box[1], f64)
+                first_box = False
+                d = segment_box_distance(a, b, pos, ext)
             else:
                 raise ValueError(kind)
             total += max(0.0, radius - d)
@@ -214,13 +260,19 @@ class OracleEnv:
         self.potential = 0.0
         self.elapsed = 0                             # TimeLimit._elapsed_steps
         self.ep_return = f32(0)                      # float32 accumulator, as the device keeps it
+        self.box = None                              # (centre, half extents) of the per-env random box
 
     # -- pioneer_knm_env.py:76-105 -----------------------------------------------------------
     def reset_world(self, joint_positions=None, target_position=None, tick: int = 0):
         """Injected values are rounded to float32 (the device stores float32 state); sampled values
         come from Philox keyed on (seed, global env id, tick) instead of the reference's MT19937."""
-        if joint_positions is None or target_position is None:
-            u = reset_draws(self.rng_seed, self.global_env_id, tick)
+        u = reset_draws(self.rng_seed, self.global_env_id, tick, 14)
+        rb = self.config.random_box
+        if rb is not None:
+            pos_lo, pos_hi, size_lo, size_hi = (np.array(x, f32) for x in rb)
+            ext = [f32(size_lo[i] + f32((size_hi[i] - size_lo[i]) * u[9 + i])) for i in range(3)]
+            pos = [f32(pos_lo[i] + f32((pos_hi[i] - pos_lo[i]) * u[12 + i])) for i in range(2)] + [ext[2]]
+            self.box = (np.array(pos, f64), np.array(ext, f64))
         if joint_positions is None:
             joint_positions = [f32(self.r_lo[i] + f32((self.r_hi[i] - self.r_lo[i]) * u[i])) for i in range(DOF)]
         if target_position is None:
@@ -301,7 +353,7 @@ class OracleEnv:
         reward = (self.potential - old_potential) + (-self.config.penalty_step) \
             + (self.config.award_done if done else 0)                                  # :162-165
         if self.config.obstacles and self.config.contact_penalty:
-            self.last_contact_depth = contact_depth(self.chain, self.r, self.config.obstacles, self.config.box_samples)
+            self.last_contact_depth = contact_depth(self.chain, self.r, self.config.obstacles, self.box)
             reward -= self.config.contact_penalty * self.last_contact_depth
         # world.step(): frame_skip x stepSimulation with g = 0, qdot = 0, tau = 0 leaves q unchanged (:181)
         return float(reward), bool(done)

@@ -11,7 +11,7 @@ from typing import Optional
 
 from . import build as _build
 
-PNR_ABI_VERSION = 3
+PNR_ABI_VERSION = 4
 PNR_DOF = 6
 PNR_OBS_DIM = 137
 PNR_MAX_CAPSULES = 8
@@ -25,6 +25,9 @@ PNR_OBS_TERMINAL, PNR_OBS_AUTORESET = 0, 1
 PNR_MODE_KINEMATIC, PNR_MODE_DYNAMIC = 0, 1
 PNR_DONE, PNR_TRUNCATED = 1, 2
 PNR_OBSTACLE_NONE, PNR_OBSTACLE_PLANE, PNR_OBSTACLE_BOX, PNR_OBSTACLE_SPHERE = 0, 1, 2, 3
+PNR_STEPPING_EXPLICIT, PNR_STEPPING_BULLET = 0, 1
+PNR_HOST_FULL, PNR_HOST_COMPACT = 0, 1
+PNR_OBS_COMPACT_DIM, PNR_OBS_CONST_BEGIN, PNR_OBS_CONST_END = 101, 18, 54
 
 _d3 = C.c_double * 3
 _d9 = C.c_double * 9
@@ -58,6 +61,11 @@ class pnr_config(C.Structure):
         ("n_obstacles", C.c_int32), ("obstacle_type", C.c_int32 * PNR_MAX_OBSTACLES),
         ("obstacle_p", _d3 * PNR_MAX_OBSTACLES), ("obstacle_e", _d3 * PNR_MAX_OBSTACLES),
         ("contact_penalty", C.c_double),
+        ("random_box", C.c_int32),
+        ("box_pos_lo", C.c_double * 2), ("box_pos_hi", C.c_double * 2), ("box_size_lo", _d3), ("box_size_hi", _d3),
+        ("stepping", C.c_int32),
+        ("link_damping", C.c_double), ("max_velocity", C.c_double),
+        ("motor_kp", C.c_double), ("motor_kd", C.c_double), ("motor_max_force", C.c_double),
     ]
 
 
@@ -76,6 +84,7 @@ SIGNATURES = {
     "pnr_num_envs": (C.c_int64, [_H]),
     "pnr_get_bounds": (C.c_int, [_H, C.POINTER(C.c_float), C.POINTER(C.c_float), C.POINTER(C.c_float),
                                  C.POINTER(C.c_float)]),
+    "pnr_get_obs_constants": (C.c_int, [_H, C.POINTER(C.c_float)]),
     "pnr_seed": (C.c_int, [_H, C.c_uint64]),
     "pnr_get_counters": (C.c_int, [_H, C.POINTER(C.c_uint32), C.POINTER(C.c_double), C.POINTER(C.c_uint64)]),
     "pnr_set_counters": (C.c_int, [_H, C.c_uint32, C.c_double]),
@@ -83,10 +92,17 @@ SIGNATURES = {
     "pnr_reset": (C.c_int, [_H, _P, C.c_int64, _P, _P, _P, _S]),
     "pnr_step": (C.c_int, [_H, _P, _P, _P, _P, _S]),
     "pnr_step_host": (C.c_int, [_H, _P, _P, _P, _P]),
+    "pnr_step_host_begin": (C.c_int, [_H, _P, _P, _P, _P, C.c_int]),
+    "pnr_step_host_end": (C.c_int, [_H]),
+    "pnr_expand_obs_host": (C.c_int, [_H, _P, _P, C.c_int64]),
     "pnr_observe": (C.c_int, [_H, _P, C.c_int64, _P, _S]),
+    "pnr_observe_done": (C.c_int, [_H, _P, _P, _P, _S]),
     "pnr_get_state": (C.c_int, [_H, _P, _P, _P, _P, _P, _P, _P, _S]),
     "pnr_set_state": (C.c_int, [_H, _P, _P, _P, _P, _P, _P, _P, _S]),
+    "pnr_get_boxes": (C.c_int, [_H, _P, _S]),
+    "pnr_set_boxes": (C.c_int, [_H, _P, _S]),
     "pnr_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.c_int, _S]),
+    "pnr_set_stats": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "pnr_stats_device": (C.c_int, [_H, _P, C.c_int, _S]),
     "pnr_filter_configure": (C.c_int, [_H, C.c_double, C.c_int, C.c_int]),
     "pnr_filter_apply": (C.c_int, [_H, _P, _P, C.c_int64, C.c_int, C.c_int, _S]),

@@ -57,6 +57,14 @@ def make_config(pioneer_config: PioneerKinematicConfig, simulation_config: Simul
             c.obstacle_p[i][k] = float(ob.position[k])
             c.obstacle_e[i][k] = float(ob.extent[k])
     c.contact_penalty = float(bc.contact_penalty)
+    c.random_box = 1 if bc.random_box else 0
+    for k in range(2):
+        c.box_pos_lo[k], c.box_pos_hi[k] = float(bc.box_pos_lo[k]), float(bc.box_pos_hi[k])
+    for k in range(3):
+        c.box_size_lo[k], c.box_size_hi[k] = float(bc.box_size_lo[k]), float(bc.box_size_hi[k])
+    c.stepping = {"explicit": _cabi.PNR_STEPPING_EXPLICIT, "bullet": _cabi.PNR_STEPPING_BULLET}[bc.stepping]
+    c.link_damping, c.max_velocity = float(bc.link_damping), float(bc.max_velocity)
+    c.motor_kp, c.motor_kd, c.motor_max_force = float(bc.motor_kp), float(bc.motor_kd), float(bc.motor_max_force)
     return c
 
 
@@ -103,7 +111,17 @@ class BatchedPioneerEnv:
         self.metadata = {"render.modes": [], "video.frames_per_second": self.simulation_config.frames_per_second}
         # spaces of ONE env (pioneer_knm_env.py:72-74); the GPU emits float32 observations (the reference
         # concatenates float32 and float64 pieces into float64)
-        self.action_space = Box(-self.a_max, self.a_max, dtype=np.float32)
+        bc = self.batch_config
+        if bc.mode == "dynamic":
+            # the action is a motor set point, not the kinematic env's acceleration: desired joint positions under PD /
+            # POSITION_CONTROL, joint torques (clamped to +-effort * torque_scale) otherwise
+            if bc.kp or bc.kd or (bc.stepping == "bullet" and bc.motor_max_force > 0):
+                self.action_space = Box(self.r_lo.copy(), self.r_hi.copy(), dtype=np.float32)
+            else:
+                tau = (np.asarray(self.chain.effort, np.float64) * bc.torque_scale).astype(np.float32)
+                self.action_space = Box(-tau, tau, dtype=np.float32)
+        else:
+            self.action_space = Box(-self.a_max, self.a_max, dtype=np.float32)
         self.observation_space = Box(np.full(OBS_DIM, -np.inf, np.float32), np.full(OBS_DIM, np.inf, np.float32),
                                      dtype=np.float32)
         self.reward_range = (-float("inf"), float("inf"))
@@ -112,12 +130,16 @@ class BatchedPioneerEnv:
         self._reward = torch.empty(self.n_envs, dtype=torch.float32, **kw)
         self._flags = torch.empty(self.n_envs, dtype=torch.uint8, **kw)
         self._host: Optional[Dict[str, torch.Tensor]] = None
+        self._host_ring = None
+        self._filters = []                                   # MeanStdObsFilter objects bound to this handle
         self.step_index = 0
 
     # ---- lifetime ---------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             torch.cuda.synchronize(self.device)
+            for f in getattr(self, "_filters", ()):          # a filter must not outlive the handle it points into
+                f._h = None
             self._lib.pnr_destroy(self._h)
             self._h = C.c_void_p()
 
@@ -209,7 +231,10 @@ class BatchedPioneerEnv:
         assert actions.shape == (T, self.n_envs, DOF) and obs.shape == (T, self.n_envs, OBS_DIM)
         assert reward.shape == (T, self.n_envs) and flags.shape == (T, self.n_envs)
         for t_ in (actions, obs, reward, flags):
-            assert t_.is_contiguous() and t_.device == self.device
+            assert t_.device == self.device and all(t_[k].is_contiguous() for k in range(T))
+        # pnr_step stores observation tiles with 16-byte bulk copies: every obs[t] must start on a 16-byte boundary, i.e.
+        # the row count of the allocation must be a multiple of 4 (allocate [T, ceil4(N), 137] and pass obs[:, :N])
+        assert all(obs[k].data_ptr() % 16 == 0 for k in range(T)), "obs[t] must be 16-byte aligned (pad N to a multiple of 4)"
         assert actions.dtype == torch.float32 and obs.dtype == torch.float32 and flags.dtype == torch.uint8
         with torch.cuda.device(self.device):
             self.step_tensor(actions[0], out=(obs[0], reward[0], flags[0]))     # one-time kernel attribute setup
@@ -251,6 +276,54 @@ class BatchedPioneerEnv:
         self.step_index += 1
         return h["obs"].numpy(), h["reward"].numpy(), h["flags"].numpy()
 
+    def obs_constants(self) -> np.ndarray:
+        """obs[18:54] of every row (r_lo, r_hi and their cos / sin), exactly as the kernels write them."""
+        out = (C.c_float * 36)()
+        _cabi.check(self._lib.pnr_get_obs_constants(self._h, out), "pnr_get_obs_constants")
+        return np.array(out, dtype=np.float32)
+
+    def expand_compact(self, compact: np.ndarray) -> np.ndarray:
+        """float32 [n, 101] (PNR_HOST_COMPACT) -> float32 [n, 137], bit for bit what the full layout delivers."""
+        compact = np.ascontiguousarray(compact, dtype=np.float32)
+        n = compact.shape[0]
+        full = np.empty((n, OBS_DIM), np.float32)
+        _cabi.check(self._lib.pnr_expand_obs_host(self._h, compact.ctypes.data, full.ctypes.data, n), "pnr_expand_obs_host")
+        return full
+
+    def step_host_begin(self, actions: torch.Tensor, compact: bool = False):
+        """Asynchronous, double-buffered host step (pnr_step_host_begin): ``actions`` is a pinned float32 [N,6] host tensor
+        that must stay untouched until the matching ``step_host_end``.  At most two steps may be in flight; the results
+        land in a ring of two pinned buffer sets.  ``compact=True`` moves 101 instead of 137 columns per row over PCIe."""
+        assert actions.device.type == "cpu" and actions.dtype == torch.float32 and actions.is_contiguous() \
+            and actions.numel() == self.n_envs * DOF
+        if self._host_ring is None:
+            pin = dict(pin_memory=True)
+            self._host_ring = dict(slot=0, pending=[], sets=[
+                dict(obs=torch.empty((self.n_envs, OBS_DIM), dtype=torch.float32, **pin),
+                     reward=torch.empty(self.n_envs, dtype=torch.float32, **pin),
+                     flags=torch.empty(self.n_envs, dtype=torch.uint8, **pin)) for _ in range(2)])
+        ring = self._host_ring
+        buf = ring["sets"][ring["slot"]]
+        width = _cabi.PNR_OBS_COMPACT_DIM if compact else OBS_DIM
+        _cabi.check(self._lib.pnr_step_host_begin(self._h, actions.data_ptr(), buf["obs"].data_ptr(), buf["reward"].data_ptr(),
+                                                  buf["flags"].data_ptr(),
+                                                  _cabi.PNR_HOST_COMPACT if compact else _cabi.PNR_HOST_FULL),
+                    "pnr_step_host_begin")
+        ring["pending"].append((ring["slot"], width, actions))
+        ring["slot"] ^= 1
+        self.step_index += 1
+
+    def step_host_end(self):
+        """Wait for the oldest step begun; returns numpy views (obs [N,137] or [N,101], reward, flags) of its pinned
+        buffers, valid until two more steps have been begun."""
+        ring = self._host_ring
+        assert ring is not None and ring["pending"], "no host step in flight"
+        _cabi.check(self._lib.pnr_step_host_end(self._h), "pnr_step_host_end")
+        slot, width, _ = ring["pending"].pop(0)
+        buf = ring["sets"][slot]
+        obs = buf["obs"].numpy().reshape(-1)[:self.n_envs * width].reshape(self.n_envs, width)
+        return obs, buf["reward"].numpy(), buf["flags"].numpy()
+
     def _ensure_host(self) -> Dict[str, torch.Tensor]:
         if self._host is None:
             pin = dict(pin_memory=True)
@@ -274,6 +347,18 @@ class BatchedPioneerEnv:
             _cabi.check(self._lib.pnr_observe(self._h, None if idx is None else idx.data_ptr(), n, out.data_ptr(),
                                               self._stream()), "pnr_observe")
         return out
+
+    def observe_done(self, flags: torch.Tensor, obs: torch.Tensor, terminal_out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """RLlib's ``reset_at`` after a done, for all envs at once (pnr_observe_done): rows of ``obs`` whose env finished in
+        the step that produced ``flags`` are replaced by the first observation of the new episode (what the policy must
+        see next); their terminal rows go to ``terminal_out`` when given.  In place, fixed launch shape."""
+        assert flags.dtype == torch.uint8 and flags.numel() == self.n_envs and obs.shape == (self.n_envs, OBS_DIM)
+        assert obs.is_contiguous() and obs.dtype == torch.float32 and obs.device == self.device
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.pnr_observe_done(self._h, flags.data_ptr(), obs.data_ptr(),
+                                                   None if terminal_out is None else terminal_out.data_ptr(),
+                                                   self._stream()), "pnr_observe_done")
+        return obs
 
     def state(self) -> Dict[str, torch.Tensor]:
         """r, v, a [N,6]; potential [N]; target [N,3]; t [N] int32 (TimeLimit._elapsed_steps); ep_return [N]."""
@@ -299,24 +384,53 @@ class BatchedPioneerEnv:
             _cabi.check(self._lib.pnr_set_state(self._h, *[None if x is None else x.data_ptr() for x in keep],
                                                 self._stream()), "pnr_set_state")
 
+    def boxes(self) -> torch.Tensor:
+        """The per-env random box of the obstacle variant (BatchConfig.random_box): float32 [N, 6] = centre, half extents."""
+        out = torch.empty((self.n_envs, 6), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.pnr_get_boxes(self._h, out.data_ptr(), self._stream()), "pnr_get_boxes")
+        return out
+
+    def set_boxes(self, boxes) -> None:
+        with torch.cuda.device(self.device):
+            b = self._dev(boxes, torch.float32, (self.n_envs, 6))
+            _cabi.check(self._lib.pnr_set_boxes(self._h, b.data_ptr(), self._stream()), "pnr_set_boxes")
+            self._keep_boxes = b
+
     # ---- checkpoint / resume -------------------------------------------------------------------
     def state_dict(self) -> Dict[str, object]:
-        """Everything needed to continue bit-identically: per-env state (host copies), the reset generator's seed and
-        call counter, and the episode statistics of the current window.  (The reference env has no save / restore; it
-        is re-created from constructor arguments, pioneer_knm_env.py:38,51.)"""
+        """Everything needed to continue bit-identically: per-env state (host copies, incl. the random boxes), the reset
+        generator's seed and call counter, the episode statistics of the current window (all eight numbers) and the running
+        statistics of every observation filter bound to this env.  (The reference env has no save / restore; it is
+        re-created from constructor arguments, pioneer_knm_env.py:38,51 -- RLlib checkpoints carry the filter state.)"""
         tick, steps, seed = C.c_uint32(), C.c_double(), C.c_uint64()
         _cabi.check(self._lib.pnr_get_counters(self._h, C.byref(tick), C.byref(steps), C.byref(seed)), "pnr_get_counters")
-        return {"n_envs": self.n_envs, "env_id_base": self.env_id_base, "seed": int(seed.value), "tick": int(tick.value),
-                "env_steps": float(steps.value), "step_index": self.step_index,
-                "state": {k: v.cpu() for k, v in self.state().items()}}
+        sd = {"n_envs": self.n_envs, "env_id_base": self.env_id_base, "seed": int(seed.value), "tick": int(tick.value),
+              "env_steps": float(steps.value), "step_index": self.step_index,
+              "state": {k: v.cpu() for k, v in self.state().items()},
+              "episode_stats": self.episode_stats(clear=False)}
+        if self.batch_config.random_box and self.batch_config.contact_penalty and self.batch_config.obstacles:
+            sd["boxes"] = self.boxes().cpu()
+        if self._filters:
+            f = self._filters[-1]
+            sd["obs_filter"] = {"count": f.n, "mean": f.mean, "var": f.var}
+        return sd
 
     def load_state_dict(self, sd: Dict[str, object]) -> None:
         assert sd["n_envs"] == self.n_envs and sd["env_id_base"] == self.env_id_base, "checkpoint is for another shard"
         st = sd["state"]
         self.set_state(r=st["r"], v=st["v"], a=st["a"], potential=st["potential"], target=st["target"], t=st["t"],
                        ep_return=st["ep_return"])
+        if "boxes" in sd:
+            self.set_boxes(sd["boxes"])
         self.seed(int(sd["seed"]))
         _cabi.check(self._lib.pnr_set_counters(self._h, int(sd["tick"]), float(sd["env_steps"])), "pnr_set_counters")
+        if "episode_stats" in sd:
+            vals = (C.c_double * _cabi.PNR_STATS_LEN)(*[float(sd["episode_stats"][k]) for k in STATS_FIELDS])
+            _cabi.check(self._lib.pnr_set_stats(self._h, vals), "pnr_set_stats")
+        if "obs_filter" in sd and self._filters:
+            f = sd["obs_filter"]
+            self._filters[-1].set_stats(f["count"], f["mean"], f["var"])
         self.step_index = int(sd["step_index"])
 
     # the reference's per-env attributes, batched

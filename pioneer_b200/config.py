@@ -87,3 +87,19 @@ class BatchConfig:
     torque_scale: float = 1.0
     obstacles: List[Obstacle] = field(default_factory=list)
     contact_penalty: float = 0.0
+    # per-env random box (the legacy randomizer, pioneer/temp/pioneer_env.py:169-192): the first box among `obstacles` is
+    # redrawn at every reset -- half extents ~ U(box_size_lo, box_size_hi), centre = (U(box_pos_lo, box_pos_hi), half height)
+    random_box: bool = False
+    box_pos_lo: Tuple[float, float] = (8.0, -6.0)
+    box_pos_hi: Tuple[float, float] = (14.0, 6.0)
+    box_size_lo: Tuple[float, float, float] = (0.3, 0.3, 3.0)
+    box_size_hi: Tuple[float, float, float] = (0.7, 0.7, 7.0)
+    # dynamic mode: 'explicit'  | 'bullet' (opt-in Bullet-like substep: per-link damping, +-max_velocity
+    # clamp, POSITION_CONTROL as a velocity-level motor constraint with impulse clamp motor_max_force * dt;
+    # Joint.control_position, bullet_scene.py:123-142)
+    stepping: str = "explicit"
+    link_damping: float = 0.04
+    max_velocity: float = 100.0
+    motor_kp: float = 0.1                 # setJointMotorControl2 positionGain
+    motor_kd: float = 1.0                 # velocityGain
+    motor_max_force: float = 0.0          # `force`; 0 = motors off

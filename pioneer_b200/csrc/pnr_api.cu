@@ -35,6 +35,11 @@ struct pnr_handle {
     double* stats_out = nullptr;    // device double[8] snapshot
     double* stats_host = nullptr;   // pinned
     uint32_t tick = 0;              // keys the reset generator: one tick per reset/step call
+    uint64_t seed = 0;              // host copy of the key in PnrStats::seed_*
+    uint32_t n_graphs = 0;          // CUDA graphs this handle's steps were captured into: each gets its own reset-key domain
+    unsigned long long capture_id = 0;
+    float4* box_a = nullptr;        // per-env random box (cfg.random_box): centre x y | half extents x y
+    float* box_z = nullptr;         //                                      half height = centre z
     int64_t launches = 0;
     float a_max[PNR_DOF];
     // observation normaliser (pnr_filter_*): device accumulator, applied statistics, host-side running statistics
@@ -45,11 +50,18 @@ struct pnr_handle {
     double filt_clip = 10.0;
     int filt_demean = 1, filt_destd = 1;
     int filt_fused = 0, filt_fused_update = 1;   // pnr_filter_fuse: the step kernel normalises and pushes statistics
-    // host-buffer path (pnr_step_host)
-    float *h_actions = nullptr, *h_obs = nullptr, *h_reward = nullptr;
-    uint8_t* h_done = nullptr;
-    cudaStream_t host_stream = nullptr, host_stream2 = nullptr;
-    cudaEvent_t host_event = nullptr, host_order_event = nullptr;
+    // host-buffer path (pnr_step_host, pnr_step_host_begin / _end): two device staging sets, so that the D2H of step k
+    // (copy streams) overlaps H2D + kernel of step k + 1 (compute stream)
+    struct HostSlot {
+        float *actions = nullptr, *obs = nullptr, *reward = nullptr, *compact = nullptr;
+        uint8_t* done = nullptr;
+        cudaEvent_t kernel_done = nullptr, copy1_done = nullptr, copy2_done = nullptr;
+        bool busy = false;
+    } slot[2];
+    bool host_ready = false;
+    int host_next = 0, host_inflight = 0;
+    cudaStream_t host_stream = nullptr, copy_stream1 = nullptr, copy_stream2 = nullptr;
+    cudaEvent_t host_order_event = nullptr;
 };
 
 struct PnrDeviceGuard {
@@ -90,6 +102,15 @@ extern "C" void pnr_default_config(pnr_config* c) {
     c->kp = 0.0; c->kd = 0.0; c->torque_scale = 1.0;
     c->n_obstacles = 0;
     c->contact_penalty = 0.0;
+    // per-env random box, off; ranges around the demo box (half extents (0.5, 0.5, 5) at (10, 5, 0), pioneer_knm_env.py:249-255)
+    c->random_box = 0;
+    c->box_pos_lo[0] = 8; c->box_pos_lo[1] = -6; c->box_pos_hi[0] = 14; c->box_pos_hi[1] = 6;
+    c->box_size_lo[0] = 0.3; c->box_size_lo[1] = 0.3; c->box_size_lo[2] = 3.0;
+    c->box_size_hi[0] = 0.7; c->box_size_hi[1] = 0.7; c->box_size_hi[2] = 7.0;
+    // Bullet-like substep, off; Bullet's defaults [UPSTREAM-MEMORY]
+    c->stepping = PNR_STEPPING_EXPLICIT;
+    c->link_damping = 0.04; c->max_velocity = 100.0;
+    c->motor_kp = 0.1; c->motor_kd = 1.0; c->motor_max_force = 0.0;
 }
 
 static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_envs, int64_t env_id_base,
@@ -262,8 +283,20 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
     p.award_done = (float)c.award_done;
     p.max_episode_steps = c.max_episode_steps;
     p.auto_reset = c.auto_reset;
-    p.seed_lo = (uint32_t)seed;
-    p.seed_hi = (uint32_t)(seed >> 32);
+    (void)seed;                                  // the reset key lives in device memory (PnrStats::seed_*)
+    p.random_box = -1;
+    if (c.random_box) {
+        for (int i = 0; i < c.n_obstacles && p.random_box < 0; ++i)
+            if (c.obstacle_type[i] == PNR_OBSTACLE_BOX) p.random_box = i;
+        if (p.random_box < 0) return pnr_fail(PNR_ERR_INVALID, "pnr_config.random_box needs a box among the obstacles");
+        for (int k = 0; k < 2; ++k) { p.box_pos_lo[k] = (float)c.box_pos_lo[k]; p.box_pos_hi[k] = (float)c.box_pos_hi[k]; }
+        for (int k = 0; k < 3; ++k) {
+            p.box_size_lo[k] = (float)c.box_size_lo[k]; p.box_size_hi[k] = (float)c.box_size_hi[k];
+            if (!(c.box_size_lo[k] > 0.0) || !(c.box_size_hi[k] >= c.box_size_lo[k]))
+                return pnr_fail(PNR_ERR_INVALID, "pnr_config.box_size_lo / box_size_hi must be positive and ordered");
+        }
+        if (p.n_obstacles == 0) p.random_box = -1;           // no penalty weight: nothing reads the box
+    }
     p.env_id_base = env_id_base;
     p.n_envs = n_envs;
     return PNR_OK;
@@ -324,6 +357,19 @@ extern "C" int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t
     if ((e = cudaMalloc(&h->state, sizeof(float4) * 6 * (size_t)n_envs)) != cudaSuccess) return bail(e, "cudaMalloc(state)");
     if ((e = cudaMalloc(&h->stats, sizeof(PnrStats))) != cudaSuccess) return bail(e, "cudaMalloc(stats)");
     if ((e = cudaMemset(h->stats, 0, sizeof(PnrStats))) != cudaSuccess) return bail(e, "cudaMemset(stats)");
+    h->params.stats_ro = h->stats;
+    h->seed = seed;
+    {
+        const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+        if ((e = cudaMemcpy(reinterpret_cast<char*>(h->stats) + offsetof(PnrStats, seed_lo), key, sizeof(key),
+                            cudaMemcpyHostToDevice)) != cudaSuccess) return bail(e, "cudaMemcpy(seed)");
+    }
+    if (h->params.random_box >= 0) {
+        if ((e = cudaMalloc(&h->box_a, sizeof(float4) * (size_t)n_envs)) != cudaSuccess) return bail(e, "cudaMalloc(box)");
+        if ((e = cudaMalloc(&h->box_z, sizeof(float) * (size_t)n_envs)) != cudaSuccess) return bail(e, "cudaMalloc(box)");
+        h->params.box_a = h->box_a;
+        h->params.box_z = h->box_z;
+    }
     if ((e = cudaMalloc(&h->stats_out, sizeof(double) * PNR_STATS_LEN)) != cudaSuccess) return bail(e, "cudaMalloc(stats_out)");
     if ((e = cudaMallocHost(&h->stats_host, sizeof(double) * PNR_STATS_LEN)) != cudaSuccess) return bail(e, "cudaMallocHost");
     // clear statistics, then reset every env (reset_world) with tick 0
@@ -340,13 +386,15 @@ extern "C" int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t
 extern "C" void pnr_destroy(pnr_handle* h) {
     if (!h) return;
     PnrDeviceGuard guard(h->device);
-    if (h->host_stream) { cudaStreamSynchronize(h->host_stream); cudaStreamDestroy(h->host_stream); }
-    if (h->host_stream2) { cudaStreamSynchronize(h->host_stream2); cudaStreamDestroy(h->host_stream2); }
-    if (h->host_event) cudaEventDestroy(h->host_event);
+    for (cudaStream_t st : {h->host_stream, h->copy_stream1, h->copy_stream2})
+        if (st) { cudaStreamSynchronize(st); cudaStreamDestroy(st); }
     if (h->host_order_event) cudaEventDestroy(h->host_order_event);
-    cudaFree(h->state); cudaFree(h->stats); cudaFree(h->stats_out);
+    for (auto& sl : h->slot) {
+        for (cudaEvent_t ev : {sl.kernel_done, sl.copy1_done, sl.copy2_done}) if (ev) cudaEventDestroy(ev);
+        cudaFree(sl.actions); cudaFree(sl.obs); cudaFree(sl.reward); cudaFree(sl.compact); cudaFree(sl.done);
+    }
+    cudaFree(h->state); cudaFree(h->stats); cudaFree(h->stats_out); cudaFree(h->box_a); cudaFree(h->box_z);
     cudaFree(h->filt_delta); cudaFree(h->filt_applied); cudaFree(h->filt_state); cudaFree(h->filt_merged);
-    cudaFree(h->h_actions); cudaFree(h->h_obs); cudaFree(h->h_reward); cudaFree(h->h_done);
     if (h->stats_host) cudaFreeHost(h->stats_host);
     delete h;
 }
@@ -375,6 +423,10 @@ extern "C" int pnr_tick_advance(pnr_handle* h, uint32_t n, void* stream) {
 
 extern "C" int pnr_get_counters(const pnr_handle* h, uint32_t* tick, double* env_steps, uint64_t* seed) {
     if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_get_counters: null handle");
+    if (tick || env_steps) {                      // the steps may have run on any stream
+        PnrDeviceGuard guard(h->device);
+        PNR_CUDA(cudaDeviceSynchronize());
+    }
     if (tick) {                                   // host call counter + what graph replays added on the device
         PnrDeviceGuard guard(h->device);
         uint32_t off = 0;
@@ -387,7 +439,7 @@ extern "C" int pnr_get_counters(const pnr_handle* h, uint32_t* tick, double* env
         PNR_CUDA(cudaMemcpy(env_steps, reinterpret_cast<const char*>(h->stats) + offsetof(PnrStats, env_steps),
                             sizeof(double), cudaMemcpyDeviceToHost));
     }
-    if (seed) *seed = ((uint64_t)h->params.seed_hi << 32) | h->params.seed_lo;
+    if (seed) *seed = h->seed;
     return PNR_OK;
 }
 
@@ -405,8 +457,11 @@ extern "C" int pnr_set_counters(pnr_handle* h, uint32_t tick, double env_steps) 
 
 extern "C" int pnr_seed(pnr_handle* h, uint64_t seed) {
     if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_seed: null handle");
-    h->params.seed_lo = (uint32_t)seed;
-    h->params.seed_hi = (uint32_t)(seed >> 32);
+    PnrDeviceGuard guard(h->device);
+    const uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)};
+    PNR_CUDA(cudaDeviceSynchronize());            // steps in flight keep the old key
+    PNR_CUDA(cudaMemcpy(reinterpret_cast<char*>(h->stats) + offsetof(PnrStats, seed_lo), key, sizeof(key), cudaMemcpyHostToDevice));
+    h->seed = seed;
     return PNR_OK;
 }
 
@@ -414,6 +469,8 @@ extern "C" int pnr_reset(pnr_handle* h, const int64_t* idx, int64_t n, const flo
                          float* obs_out, void* stream) {
     if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_reset: null handle");
     if (n < 0 || (!idx && n != h->n_envs)) return pnr_fail(PNR_ERR_INVALID, "pnr_reset: idx == NULL requires n == n_envs");
+    if (reinterpret_cast<uintptr_t>(obs_out) & 15)            // the tile leaves through cp.async.bulk / 16-byte stores
+        return pnr_fail(PNR_ERR_INVALID, "pnr_reset: obs_out must be 16-byte aligned");
     PnrDeviceGuard guard(h->device);
     PNR_CUDA(pnr_launch_reset_observe(h->params, h->device, 0, h->state, idx, n, q0, target, obs_out, h->tick,
                                       (cudaStream_t)stream));
@@ -425,6 +482,8 @@ extern "C" int pnr_reset(pnr_handle* h, const int64_t* idx, int64_t n, const flo
 extern "C" int pnr_observe(pnr_handle* h, const int64_t* idx, int64_t n, float* obs_out, void* stream) {
     if (!h || !obs_out) return pnr_fail(PNR_ERR_INVALID, "pnr_observe: null argument");
     if (n < 0 || (!idx && n != h->n_envs)) return pnr_fail(PNR_ERR_INVALID, "pnr_observe: idx == NULL requires n == n_envs");
+    if (reinterpret_cast<uintptr_t>(obs_out) & 15)
+        return pnr_fail(PNR_ERR_INVALID, "pnr_observe: obs_out must be 16-byte aligned");
     PnrDeviceGuard guard(h->device);
     PNR_CUDA(pnr_launch_reset_observe(h->params, h->device, 1, h->state, idx, n, nullptr, nullptr, obs_out, h->tick,
                                       (cudaStream_t)stream));
@@ -437,14 +496,24 @@ extern "C" int pnr_step(pnr_handle* h, const float* actions, float* obs, float* 
     if ((reinterpret_cast<uintptr_t>(obs) & 15) || (reinterpret_cast<uintptr_t>(actions) & 7))
         return pnr_fail(PNR_ERR_INVALID, "pnr_step: obs must be 16-byte and actions 8-byte aligned");
     PnrDeviceGuard guard(h->device);
+    // a launch that is being captured into a CUDA graph draws its reset keys from that graph's own domain (see the header)
+    uint32_t domain = 0;
+    {
+        cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+        unsigned long long id = 0;
+        if (stream && cudaStreamGetCaptureInfo((cudaStream_t)stream, &cs, &id) == cudaSuccess && cs == cudaStreamCaptureStatusActive) {
+            if (h->n_graphs == 0 || id != h->capture_id) { h->n_graphs += 1; h->capture_id = id; }
+            domain = h->n_graphs;
+        }
+    }
     if (h->cfg.mode == PNR_MODE_DYNAMIC)
         PNR_CUDA(pnr_launch_step_dynamic(h->params, h->device, h->cfg.obs_mode, h->state, actions, obs, reward, done,
-                                         h->stats, h->tick, h->filt_fused ? h->filt_applied : nullptr,
+                                         h->stats, h->tick, domain, h->filt_fused ? h->filt_applied : nullptr,
                                          (h->filt_fused && h->filt_fused_update) ? h->filt_delta : nullptr,
                                          (float)h->filt_clip, (cudaStream_t)stream));
     else
         PNR_CUDA(pnr_launch_step(h->params, h->device, h->cfg.arith, h->cfg.obs_mode, h->state, actions, obs, reward, done,
-                                 h->stats, h->tick, h->filt_fused ? h->filt_applied : nullptr,
+                                 h->stats, h->tick, domain, h->filt_fused ? h->filt_applied : nullptr,
                                  (h->filt_fused && h->filt_fused_update) ? h->filt_delta : nullptr, (float)h->filt_clip,
                                  (cudaStream_t)stream));
     h->tick += 1;
@@ -452,54 +521,140 @@ extern "C" int pnr_step(pnr_handle* h, const float* actions, float* obs, float* 
     return PNR_OK;
 }
 
-extern "C" int pnr_step_host(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done) {
-    if (!h || !actions || !obs || !reward || !done) return pnr_fail(PNR_ERR_INVALID, "pnr_step_host: null argument");
+extern "C" int pnr_observe_done(pnr_handle* h, const uint8_t* done, float* obs, float* terminal_obs, void* stream) {
+    if (!h || !done || !obs) return pnr_fail(PNR_ERR_INVALID, "pnr_observe_done: null argument");
     PnrDeviceGuard guard(h->device);
+    const bool fused = h->filt_fused != 0;
+    PNR_CUDA(pnr_launch_observe_done(h->params, h->state, done, obs, terminal_obs, fused ? h->filt_applied : nullptr,
+                                     (fused && h->filt_fused_update) ? h->filt_delta : nullptr, (float)h->filt_clip,
+                                     (cudaStream_t)stream));
+    h->launches += 1;
+    return PNR_OK;
+}
+
+static int pnr_host_setup(pnr_handle* h) {
+    if (h->host_ready) return PNR_OK;
     const size_t n = (size_t)h->n_envs;
-    if (!h->h_done) {                                           // first call: streams + device staging, all or nothing
-        auto setup = [&]() -> cudaError_t {
-            cudaError_t e;
-            if (!h->host_stream && (e = cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
-            if (!h->host_order_event && (e = cudaEventCreateWithFlags(&h->host_order_event, cudaEventDisableTiming)) != cudaSuccess) return e;
-            if (!getenv("PNR_HOST_ONE_STREAM")) {               // developer knob: single-stream copies
-                if (!h->host_stream2 && (e = cudaStreamCreateWithFlags(&h->host_stream2, cudaStreamNonBlocking)) != cudaSuccess) return e;
-                if (!h->host_event && (e = cudaEventCreateWithFlags(&h->host_event, cudaEventDisableTiming)) != cudaSuccess) return e;
-            }
-            if (!h->h_actions && (e = cudaMalloc(&h->h_actions, n * PNR_DOF * sizeof(float))) != cudaSuccess) return e;
-            if (!h->h_obs && (e = cudaMalloc(&h->h_obs, n * PNR_OBS_DIM * sizeof(float))) != cudaSuccess) return e;
-            if (!h->h_reward && (e = cudaMalloc(&h->h_reward, n * sizeof(float))) != cudaSuccess) return e;
-            return cudaMalloc(&h->h_done, n);                   // last: its presence marks the set-up as complete
-        };
-        const cudaError_t e = setup();
-        if (e != cudaSuccess)                                   // what was allocated is kept for the retry / freed by pnr_destroy
-            return pnr_fail(e == cudaErrorMemoryAllocation ? PNR_ERR_ALLOC : PNR_ERR_CUDA,
-                            std::string("pnr_step_host: staging set-up: ") + cudaGetErrorString(e));
+    auto setup = [&]() -> cudaError_t {                           // all or nothing; what was allocated is kept for the retry
+        cudaError_t e;
+        if (!h->host_stream && (e = cudaStreamCreateWithFlags(&h->host_stream, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if (!h->copy_stream1 && (e = cudaStreamCreateWithFlags(&h->copy_stream1, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if (!getenv("PNR_HOST_ONE_STREAM") && !h->copy_stream2 &&  // developer knob: one copy engine for the observations
+            (e = cudaStreamCreateWithFlags(&h->copy_stream2, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        if (!h->host_order_event && (e = cudaEventCreateWithFlags(&h->host_order_event, cudaEventDisableTiming)) != cudaSuccess) return e;
+        for (auto& sl : h->slot) {
+            for (cudaEvent_t* ev : {&sl.kernel_done, &sl.copy1_done, &sl.copy2_done})
+                if (!*ev && (e = cudaEventCreateWithFlags(ev, cudaEventDisableTiming)) != cudaSuccess) return e;
+            if (!sl.actions && (e = cudaMalloc(&sl.actions, n * PNR_DOF * sizeof(float))) != cudaSuccess) return e;
+            if (!sl.obs && (e = cudaMalloc(&sl.obs, n * PNR_OBS_DIM * sizeof(float))) != cudaSuccess) return e;
+            if (!sl.reward && (e = cudaMalloc(&sl.reward, n * sizeof(float))) != cudaSuccess) return e;
+            if (!sl.done && (e = cudaMalloc(&sl.done, n)) != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    };
+    const cudaError_t e = setup();
+    if (e != cudaSuccess)
+        return pnr_fail(e == cudaErrorMemoryAllocation ? PNR_ERR_ALLOC : PNR_ERR_CUDA,
+                        std::string("pnr_step_host: staging set-up: ") + cudaGetErrorString(e));
+    h->host_ready = true;
+    return PNR_OK;
+}
+
+extern "C" int pnr_step_host_begin(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, int layout) {
+    if (!h || !actions || !obs || !reward || !done) return pnr_fail(PNR_ERR_INVALID, "pnr_step_host_begin: null argument");
+    if (layout != PNR_HOST_FULL && layout != PNR_HOST_COMPACT) return pnr_fail(PNR_ERR_INVALID, "pnr_step_host_begin: unknown layout");
+    PnrDeviceGuard guard(h->device);
+    int rc = pnr_host_setup(h);
+    if (rc != PNR_OK) return rc;
+    pnr_handle::HostSlot& sl = h->slot[h->host_next];
+    if (sl.busy) return pnr_fail(PNR_ERR_INVALID, "pnr_step_host_begin: two steps are already in flight; call pnr_step_host_end");
+    const size_t n = (size_t)h->n_envs;
+    const int width = layout == PNR_HOST_COMPACT ? PNR_OBS_COMPACT_DIM : PNR_OBS_DIM;
+    if (layout == PNR_HOST_COMPACT && !sl.compact) {
+        cudaError_t e = cudaMalloc(&sl.compact, n * PNR_OBS_COMPACT_DIM * sizeof(float));
+        if (e != cudaSuccess) return pnr_fail(PNR_ERR_ALLOC, std::string("pnr_step_host_begin: ") + cudaGetErrorString(e));
     }
     cudaStream_t s = h->host_stream;
-    // the library's own (non-blocking) stream: order it after whatever the caller queued on the default stream (a reset,
+    // the library's own (non-blocking) streams: order them after whatever the caller queued on the default stream (a reset,
     // a set_state, a previous pnr_step); work on other non-blocking streams is the caller's to synchronise
-    PNR_CUDA(cudaEventRecord(h->host_order_event, nullptr));
-    PNR_CUDA(cudaStreamWaitEvent(s, h->host_order_event, 0));
-    PNR_CUDA(cudaMemcpyAsync(h->h_actions, actions, n * PNR_DOF * sizeof(float), cudaMemcpyHostToDevice, s));
-    int rc = pnr_step(h, h->h_actions, h->h_obs, h->h_reward, h->h_done, s);
-    if (rc != PNR_OK) return rc;
-    // The 548 B/env observation copy is what bounds this call (PCIe).  Two copy engines working on the two halves
-    // keep the link fuller than one; reward / done ride on the first stream.
-    const size_t half = (n / 2) * PNR_OBS_DIM;
-    const size_t total = n * PNR_OBS_DIM;
-    if (h->host_stream2 && half > 0) {
-        PNR_CUDA(cudaEventRecord(h->host_event, s));
-        PNR_CUDA(cudaStreamWaitEvent(h->host_stream2, h->host_event, 0));
-        PNR_CUDA(cudaMemcpyAsync(obs + half, h->h_obs + half, (total - half) * sizeof(float), cudaMemcpyDeviceToHost,
-                                 h->host_stream2));
-        PNR_CUDA(cudaMemcpyAsync(obs, h->h_obs, half * sizeof(float), cudaMemcpyDeviceToHost, s));
-    } else {
-        PNR_CUDA(cudaMemcpyAsync(obs, h->h_obs, total * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (h->host_inflight == 0) {
+        PNR_CUDA(cudaEventRecord(h->host_order_event, nullptr));
+        PNR_CUDA(cudaStreamWaitEvent(s, h->host_order_event, 0));
     }
-    PNR_CUDA(cudaMemcpyAsync(reward, h->h_reward, n * sizeof(float), cudaMemcpyDeviceToHost, s));
-    PNR_CUDA(cudaMemcpyAsync(done, h->h_done, n, cudaMemcpyDeviceToHost, s));
-    if (h->host_stream2) PNR_CUDA(cudaStreamSynchronize(h->host_stream2));
-    PNR_CUDA(cudaStreamSynchronize(s));
+    PNR_CUDA(cudaMemcpyAsync(sl.actions, actions, n * PNR_DOF * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = pnr_step(h, sl.actions, sl.obs, sl.reward, sl.done, s);
+    if (rc != PNR_OK) return rc;
+    const float* src = sl.obs;
+    if (layout == PNR_HOST_COMPACT) {
+        PNR_CUDA(pnr_launch_compact_obs(sl.obs, sl.compact, h->n_envs, s));
+        h->launches += 1;
+        src = sl.compact;
+    }
+    PNR_CUDA(cudaEventRecord(sl.kernel_done, s));
+    // The observation copy is what bounds this call (PCIe).  Two copy engines working on the two halves keep the link
+    // fuller than one; reward / done ride on the first stream.
+    const size_t total = n * (size_t)width;
+    const size_t half = h->copy_stream2 ? (n / 2) * (size_t)width : total;
+    PNR_CUDA(cudaStreamWaitEvent(h->copy_stream1, sl.kernel_done, 0));
+    if (half < total) {
+        PNR_CUDA(cudaStreamWaitEvent(h->copy_stream2, sl.kernel_done, 0));
+        PNR_CUDA(cudaMemcpyAsync(obs + half, src + half, (total - half) * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream2));
+        PNR_CUDA(cudaEventRecord(sl.copy2_done, h->copy_stream2));
+    }
+    if (half > 0) PNR_CUDA(cudaMemcpyAsync(obs, src, half * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream1));
+    PNR_CUDA(cudaMemcpyAsync(reward, sl.reward, n * sizeof(float), cudaMemcpyDeviceToHost, h->copy_stream1));
+    PNR_CUDA(cudaMemcpyAsync(done, sl.done, n, cudaMemcpyDeviceToHost, h->copy_stream1));
+    PNR_CUDA(cudaEventRecord(sl.copy1_done, h->copy_stream1));
+    if (half >= total) PNR_CUDA(cudaEventRecord(sl.copy2_done, h->copy_stream1));
+    sl.busy = true;
+    h->host_next ^= 1;
+    h->host_inflight += 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_step_host_end(pnr_handle* h) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_step_host_end: null handle");
+    if (h->host_inflight == 0) return pnr_fail(PNR_ERR_INVALID, "pnr_step_host_end: no step in flight");
+    PnrDeviceGuard guard(h->device);
+    pnr_handle::HostSlot& sl = h->slot[h->host_inflight == 2 ? h->host_next : (h->host_next ^ 1)];   // the oldest one
+    PNR_CUDA(cudaEventSynchronize(sl.copy1_done));
+    PNR_CUDA(cudaEventSynchronize(sl.copy2_done));
+    sl.busy = false;
+    h->host_inflight -= 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_step_host(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done) {
+    if (!h) return pnr_fail(PNR_ERR_INVALID, "pnr_step_host: null argument");
+    while (h->host_inflight > 0) {                                  // results of asynchronous steps land first
+        int rc = pnr_step_host_end(h);
+        if (rc != PNR_OK) return rc;
+    }
+    int rc = pnr_step_host_begin(h, actions, obs, reward, done, PNR_HOST_FULL);
+    return rc != PNR_OK ? rc : pnr_step_host_end(h);
+}
+
+extern "C" int pnr_get_obs_constants(const pnr_handle* h, float* out36) {
+    if (!h || !out36) return pnr_fail(PNR_ERR_INVALID, "pnr_get_obs_constants: null argument");
+    const PnrParams& p = h->params;
+    for (int j = 0; j < PNR_DOF; ++j) {                             // pnr_pack_obs_const
+        out36[j] = p.r_lo[j];       out36[6 + j] = p.cos_r_lo[j];   out36[12 + j] = p.sin_r_lo[j];
+        out36[18 + j] = p.r_hi[j];  out36[24 + j] = p.cos_r_hi[j];  out36[30 + j] = p.sin_r_hi[j];
+    }
+    return PNR_OK;
+}
+
+extern "C" int pnr_expand_obs_host(const pnr_handle* h, const float* compact, float* full, int64_t n_rows) {
+    if (!h || !compact || !full || n_rows < 0) return pnr_fail(PNR_ERR_INVALID, "pnr_expand_obs_host: bad argument");
+    float c36[PNR_OBS_CONST_END - PNR_OBS_CONST_BEGIN];
+    pnr_get_obs_constants(h, c36);
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const float* src = compact + r * PNR_OBS_COMPACT_DIM;
+        float* dst = full + r * PNR_OBS_DIM;
+        std::memcpy(dst, src, PNR_OBS_CONST_BEGIN * sizeof(float));
+        std::memcpy(dst + PNR_OBS_CONST_BEGIN, c36, sizeof(c36));
+        std::memcpy(dst + PNR_OBS_CONST_END, src + PNR_OBS_CONST_BEGIN, (PNR_OBS_DIM - PNR_OBS_CONST_END) * sizeof(float));
+    }
     return PNR_OK;
 }
 
@@ -520,6 +675,38 @@ extern "C" int pnr_set_state(pnr_handle* h, const float* r, const float* v, cons
                                  const_cast<float*>(a), const_cast<float*>(potential), const_cast<float*>(target),
                                  const_cast<int32_t*>(t), const_cast<float*>(ep_return), (cudaStream_t)stream));
     h->launches += 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_get_boxes(pnr_handle* h, float* box, void* stream) {
+    if (!h || !box) return pnr_fail(PNR_ERR_INVALID, "pnr_get_boxes: null argument");
+    if (!h->box_a) return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_get_boxes: the handle was created without cfg.random_box");
+    PnrDeviceGuard guard(h->device);
+    PNR_CUDA(pnr_launch_box_io(false, h->box_a, h->box_z, h->n_envs, box, (cudaStream_t)stream));
+    h->launches += 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_set_boxes(pnr_handle* h, const float* box, void* stream) {
+    if (!h || !box) return pnr_fail(PNR_ERR_INVALID, "pnr_set_boxes: null argument");
+    if (!h->box_a) return pnr_fail(PNR_ERR_UNSUPPORTED, "pnr_set_boxes: the handle was created without cfg.random_box");
+    PnrDeviceGuard guard(h->device);
+    PNR_CUDA(pnr_launch_box_io(true, h->box_a, h->box_z, h->n_envs, const_cast<float*>(box), (cudaStream_t)stream));
+    h->launches += 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_set_stats(pnr_handle* h, const double* in8) {
+    if (!h || !in8) return pnr_fail(PNR_ERR_INVALID, "pnr_set_stats: null argument");
+    PnrDeviceGuard guard(h->device);
+    PNR_CUDA(cudaDeviceSynchronize());
+    PnrStats st;
+    PNR_CUDA(cudaMemcpy(&st, h->stats, sizeof(st), cudaMemcpyDeviceToHost));
+    st.episodes = in8[0]; st.sum_return = in8[1]; st.sum_length = in8[2]; st.sum_return_sq = in8[3];
+    st.max_return_ord = pnr_float_to_ordered((float)in8[4]);
+    st.min_return_ord = pnr_float_to_ordered((float)in8[5]);
+    st.env_steps = in8[6]; st.reached = in8[7];
+    PNR_CUDA(cudaMemcpy(h->stats, &st, sizeof(st), cudaMemcpyHostToDevice));
     return PNR_OK;
 }
 
@@ -606,6 +793,8 @@ extern "C" int pnr_filter_apply(pnr_handle* h, const float* obs_in, float* obs_o
 
 extern "C" int pnr_filter_delta_device(pnr_handle* h, double* out_device, void* stream) {
     if (!h || !out_device) return pnr_fail(PNR_ERR_INVALID, "pnr_filter_delta_device: null argument");
+    if (reinterpret_cast<uintptr_t>(out_device) & 7)
+        return pnr_fail(PNR_ERR_INVALID, "pnr_filter_delta_device: out_device must be 8-byte aligned");
     PnrDeviceGuard guard(h->device);
     int rc = pnr_filter_ensure(h, (cudaStream_t)stream);
     if (rc != PNR_OK) return rc;

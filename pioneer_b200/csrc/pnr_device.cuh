@@ -62,7 +62,13 @@ struct PnrParams {
     int32_t obstacle_type[PNR_MAX_OBSTACLES];
     float obstacle_p[PNR_MAX_OBSTACLES][3], obstacle_e[PNR_MAX_OBSTACLES][3];
     float contact_penalty;
-    uint32_t seed_lo, seed_hi;
+    // per-env random box (pioneer/temp/pioneer_env.py:169-192): obstacle `random_box` (-1: none) is redrawn at every reset;
+    // centre x y | half extents x y live in box_a[env], the half height (= centre z: the box stands on z = 0) in box_z[env]
+    int32_t random_box;
+    float box_pos_lo[2], box_pos_hi[2], box_size_lo[3], box_size_hi[3];
+    float4* box_a;
+    float* box_z;
+    const struct PnrStats* stats_ro;   // the handle's PnrStats (reset key: seed, device-side tick advance), for the rare reset paths
     int64_t env_id_base;
     int64_t n_envs;
 };
@@ -89,14 +95,20 @@ __device__ __forceinline__ float pnr_uniform(float lo, float hi, float u) {
     return __fadd_rn(lo, __fmul_rn(__fsub_rn(hi, lo), u));
 }
 
-// 6 joint positions then 3 target coordinates (reference draw order, pioneer_knm_env.py:80-90),
-// counter = (global env id lo, hi, tick, block), key = seed
-__device__ __forceinline__ void pnr_reset_draws(const PnrParams& p, int64_t global_env, uint32_t tick,
-                                                float (&q)[PNR_DOF], float (&tgt)[3]) {
-    const uint32_t g0 = (uint32_t)global_env, g1 = (uint32_t)((uint64_t)global_env >> 32);
-    const uint4 b0 = pnr_philox4x32_10(make_uint4(g0, g1, tick, 0u), p.seed_lo, p.seed_hi);
-    const uint4 b1 = pnr_philox4x32_10(make_uint4(g0, g1, tick, 1u), p.seed_lo, p.seed_hi);
-    const uint4 b2 = pnr_philox4x32_10(make_uint4(g0, g1, tick, 2u), p.seed_lo, p.seed_hi);
+// Reset key.  The Philox key is the seed, which lives in DEVICE memory (PnrStats::seed_*; pnr_seed reaches kernels that are
+// already captured in a CUDA graph); the counter is (global env id lo, hi, tick, block | domain << 8).  `tick` is the host's
+// call counter for eager launches (domain 0); launches captured into CUDA graph number g (domain g >= 1) add the device-side
+// offset that pnr_tick_advance bumps once per replay, so no (domain, tick) pair is ever used twice.
+struct PnrResetKey { uint32_t seed_lo, seed_hi, tick, domain; };
+
+// 6 joint positions then 3 target coordinates (reference draw order, pioneer_knm_env.py:80-90), then the per-env box of the
+// obstacle variant: 3 half extents, 2 centre coordinates (draw order of pioneer/temp/pioneer_env.py:173-174)
+__device__ __forceinline__ void pnr_reset_draws(const PnrParams& p, int64_t global_env, PnrResetKey k,
+                                                float (&q)[PNR_DOF], float (&tgt)[3], float (&box)[5]) {
+    const uint32_t g0 = (uint32_t)global_env, g1 = (uint32_t)((uint64_t)global_env >> 32), dom = k.domain << 8;
+    const uint4 b0 = pnr_philox4x32_10(make_uint4(g0, g1, k.tick, dom | 0u), k.seed_lo, k.seed_hi);
+    const uint4 b1 = pnr_philox4x32_10(make_uint4(g0, g1, k.tick, dom | 1u), k.seed_lo, k.seed_hi);
+    const uint4 b2 = pnr_philox4x32_10(make_uint4(g0, g1, k.tick, dom | 2u), k.seed_lo, k.seed_hi);
     q[0] = pnr_uniform(p.r_lo[0], p.r_hi[0], pnr_u01(b0.x));
     q[1] = pnr_uniform(p.r_lo[1], p.r_hi[1], pnr_u01(b0.y));
     q[2] = pnr_uniform(p.r_lo[2], p.r_hi[2], pnr_u01(b0.z));
@@ -106,6 +118,20 @@ __device__ __forceinline__ void pnr_reset_draws(const PnrParams& p, int64_t glob
     tgt[0] = pnr_uniform(p.target_lo[0], p.target_hi[0], pnr_u01(b1.z));
     tgt[1] = pnr_uniform(p.target_lo[1], p.target_hi[1], pnr_u01(b1.w));
     tgt[2] = pnr_uniform(p.target_lo[2], p.target_hi[2], pnr_u01(b2.x));
+    if (p.random_box >= 0) {                                  // warp-uniform (constant bank)
+        const uint4 b3 = pnr_philox4x32_10(make_uint4(g0, g1, k.tick, dom | 3u), k.seed_lo, k.seed_hi);
+        box[2] = pnr_uniform(p.box_size_lo[0], p.box_size_hi[0], pnr_u01(b2.y));     // half extents x y z
+        box[3] = pnr_uniform(p.box_size_lo[1], p.box_size_hi[1], pnr_u01(b2.z));
+        box[4] = pnr_uniform(p.box_size_lo[2], p.box_size_hi[2], pnr_u01(b2.w));
+        box[0] = pnr_uniform(p.box_pos_lo[0], p.box_pos_hi[0], pnr_u01(b3.x));       // centre x y (z = half height)
+        box[1] = pnr_uniform(p.box_pos_lo[1], p.box_pos_hi[1], pnr_u01(b3.y));
+    }
+}
+__device__ __forceinline__ void pnr_store_box(const PnrParams& p, int64_t env, const float (&box)[5]) {
+    if (p.random_box >= 0) {
+        p.box_a[env] = make_float4(box[0], box[1], box[2], box[3]);
+        p.box_z[env] = box[4];
+    }
 }
 
 // np.clip for scalars: NaN propagates (comparisons are false)
@@ -186,4 +212,15 @@ struct PnrStats {
     // is a kernel argument and therefore FROZEN into a captured CUDA graph; pnr_tick_advance bumps this one from inside
     // the graph, so every replay draws fresh reset states.  0 unless pnr_tick_advance is used.
     uint32_t tick_offset;
+    uint32_t seed_lo, seed_hi;      // the reset generator's key (pnr_create / pnr_seed)
 };
+// tickdom = domain << 32 | host call counter: ONE 64-bit argument for the rare, non-inlined reset paths
+__device__ __forceinline__ PnrResetKey pnr_reset_key(const PnrParams& p, uint64_t tickdom) {
+    const PnrStats* __restrict__ stats = p.stats_ro;
+    PnrResetKey k;
+    k.domain = (uint32_t)(tickdom >> 32);
+    k.seed_lo = stats->seed_lo; k.seed_hi = stats->seed_hi;
+    k.tick = k.domain ? (uint32_t)tickdom + stats->tick_offset : (uint32_t)tickdom;
+    return k;
+}
+__device__ __forceinline__ uint64_t pnr_tickdom(uint32_t tick, uint32_t domain) { return ((uint64_t)domain << 32) | tick; }

@@ -18,7 +18,7 @@ template <int OBS_MODE, bool OBSTACLES, int CHAIN>
 __global__ void __launch_bounds__(PNR_STEP_THREADS, PNR_DYN_MIN_CTAS)
 pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                         float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
-                        PnrStats* __restrict__ stats, uint32_t tick, const float* __restrict__ f_applied,
+                        PnrStats* __restrict__ stats, uint32_t tick, uint32_t domain, const float* __restrict__ f_applied,
                         double* __restrict__ f_delta, float f_clip) {
     extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -62,7 +62,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
             PnrSinCos sc;
 #pragma unroll
             for (int i = 0; i < PNR_DOF; ++i) { sc.sn[i] = o.sn[i]; sc.cs[i] = o.cs[i]; }
-            rew = __fsub_rn(rew, __fmul_rn(p.contact_penalty, pnr_contact_depth(p, sc)));
+            rew = __fsub_rn(rew, __fmul_rn(p.contact_penalty, pnr_contact_depth(p, sc, pnr_load_box(p, env))));
         }
         s.pot = pot_new;
         s.t += 1;
@@ -84,9 +84,10 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         const bool do_reset = is_done && (p.auto_reset != 0);
         if (OBS_MODE == PNR_OBS_TERMINAL) pnr_pack_obs_dyn<true>(p, row, s, o, s.pot, slow);
         if (do_reset) {
-            float q[PNR_DOF], tg[3];
-            pnr_reset_draws(p, p.env_id_base + env, tick + stats->tick_offset, q, tg);
+            float q[PNR_DOF], tg[3], box[5];
+            pnr_reset_draws(p, p.env_id_base + env, pnr_reset_key(p, pnr_tickdom(tick, domain)), q, tg, box);
             pnr_reset_env(s, q, tg);
+            if (active) pnr_store_box(p, env, box);
         }
         if (OBS_MODE == PNR_OBS_AUTORESET) {
             if (__any_sync(PNR_FULL_MASK, do_reset)) {
@@ -160,10 +161,10 @@ static int pnr_dyn_resident(const void* fn) {
 }
 
 cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode, float4* state, const float* actions,
-                                    float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick,
+                                    float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain,
                                     const float* f_applied, double* f_delta, float f_clip, cudaStream_t stream) {
-    typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, const float*,
-                         double*, float);
+    typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, uint32_t,
+                         const float*, double*, float);
 #define PNR_DYN_ROW(CH) \
     {{pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, false, CH>, pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, true, CH>}, \
      {pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, false, CH>, pnr_step_dynamic_kernel<PNR_OBS_AUTORESET, true, CH>}}
@@ -184,7 +185,7 @@ cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode
     int64_t grid = (p.n_envs + per_cta - 1) / per_cta;
     if (grid > resident) grid = resident;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, PNR_STEP_THREADS, PNR_RO_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick, f_applied,
-                                                                        f_delta, f_clip);
+    kern<<<(unsigned)grid, PNR_STEP_THREADS, PNR_RO_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick, domain,
+                                                                        f_applied, f_delta, f_clip);
     return cudaGetLastError();
 }

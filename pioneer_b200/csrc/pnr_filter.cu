@@ -1,5 +1,5 @@
-// N2: fused observation normaliser (the MeanStdFilter the reference launcher configures for its rollout workers,
-// pioneer/launch/pioneer_knm_train.py:66 'observation_filter': 'MeanStdFilter').  ONE streaming pass over the
+// N2: fused observation normaliser (the ConcurrentMeanStdFilter -- RLlib's MeanStdFilter behind a lock -- the reference launcher configures for its rollout workers,
+// pioneer/launch/pioneer_knm_train.py:66 'observation_filter': 'ConcurrentMeanStdFilter').  ONE streaming pass over the
 // observation batch does what the host-side filter does in three (push statistics, demean, scale): a CTA pulls a
 // tile of 32 rows into shared memory with a TMA bulk load, every thread owns one of the 137 columns -- accumulates
 // sum and sum of squares of (x - applied_mean) over the tile's rows, rewrites the column as
@@ -136,6 +136,11 @@ __global__ void pnr_filter_fold_kernel(double* __restrict__ slots) {
 // mean^2 (RLlib, restated in oracle/filter_oracle.py)
 __device__ __forceinline__ void pnr_filter_refresh_column(double count, double mean, double m2, float* applied, int c,
                                                           int demean, int destd) {
+    if (!(count > 0.0)) {           // nothing pushed yet: identity (an RLlib filter that has seen no sample never normalises)
+        applied[c] = 0.f;
+        applied[PNR_OBS_DIM + c] = 1.f;
+        return;
+    }
     const double var = count > 1.0 ? m2 / (count - 1.0) : mean * mean;
     applied[c] = demean ? (float)mean : 0.f;
     applied[PNR_OBS_DIM + c] = destd ? (float)(1.0 / (sqrt(var) + 1e-8)) : 1.f;

@@ -27,14 +27,15 @@
 // PNR_OBS_AUTORESET mode the env's observation row is replaced by the first observation of the new episode.
 // Rare (once per episode), so deliberately not inlined: keeps registers and code out of the hot loop.
 template <int OBS_MODE>
-__device__ __noinline__ void pnr_auto_reset(const PnrParams& p, float4* __restrict__ state, int64_t env, uint32_t tick,
+__device__ __noinline__ void pnr_auto_reset(const PnrParams& p, float4* __restrict__ state, int64_t env, uint64_t tickdom,
                                             float* __restrict__ row) {
     const int64_t N = p.n_envs;
     PnrEnv s;
-    float q[PNR_DOF], tg[3];
-    pnr_reset_draws(p, p.env_id_base + env, tick, q, tg);
+    float q[PNR_DOF], tg[3], box[5];
+    pnr_reset_draws(p, p.env_id_base + env, pnr_reset_key(p, tickdom), q, tg, box);
     pnr_reset_env(s, q, tg);
     pnr_store_env(state, N, env, s);
+    pnr_store_box(p, env, box);
     if (OBS_MODE == PNR_OBS_AUTORESET) {
         PnrPose o;
         pnr_pose<true>(p, s, o);                              // fresh joint angles lie inside the limits
@@ -65,7 +66,7 @@ extern "C" int pnr_debug_trace(unsigned long long* out_host) {
 #define PNR_TRACE_NEXT()
 #endif
 
-// FILTER = true fuses the observation normaliser (pnr_filter.cu, 'MeanStdFilter') into the step: what leaves the
+// FILTER = true fuses the observation normaliser (pnr_filter.cu, 'ConcurrentMeanStdFilter') into the step: what leaves the
 // kernel is clip((x - mean) * inv_std), and the column statistics of the raw values go to the same float64 accumulator
 // pnr_filter_apply feeds, so the 548 B/env observation is never re-read.  Every warp normalises the columns it owns
 // while the tile is still in shared memory: a joint warp runs one column pass (lane = one of its 30 changing
@@ -77,7 +78,7 @@ template <int ARITH, int OBS_MODE, bool OBSTACLES, bool FILTER>
 __global__ void __launch_bounds__(PNR_STEP_THREADS, FILTER ? PNR_STEP_MIN_CTAS_FILTER : PNR_STEP_MIN_CTAS)
 pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
-                PnrStats* __restrict__ stats, uint32_t tick, const float* __restrict__ f_applied,
+                PnrStats* __restrict__ stats, uint32_t tick, uint32_t domain, const float* __restrict__ f_applied,
                 double* __restrict__ f_delta, float f_clip) {
     extern __shared__ __align__(128) float tiles[];           // PNR_STEP_BUFS tiles: the bulk store of one drains
     const int lane = threadIdx.x & 31;                        // while the next is being filled
@@ -260,7 +261,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                 PnrSinCos sc;
 #pragma unroll
                 for (int i = 0; i < PNR_DOF; ++i) { sc.sn[i] = o.sn[i]; sc.cs[i] = o.cs[i]; }
-                rew = __fsub_rn(rew, __fmul_rn(p.contact_penalty, pnr_contact_depth(p, sc)));
+                rew = __fsub_rn(rew, __fmul_rn(p.contact_penalty, pnr_contact_depth(p, sc, pnr_load_box(p, env))));
             }
             t += 1;
             ep_ret = __fadd_rn(ep_ret, rew);
@@ -303,7 +304,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
 
         if (part == 3) {
             if (__any_sync(PNR_FULL_MASK, do_reset)) {         // rare: auto-reset (reset_world, :76-105)
-                if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, tick + stats->tick_offset, row);
+                if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick, domain), row);
                 pnr_fence_async_smem();
                 __syncwarp();
             }
@@ -395,15 +396,15 @@ pnr_reset_observe_kernel(const __grid_constant__ PnrParams p, float4* __restrict
         const int64_t env = idx ? idx[k] : k;
         PnrEnv s;
         if (MODE == 0) {
-            float q[PNR_DOF], tg[3];
-            pnr_reset_draws(p, p.env_id_base + env, tick, q, tg);
+            float q[PNR_DOF], tg[3], box[5];
+            pnr_reset_draws(p, p.env_id_base + env, pnr_reset_key(p, pnr_tickdom(tick, 0u)), q, tg, box);
             if (q0) {
 #pragma unroll
                 for (int i = 0; i < PNR_DOF; ++i) q[i] = q0[k * PNR_DOF + i];
             }
             if (target) { tg[0] = target[k * 3 + 0]; tg[1] = target[k * 3 + 1]; tg[2] = target[k * 3 + 2]; }
             pnr_reset_env(s, q, tg);
-            if (active) pnr_store_env(state, N, env, s);
+            if (active) { pnr_store_env(state, N, env, s); pnr_store_box(p, env, box); }
         } else {
             pnr_load_env(state, N, env, s);
         }
@@ -423,6 +424,58 @@ pnr_reset_observe_kernel(const __grid_constant__ PnrParams p, float4* __restrict
         }
     }
     if (lane == 0) pnr_bulk_wait_read<0>();
+}
+
+// ---------------------------------------------------------------------------------------------
+// RLlib's reset_at(i) after a done (the sampler feeds the policy the RESET observation, bullet_env.py:187-190): for every
+// env whose done flag is set -- pnr_step has already reset it -- optionally save the terminal row, then overwrite the row with
+// the first observation of the new episode, normalised / pushed into the statistics like the step kernel's output when the
+// filter is fused.  Rare rows, thread per env, scalar global stores; fixed launch shape, so it can live in a CUDA graph.
+// ---------------------------------------------------------------------------------------------
+__global__ void pnr_observe_done_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
+                                        const uint8_t* __restrict__ done, float* __restrict__ obs,
+                                        float* __restrict__ terminal_out, const float* __restrict__ f_applied,
+                                        double* __restrict__ f_delta, float f_clip) {
+    const int64_t N = p.n_envs;
+    for (int64_t env = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; env < N; env += (int64_t)gridDim.x * blockDim.x) {
+        if (!(done[env] & PNR_DONE)) continue;
+        float* row = obs + env * PNR_OBS_DIM;
+        if (terminal_out) {
+            float* dst = terminal_out + env * PNR_OBS_DIM;
+            for (int c = 0; c < PNR_OBS_DIM; ++c) dst[c] = row[c];
+        }
+        PnrEnv s;
+        pnr_load_env(state, N, env, s);
+        PnrPose o;
+        pnr_pose<false>(p, s, o);
+        bool within;
+        if (fabsf(o.dist - p.done_distance) < p.done_band) pnr_fk_tip_f64(p, s.r, s.tgt, o.ptr, o.dist, within);
+        pnr_pack_obs_const(p, row);
+        pnr_pack_obs_dyn<false>(p, row, s, o, s.pot);
+        if (f_applied) {
+            double* slot = f_delta ? f_delta + (size_t)(env & (PNR_FILTER_SLOTS - 1)) * PNR_FILTER_DELTA_LEN : nullptr;
+            for (int c = 0; c < PNR_OBS_DIM; ++c) {
+                const float d = row[c] - f_applied[c];
+                if (slot) {
+                    atomicAdd(&slot[1 + c], (double)d);
+                    atomicAdd(&slot[1 + PNR_OBS_DIM + c], (double)d * (double)d);
+                }
+                row[c] = fminf(fmaxf(d * f_applied[PNR_OBS_DIM + c], -f_clip), f_clip);
+            }
+            if (slot) atomicAdd(&slot[0], 1.0);
+        }
+    }
+}
+
+cudaError_t pnr_launch_observe_done(const PnrParams& p, float4* state, const uint8_t* done, float* obs, float* terminal_out,
+                                    const float* f_applied, double* f_delta, float f_clip, cudaStream_t stream) {
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t grid = (p.n_envs + 127) / 128;
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;
+    pnr_observe_done_kernel<<<(unsigned)grid, 128, 0, stream>>>(p, state, done, obs, terminal_out, f_applied, f_delta, f_clip);
+    return cudaGetLastError();
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -448,6 +501,32 @@ __global__ void pnr_state_io_kernel(float4* __restrict__ state, int64_t N, float
     if (t) { if (SET) s.t = t[e]; else t[e] = s.t; }
     if (ep_return) { if (SET) s.ep_ret = ep_return[e]; else ep_return[e] = s.ep_ret; }
     if (SET) pnr_store_env(state, N, e, s);
+}
+
+// per-env random box <-> row-major float[N,6] (centre xyz, half extents xyz); utility path
+template <bool SET>
+__global__ void pnr_box_io_kernel(float4* __restrict__ box_a, float* __restrict__ box_z, int64_t N, float* __restrict__ box) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= N) return;
+    if (SET) {
+        box_a[e] = make_float4(box[e * 6 + 0], box[e * 6 + 1], box[e * 6 + 3], box[e * 6 + 4]);
+        box_z[e] = box[e * 6 + 5];                              // the box stands on z = 0: centre z = half height
+    } else {
+        const float4 a = box_a[e];
+        const float z = box_z[e];
+        box[e * 6 + 0] = a.x; box[e * 6 + 1] = a.y; box[e * 6 + 2] = z;
+        box[e * 6 + 3] = a.z; box[e * 6 + 4] = a.w; box[e * 6 + 5] = z;
+    }
+}
+
+// PNR_HOST_COMPACT: gather the 101 changing columns (0:18 and 54:137) of every row for the D2H copy; thread = output float
+__global__ void pnr_compact_obs_kernel(const float* __restrict__ full, float* __restrict__ compact, int64_t n_out) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_out; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t row = i / PNR_OBS_COMPACT_DIM;
+        const int c = (int)(i - row * PNR_OBS_COMPACT_DIM);
+        const int col = c < PNR_OBS_CONST_BEGIN ? c : c + (PNR_OBS_CONST_END - PNR_OBS_CONST_BEGIN);
+        pnr_st_stream(compact + i, full[row * PNR_OBS_DIM + col]);
+    }
 }
 
 __global__ void pnr_stats_snapshot_kernel(PnrStats* stats, double* out, int clear) {
@@ -493,10 +572,10 @@ static int64_t pnr_grid_for(int64_t n_envs, int envs_per_cta, int resident) {
 }
 
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions, float* obs,
-                            float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, const float* f_applied,
+                            float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain, const float* f_applied,
                             double* f_delta, float f_clip, cudaStream_t stream) {
-    typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, const float*,
-                         double*, float);
+    typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, uint32_t,
+                         const float*, double*, float);
     // the obstacle variant and the fused normaliser are separate instantiations: the plain kernel carries no trace of
     // them (a call site alone cost 40 % at 1M envs through caller-saved register spills)
     static Kern kernels[2][2][2] = {
@@ -527,8 +606,8 @@ cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_m
     if (const char* e = getenv("PNR_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // developer knob
     int cap = per_sm * dev_sms < resident ? per_sm * dev_sms : resident;
     const int64_t grid = pnr_grid_for(p.n_envs, PNR_TILE_ENVS, cap);
-    k<<<(unsigned)grid, PNR_STEP_THREADS, smem, stream>>>(p, state, actions, obs, reward, done, stats, tick, f_applied, f_delta,
-                                                          f_clip);
+    k<<<(unsigned)grid, PNR_STEP_THREADS, smem, stream>>>(p, state, actions, obs, reward, done, stats, tick, domain, f_applied,
+                                                          f_delta, f_clip);
     return cudaGetLastError();
 }
 
@@ -555,6 +634,26 @@ cudaError_t pnr_launch_state_io(bool set, float4* state, int64_t N, float* r, fl
     const unsigned grid = (unsigned)((N + threads - 1) / threads);
     if (set) pnr_state_io_kernel<true><<<grid, threads, 0, stream>>>(state, N, r, v, a, potential, target, t, ep_return);
     else pnr_state_io_kernel<false><<<grid, threads, 0, stream>>>(state, N, r, v, a, potential, target, t, ep_return);
+    return cudaGetLastError();
+}
+
+cudaError_t pnr_launch_box_io(bool set, float4* box_a, float* box_z, int64_t N, float* box, cudaStream_t stream) {
+    const int threads = 256;
+    const unsigned grid = (unsigned)((N + threads - 1) / threads);
+    if (set) pnr_box_io_kernel<true><<<grid, threads, 0, stream>>>(box_a, box_z, N, box);
+    else pnr_box_io_kernel<false><<<grid, threads, 0, stream>>>(box_a, box_z, N, box);
+    return cudaGetLastError();
+}
+
+cudaError_t pnr_launch_compact_obs(const float* full, float* compact, int64_t n_rows, cudaStream_t stream) {
+    const int64_t n_out = n_rows * PNR_OBS_COMPACT_DIM;
+    if (n_out <= 0) return cudaSuccess;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int64_t grid = (n_out + 255) / 256;
+    if (grid > (int64_t)sms * 8) grid = (int64_t)sms * 8;          // 8 CTAs of 256 threads per SM, grid-stride
+    pnr_compact_obs_kernel<<<(unsigned)grid, 256, 0, stream>>>(full, compact, n_out);
     return cudaGetLastError();
 }
 

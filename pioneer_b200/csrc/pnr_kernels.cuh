@@ -195,15 +195,48 @@ __device__ __forceinline__ void pnr_fk_tip(const PnrParams& p, const float (&sn)
 
 // ---------------------------------------------------------------------------------------------
 // Obstacle variant (this repo's extension; the reference instantiates a box and a plane only in its GUI demo,
-// pioneer_knm_env.py:249-261): sum over (link capsule, obstacle) pairs of max(0, radius - distance(segment, obstacle)).
-// plane: exact (nearer end point); sphere: exact (closest point of the segment); axis-aligned box: signed-distance
-// function sampled at PNR_BOX_SAMPLES points of the segment.  Same definition as oracle/reach_oracle.py::contact_depth.
+// pioneer_knm_env.py:249-261, and a per-episode random box only in its legacy path, pioneer/temp/pioneer_env.py:169-192):
+// sum over (link capsule, obstacle) pairs of max(0, radius - d), d = the minimum of the obstacle's signed-distance function
+// over the capsule's axis segment -- exact for every kind: plane (linear: the nearer end point), sphere (closest point of the
+// segment), axis-aligned box (below).  Same definition as oracle/contact.h and oracle/reach_oracle.py::contact_depth, which
+// enumerate the breakpoints of the piecewise function in float64 instead.
 // Rare configuration => not inlined; the sin/cos travel by value so the caller's arrays stay in registers.
 // ---------------------------------------------------------------------------------------------
-#define PNR_BOX_SAMPLES 8
 struct PnrSinCos { float sn[PNR_DOF], cs[PNR_DOF]; };
+struct PnrBox { float px, py, pz, ex, ey, ez; };
 
-static __device__ __noinline__ float pnr_contact_depth(const PnrParams& p, PnrSinCos sc) {
+// signed distance of x (relative to the box centre) and its derivative along d (a subgradient at kinks)
+__device__ __forceinline__ float pnr_box_sdf(float x, float y, float z, float ex, float ey, float ez) {
+    const float qx = fabsf(x) - ex, qy = fabsf(y) - ey, qz = fabsf(z) - ez;
+    const float ox = fmaxf(qx, 0.f), oy = fmaxf(qy, 0.f), oz = fmaxf(qz, 0.f);
+    return sqrtf(ox * ox + oy * oy + oz * oz) + fminf(fmaxf(qx, fmaxf(qy, qz)), 0.f);
+}
+// The box signed-distance function is convex, so along the segment a + t d it is a convex function of t whose derivative
+// changes sign exactly once: PNR_BOX_BISECTIONS halvings of [0, 1] on the sign of the directional derivative pin the
+// minimiser to 2^-24 of the segment (below float32 resolution of the distance itself); straight-line code, no divisions.
+#define PNR_BOX_BISECTIONS 24
+__device__ __forceinline__ float pnr_segment_box(float ax, float ay, float az, float dx, float dy, float dz,
+                                                 float ex, float ey, float ez) {
+    float lo = 0.f, hi = 1.f;
+#pragma unroll 1
+    for (int it = 0; it < PNR_BOX_BISECTIONS; ++it) {
+        const float t = 0.5f * (lo + hi);
+        const float x = fmaf(t, dx, ax), y = fmaf(t, dy, ay), z = fmaf(t, dz, az);
+        const float qx = fabsf(x) - ex, qy = fabsf(y) - ey, qz = fabsf(z) - ez;
+        const float gx = copysignf(dx, x), gy = copysignf(dy, y), gz = copysignf(dz, z);   // d|x_i|/dt
+        float g;
+        if (fmaxf(qx, fmaxf(qy, qz)) > 0.f)                    // outside: sign of d/dt |max(q, 0)|^2
+            g = fmaxf(qx, 0.f) * gx + fmaxf(qy, 0.f) * gy + fmaxf(qz, 0.f) * gz;
+        else                                                   // inside: the nearest face decides
+            g = (qx >= qy && qx >= qz) ? gx : (qy >= qz ? gy : gz);
+        if (g < 0.f) lo = t; else hi = t;
+    }
+    return fminf(pnr_box_sdf(fmaf(lo, dx, ax), fmaf(lo, dy, ay), fmaf(lo, dz, az), ex, ey, ez),
+                 pnr_box_sdf(fmaf(hi, dx, ax), fmaf(hi, dy, ay), fmaf(hi, dz, az), ex, ey, ez));
+}
+
+// `rb`: this env's random box (used for obstacle p.random_box when that is >= 0)
+static __device__ __noinline__ float pnr_contact_depth(const PnrParams& p, PnrSinCos sc, PnrBox rb) {
     float total = 0.f;
     for (int c = 0; c < p.n_capsules; ++c) {
         const int body = p.capsule_body[c];
@@ -219,8 +252,9 @@ static __device__ __noinline__ float pnr_contact_depth(const PnrParams& p, PnrSi
         const float radius = p.capsule_radius[c];
         const float dx = bx - ax, dy = by - ay, dz = bz - az;
         for (int o = 0; o < p.n_obstacles; ++o) {
-            const float px = p.obstacle_p[o][0], py = p.obstacle_p[o][1], pz = p.obstacle_p[o][2];
-            const float ex = p.obstacle_e[o][0], ey = p.obstacle_e[o][1], ez = p.obstacle_e[o][2];
+            float px = p.obstacle_p[o][0], py = p.obstacle_p[o][1], pz = p.obstacle_p[o][2];
+            float ex = p.obstacle_e[o][0], ey = p.obstacle_e[o][1], ez = p.obstacle_e[o][2];
+            if (o == p.random_box) { px = rb.px; py = rb.py; pz = rb.pz; ex = rb.ex; ey = rb.ey; ez = rb.ez; }
             float d;
             if (p.obstacle_type[o] == PNR_OBSTACLE_PLANE) {
                 const float da = (ax - px) * ex + (ay - py) * ey + (az - pz) * ez;
@@ -233,21 +267,22 @@ static __device__ __noinline__ float pnr_contact_depth(const PnrParams& p, PnrSi
                 const float cx = fmaf(t, dx, ax) - px, cy = fmaf(t, dy, ay) - py, cz = fmaf(t, dz, az) - pz;
                 d = sqrtf(cx * cx + cy * cy + cz * cz) - ex;
             } else {
-                d = INFINITY;
-#pragma unroll
-                for (int k = 0; k < PNR_BOX_SAMPLES; ++k) {
-                    const float t = (float)k / (float)(PNR_BOX_SAMPLES - 1);
-                    const float qx = fabsf(fmaf(t, dx, ax) - px) - ex, qy = fabsf(fmaf(t, dy, ay) - py) - ey,
-                                qz = fabsf(fmaf(t, dz, az) - pz) - ez;
-                    const float ox = fmaxf(qx, 0.f), oy = fmaxf(qy, 0.f), oz = fmaxf(qz, 0.f);
-                    const float sdf = sqrtf(ox * ox + oy * oy + oz * oz) + fminf(fmaxf(qx, fmaxf(qy, qz)), 0.f);
-                    d = fminf(d, sdf);
-                }
+                d = pnr_segment_box(ax - px, ay - py, az - pz, dx, dy, dz, ex, ey, ez);
             }
             total += fmaxf(0.f, radius - d);
         }
     }
     return total;
+}
+// the env's random box (zeros when the variant is off)
+__device__ __forceinline__ PnrBox pnr_load_box(const PnrParams& p, int64_t env) {
+    PnrBox b = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (p.random_box >= 0) {
+        const float4 a = p.box_a[env];
+        const float z = p.box_z[env];
+        b.px = a.x; b.py = a.y; b.pz = z; b.ex = a.z; b.ey = a.w; b.ez = z;
+    }
+    return b;
 }
 
 // float64 twin, only for envs whose float32 distance falls inside the done band: the reference

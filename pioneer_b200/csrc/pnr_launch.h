@@ -30,16 +30,20 @@
 // f_applied != NULL selects the fused normaliser (kinematic: a separate instantiation, float32 arithmetic and terminal
 // observations only; dynamic: a run-time switch, both observation modes); f_delta may be NULL (normalise, no statistics)
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions,
-                            float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick,
+                            float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain,
                             const float* f_applied, double* f_delta, float f_clip, cudaStream_t stream);
 cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode, float4* state, const float* actions,
-                                    float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick,
+                                    float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain,
                                     const float* f_applied, double* f_delta, float f_clip, cudaStream_t stream);
 cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, float4* state, const int64_t* idx,
                                      int64_t n, const float* q0, const float* target, float* obs_out, uint32_t tick,
                                      cudaStream_t stream);
 cudaError_t pnr_launch_state_io(bool set, float4* state, int64_t N, float* r, float* v, float* a, float* potential,
                                 float* target, int32_t* t, float* ep_return, cudaStream_t stream);
+cudaError_t pnr_launch_observe_done(const PnrParams& p, float4* state, const uint8_t* done, float* obs, float* terminal_out,
+                                    const float* f_applied, double* f_delta, float f_clip, cudaStream_t stream);
+cudaError_t pnr_launch_box_io(bool set, float4* box_a, float* box_z, int64_t N, float* box, cudaStream_t stream);
+cudaError_t pnr_launch_compact_obs(const float* full, float* compact, int64_t n_rows, cudaStream_t stream);
 cudaError_t pnr_launch_tick_advance(PnrStats* stats, uint32_t n, int absolute, cudaStream_t stream);
 cudaError_t pnr_launch_env_steps_set(PnrStats* stats, double env_steps, cudaStream_t stream);
 cudaError_t pnr_launch_stats_snapshot(PnrStats* stats, double* out, int clear, cudaStream_t stream);

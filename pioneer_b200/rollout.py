@@ -1,6 +1,6 @@
 """Device-resident rollout worker: what an RLlib RolloutWorker does around the reference env
 (pioneer/launch/pioneer_knm_train.py:43-73 -- sample `train_batch_size` env steps with the current policy, observation
-filter 'MeanStdFilter', episode metrics back to the trainer), with every tensor staying on the GPU:
+filter 'ConcurrentMeanStdFilter', episode metrics back to the trainer), with every tensor staying on the GPU:
 
     obs --(pnr_filter_apply)--> normalised obs --(policy MLP)--> action --(pnr_step)--> obs', reward, done
 
@@ -58,11 +58,13 @@ class GaussianMlpPolicy(nn.Module):
 class RolloutWorker:
     def __init__(self, env: BatchedPioneerEnv, fragment_length: int = 8, policy: Optional[nn.Module] = None,
                  use_filter: bool = True, seed: int = 0, policy_dtype=torch.bfloat16, fused_filter: bool = True,
-                 cuda_graph: bool = False):
+                 cuda_graph: bool = False, keep_terminal_obs: bool = False):
         """``cuda_graph=True``: the T steps of a fragment (policy, sampling, env step) are captured once and replayed,
         which removes the ~25 launch gaps per env step; the noise then comes from the device's default generator
         (graph-safe) and the env's reset counter advances on the device (pnr_tick_advance).  Needs the fused filter (or
-        none): a separate filter pass would be captured too, but its synchronisation is not."""
+        none): a separate filter pass would be captured too, but its synchronisation is not.
+        ``keep_terminal_obs``: also return the terminal observations of finished rows (``terminal_obs`` [T,N,137], written
+        for those rows only)."""
         self.env, self.T = env, int(fragment_length)
         self.use_graph, self._graph = bool(cuda_graph), None
         dev, n = env.device, env.n_envs
@@ -72,13 +74,34 @@ class RolloutWorker:
         self.gen = torch.Generator(device=dev).manual_seed(seed)
         self.a_max = torch.as_tensor(env.a_max, device=dev)
         f32 = dict(dtype=torch.float32, device=dev)
-        # fragment storage [T, N, ...]: raw observations are overwritten in place by their normalised version
-        self.obs = torch.empty((self.T + 1, n, OBS_DIM), **f32)
+        # fragment storage [T, N, ...]: raw observations are overwritten in place by their normalised version.  The row
+        # count of the allocation is padded to a multiple of 4 so that every obs[t] starts on a 16-byte boundary (the step
+        # kernel stores observation tiles with 16-byte bulk copies) whatever n is.
+        n_pad = (n + 3) // 4 * 4
+        self._obs_store = torch.empty((self.T + 1, n_pad, OBS_DIM), **f32)
+        self.obs = self._obs_store[:, :n]
+        # terminal observations of the rows that finished (written for those rows only), on request: the policy input after
+        # a done is the RESET observation (RLlib's sampler, bullet_env.py:187-190), which replaces the row in `obs`
+        self.terminal_obs = torch.zeros((self.T, n_pad, OBS_DIM), **f32)[:, :n] if keep_terminal_obs else None
         self.actions = torch.empty((self.T, n, DOF), **f32)
         self.logp = torch.empty((self.T, n), **f32)
         self.reward = torch.empty((self.T, n), **f32)
         self.flags = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
         self._have_first = False
+        self._last_done: Optional[torch.Tensor] = None
+        # terminal-observation envs with in-kernel auto-reset need their done rows patched; 'autoreset' envs already return
+        # the fresh observation (and have no terminal one to offer)
+        self._patch_done = env.batch_config.auto_reset and env.batch_config.obs_mode == "terminal"
+        if keep_terminal_obs:
+            assert self._patch_done, "terminal observations exist only in obs_mode='terminal' with auto_reset"
+
+    def _filter_rows(self, obs: torch.Tensor, flags: torch.Tensor) -> None:
+        """Separate-pass filter: normalise (and push) just the rows pnr_observe_done replaced.  Eager only (dynamic shape)."""
+        idx = torch.nonzero(flags & 1).flatten()
+        if idx.numel():
+            rows = obs[idx].contiguous()
+            self.filter(rows)
+            obs[idx] = rows
 
     def _steps(self) -> None:
         env = self.env
@@ -92,6 +115,12 @@ class RolloutWorker:
             env.step_tensor(self.actions[t], out=(self.obs[t + 1], self.reward[t], self.flags[t]))
             if self.filter is not None and not self.fused:
                 self.filter(self.obs[t + 1])                                      # push + normalise in place
+            if self._patch_done:
+                # rows that finished: the next policy input is the first observation of the new episode, not the terminal one
+                env.observe_done(self.flags[t], self.obs[t + 1],
+                                 None if self.terminal_obs is None else self.terminal_obs[t])
+                if self.filter is not None and not self.fused:
+                    self._filter_rows(self.obs[t + 1], self.flags[t])
 
     @torch.no_grad()
     def collect(self) -> Dict[str, torch.Tensor]:
@@ -100,7 +129,11 @@ class RolloutWorker:
         if not self._have_first:
             self.obs[self.T].copy_(env.reset())
             if self.filter is not None:
-                self.filter(self.obs[self.T])
+                # RLlib's filter pushes a sample before it normalises it: push the reset observations, make them the running
+                # statistics, only then normalise (without pushing them twice)
+                self.filter.push(self.obs[self.T])
+                self.filter.sync()
+                self.filter(self.obs[self.T], update=False)
             self._have_first = True
             if self.use_graph:
                 with torch.cuda.device(env.device):
@@ -114,8 +147,22 @@ class RolloutWorker:
             self._graph.replay()
         else:
             self._steps()
-        return dict(obs=self.obs[:self.T], next_obs=self.obs[1:], actions=self.actions, logp=self.logp,
-                    reward=self.reward, done=(self.flags & 1).bool(), truncated=(self.flags & 2).bool())
+        done = (self.flags & 1).bool()
+        out = dict(obs=self.obs[:self.T], next_obs=self.obs[1:], actions=self.actions, logp=self.logp,
+                   reward=self.reward, done=done, truncated=(self.flags & 2).bool())
+        # obs[t] is what the policy saw at step t.  After a done that is the first observation of the NEW episode, so
+        # next_obs[t] of a finished row belongs to the next episode; its terminal observation is in `terminal_obs` (when
+        # kept).  episode_start[t]: row starts an episode at step t (within the fragment; the previous fragment's last
+        # `done` marks the starts of step 0).
+        start = torch.zeros_like(done)
+        start[1:] = done[:-1]
+        if self._last_done is not None:
+            start[0] = self._last_done
+        self._last_done = done[-1].clone()
+        out["episode_start"] = start
+        if self.terminal_obs is not None:
+            out["terminal_obs"] = self.terminal_obs
+        return out
 
     def sync(self, group=None, summary: bool = True):
         """Once per training iteration: episode statistics and filter statistics of all ranks.  ``summary=False`` returns

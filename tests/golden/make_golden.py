@@ -173,6 +173,33 @@ def main():
     out["multi__q0"] = np.stack([m["q0"][0] for m in multi])
     out["multi__target"] = np.stack([m["target"][0] for m in multi])
 
+    # sampled resets: the reference's own env.seed(s); env.reset() (pioneer_knm_env.py:80-94,107-109).  np_random.uniform
+    # returns FLOAT64 joint angles and `r` stays float64 until the first act(); a = v = 0 after a reset, so that act()
+    # computes r1 = float32(r0 + 0 + 0): the float64 start is rounded to float32 exactly once, with nothing added.
+    tl3 = make_env()
+    e3 = tl3.env
+    e3.seed(123)
+    rng_a = np.random.default_rng(71)
+    acts = rng_a.uniform(-a_max, a_max, size=(90, 6)).astype(f32)
+    rec = dict(r=np.zeros((90, 6), f32), v=np.zeros((90, 6), f32), reward=np.zeros(90), tail=np.zeros((90, 11)),
+               r_dtype_before_first_step=[], q0_f64=[], target_f64=[], reset_obs=[], reset_at=[])
+    for t in range(90):
+        if t in (0, 40):                                       # two seeded episodes from one RandomState stream
+            obs0 = tl3.reset()
+            rec["reset_at"].append(t)
+            rec["r_dtype_before_first_step"].append(str(np.asarray(e3.r).dtype))
+            rec["q0_f64"].append(np.array(e3.r, np.float64))
+            rec["target_f64"].append(np.array(obs0[129:132], np.float64))
+            rec["reset_obs"].append(obs0)
+        obs, reward, done, info = tl3.step(acts[t])
+        rec["r"][t], rec["v"][t], rec["reward"][t], rec["tail"][t] = e3.r, e3.v, reward, obs[126:137]
+        assert np.asarray(e3.r).dtype == np.float32
+    rec["actions"] = acts
+    rec["seed"] = np.array(123)
+    for k in ("q0_f64", "target_f64", "reset_obs", "reset_at", "r_dtype_before_first_step"):
+        rec[k] = np.array(rec[k])
+    put("sampled", rec)
+
     path = os.path.join(HERE, "reach_golden.npz")
     np.savez_compressed(path, **out)
     print(f"wrote {path}: {len(out)} arrays, {os.path.getsize(path) / 1024:.0f} KiB, numpy {np.__version__}")

@@ -77,6 +77,29 @@ def test_facade_seed_reproduces_the_reference_draw_order():
     env.close()
 
 
+def test_facade_after_a_seeded_reset_replays_the_reference_bit_for_bit():
+    """Golden case 'sampled': env.seed(123); env.reset() run by the unmodified reference (float64 start angles), 90 steps,
+    a second seeded reset at step 40.  The facade draws with the same generator, hands the device float32(start), and the
+    joint state is bit-equal from the first step on (see test_sampled_reset_keeps_float64... for why nothing is lost)."""
+    from pioneer_b200.launch import prepare_env
+    case = golden_case(G, "sampled")
+    tl = prepare_env({})
+    env = tl.env
+    env.seed(int(case["seed"]))
+    ep = 0
+    for t, action in enumerate(case["actions"]):
+        if t in case["reset_at"]:
+            obs0 = tl.reset()
+            np.testing.assert_allclose(obs0[:126], case["reset_obs"][ep][:126], rtol=0, atol=6e-7)
+            np.testing.assert_allclose(obs0[126:136], case["reset_obs"][ep][126:136], rtol=0, atol=2e-4)
+            ep += 1
+        obs, reward, done, info = tl.step(action)
+        assert np.array_equal(env.r, case["r"][t]) and np.array_equal(env.v, case["v"][t]), t
+        np.testing.assert_allclose(reward, case["reward"][t], atol=1e-3)
+        np.testing.assert_allclose(obs[126:136], case["tail"][t][:10], atol=2e-4)
+    tl.close()
+
+
 def test_vector_env_rllib_contract():
     from pioneer_b200 import PioneerVectorEnv
     n = 48
@@ -120,9 +143,9 @@ def test_prepare_vector_env_factory():
 
 def test_cuda_graph_rollout_equals_stepping():
     from pioneer_b200 import BatchConfig, BatchedPioneerEnv
-    n, T = 3000, 6
-    a = BatchedPioneerEnv(n, seed=4, batch_config=BatchConfig(max_episode_steps=4))
-    b = BatchedPioneerEnv(n, seed=4, batch_config=BatchConfig(max_episode_steps=4))
+    n, T, limit = 3000, 6, 4
+    a = BatchedPioneerEnv(n, seed=4, batch_config=BatchConfig(max_episode_steps=limit))
+    b = BatchedPioneerEnv(n, seed=4, batch_config=BatchConfig(max_episode_steps=limit))
     g = torch.Generator(device="cuda").manual_seed(0)
     actions = (torch.rand((T, n, 6), device="cuda", generator=g) * 2 - 1) * torch.as_tensor(a.a_max).cuda()
     obs = torch.zeros((T, n, 137), device="cuda")
@@ -133,14 +156,64 @@ def test_cuda_graph_rollout_equals_stepping():
     b.step_tensor(actions[0])
     graph.replay()
     torch.cuda.synchronize()
-    b.advance_reset_counter(T)                 # the graph's first node: the reset counter moves on by T per replay
     for t in range(T):
         o, r, f = b.step_tensor(actions[t])
-        assert torch.equal(r, rew[t]) and torch.equal(f, flg[t]), t
-        assert torch.equal(o, obs[t])
-    sa, sb = a.state(), b.state()              # including the envs that restarted inside the graph
-    assert torch.equal(sa["r"], sb["r"]) and torch.equal(sa["target"], sb["target"])
+        assert torch.equal(f, flg[t]), t                                # TimeLimit flags never depend on the reset draws
+        if t < limit - 1:                                                # the eager step + these: nobody has restarted yet
+            assert torch.equal(r, rew[t]) and torch.equal(o, obs[t]), t
+    # envs that restarted INSIDE the graph drew from the graph's own reset-key domain: valid states, different from the
+    # eager twin's draws (eager steps and graph replays can be interleaved without ever reusing a reset key)
+    sa, sb = a.state(), b.state()
+    lo, hi = torch.as_tensor(a.r_lo).cuda(), torch.as_tensor(a.r_hi).cuda()
+    assert (sa["r"] >= lo).all() and (sa["r"] <= hi).all() and torch.equal(sa["t"], sb["t"])
+    assert (sa["target"] != sb["target"]).any(dim=1).float().mean() > 0.99
     a.close(); b.close()
+
+
+def test_eager_steps_and_graph_replays_never_reuse_a_reset_key():
+    """with the host counter frozen into the graph, an eager step after replay 1 and the first captured step of
+    replay 2 used to draw the same (q, target).  Every step ends an episode here, so every step exposes its reset draw."""
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    n, T = 256, 2
+    env = BatchedPioneerEnv(n, seed=8, batch_config=BatchConfig(max_episode_steps=1))
+    actions = torch.zeros((T, n, 6), device="cuda")
+    obs = torch.zeros((T, n, 137), device="cuda")
+    rew = torch.zeros((T, n), device="cuda")
+    flg = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+    graph = env.capture_rollout(actions, obs, rew, flg)
+    seen = []
+
+    def snap():
+        torch.cuda.synchronize()
+        seen.append(env.state()["target"].clone())
+
+    for k in range(3):                      # replay, two eager steps, replay, ...
+        graph.replay(); snap()
+        env.step_tensor(actions[0]); snap()
+        env.step_tensor(actions[0]); snap()
+    # a second graph on the same handle gets its own domain
+    graph2 = env.capture_rollout(actions, obs, rew, flg); snap()
+    graph2.replay(); snap()
+    graph.replay(); snap()
+    for i in range(len(seen)):
+        for j in range(i + 1, len(seen)):
+            assert (seen[i] != seen[j]).any(dim=1).float().mean() > 0.99, (i, j)
+    env.close()
+
+
+def test_seed_reaches_steps_already_captured_in_a_graph():
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    n, T = 256, 1
+    env = BatchedPioneerEnv(n, seed=8, batch_config=BatchConfig(max_episode_steps=1))
+    twin = BatchedPioneerEnv(n, seed=8, batch_config=BatchConfig(max_episode_steps=1))
+    bufs = lambda: (torch.zeros((T, n, 6), device="cuda"), torch.zeros((T, n, 137), device="cuda"),
+                    torch.zeros((T, n), device="cuda"), torch.zeros((T, n), dtype=torch.uint8, device="cuda"))
+    g1, g2 = env.capture_rollout(*bufs()), twin.capture_rollout(*bufs())
+    twin.seed(99)                           # after capture
+    g1.replay(); g2.replay(); torch.cuda.synchronize()
+    assert (env.state()["target"] != twin.state()["target"]).any(dim=1).float().mean() > 0.99
+    assert twin.state_dict()["seed"] == 99
+    env.close(); twin.close()
 
 
 def test_graph_replays_draw_fresh_reset_states():
@@ -193,8 +266,9 @@ def test_rollout_worker_collects_fragments_on_the_device():
         assert (b["actions"].abs() <= a_max).all() and torch.isfinite(b["obs"]).all() and torch.isfinite(b["logp"]).all()
         assert float(b["obs"].abs().max()) <= 10.0                      # normalised + clipped
         s = w.sync()
-    assert s["env_steps"] == n * T and w.filter.n == n * (4 * T + 1)
-    # 24 steps with TimeLimit 10: every env finished 2 episodes, the last sync window saw the second batch
+    # 24 steps with TimeLimit 10: every env finished 2 episodes, the last sync window saw the second batch; the filter saw
+    # the reset observations, every step's observation and the 2 fresh observations that replaced terminal rows
+    assert s["env_steps"] == n * T and w.filter.n == n * (4 * T + 1 + 2)
     assert env.episode_stats()["episodes"] == 0 and s["episodes_total"] == n
     # fragments chain: the first observation of a fragment is the last of the previous one
     last = w.obs[T].clone()
@@ -221,7 +295,7 @@ def test_checkpoint_resume_is_bit_identical(tmp_path):
     for k, t in enumerate(range(5, 12)):
         o, r, f = other.step_tensor(acts[t])
         assert torch.equal(o, want[k][0]) and torch.equal(r, want[k][1]) and torch.equal(f, want[k][2]), t
-    assert other.episode_stats()["env_steps"] == stats_want["env_steps"]
+    assert other.episode_stats() == stats_want            # the whole statistics window travels with the checkpoint
     env.close(); other.close()
 
 
@@ -245,7 +319,7 @@ def test_rollout_worker_replays_fragments_from_a_cuda_graph():
     w = RolloutWorker(env, fragment_length=T, policy_dtype=torch.float32, cuda_graph=True)
     a_max = torch.as_tensor(env.a_max).cuda()
     w.collect()                                # warm-up fragment + capture + first replay
-    w.sync()
+    episodes = w.sync()["episodes_total"]
     seen = []
     for it in range(3):
         last = w.obs[T].clone()
@@ -255,8 +329,109 @@ def test_rollout_worker_replays_fragments_from_a_cuda_graph():
         assert float(b["obs"].abs().max()) <= 10.0
         s = w.sync()
         assert s["env_steps"] == n * T and s["episodes_total"] >= n    # TimeLimit 4 < T: every env finished an episode
+        episodes += s["episodes_total"]
         seen.append((b["actions"].clone(), b["obs"][-1].clone()))
     assert not torch.equal(seen[0][0], seen[1][0])                     # fresh noise on every replay
     assert not torch.equal(seen[1][1], seen[2][1])
-    assert w.filter.n == n * (1 + 5 * T)                               # reset obs + warm-up + capture replay + 3 fragments
+    # reset obs + warm-up + capture replay + 3 fragments, plus one fresh observation per finished episode (observe_done)
+    assert w.filter.n == n * (1 + 5 * T) + episodes
     env.close()
+
+
+def test_policy_input_after_done_is_the_reset_observation():
+    """RLlib's sampler feeds the policy the RESET observation after a done (bullet_env.py:187-197).  The worker
+    keeps terminal-observation stepping and patches the finished rows (pnr_observe_done); `episode_start` marks them."""
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    from pioneer_b200.rollout import RolloutWorker
+    n, T, limit = 300, 7, 3                                            # n not a multiple of 4: padded observation rows
+    env = BatchedPioneerEnv(n, seed=5, batch_config=BatchConfig(max_episode_steps=limit))
+    w = RolloutWorker(env, fragment_length=T, policy_dtype=torch.float32, use_filter=False, keep_terminal_obs=True)
+    b = w.collect()
+    done = b["done"]
+    assert done[limit - 1].all() and done[2 * limit - 1].all() and not done[0].any()
+    assert torch.equal(b["episode_start"][1:], done[:-1]) and not b["episode_start"][0].any()
+    t = limit - 1
+    fresh = b["next_obs"][t]                                           # = the policy input of step t + 1
+    assert torch.equal(fresh, b["obs"][t + 1])
+    assert (fresh[:, 90:96] == 0).all() and (fresh[:, 108:114] == 0).all() and (fresh[:, 136] == 0).all()   # a new episode
+    term = b["terminal_obs"][t]
+    assert (term[:, 136] > 0).all() and not torch.equal(term[:, 0:6], fresh[:, 0:6])
+    # the reward of the first step of the new episode carries the whole potential -- paired with the fresh observation
+    assert torch.allclose(b["reward"][t + 1], b["obs"][t + 2][:, 136] - 0.01, atol=1e-4)
+    # the state the env continues from is the one the policy saw
+    w2_obs = env.observe()
+    assert torch.equal(w2_obs[:, 129:132], b["next_obs"][-1][:, 129:132])
+    b2 = w.collect()
+    assert torch.equal(b2["episode_start"][0], done[-1])
+    env.close()
+
+
+def test_compact_host_layout_and_async_double_buffering():
+    """pnr_step_host_begin / _end: PNR_HOST_COMPACT rows (101 columns) re-expand to the 137-column rows bit for bit, and two
+    steps in flight deliver the same results as synchronous stepping."""
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    n, steps = 5000, 9
+    a = BatchedPioneerEnv(n, seed=2, batch_config=BatchConfig(max_episode_steps=4))
+    b = BatchedPioneerEnv(n, seed=2, batch_config=BatchConfig(max_episode_steps=4))
+    rng = np.random.default_rng(0)
+    acts = [torch.as_tensor((rng.uniform(-1, 1, size=(n, 6)) * a.a_max).astype(np.float32)).pin_memory() for _ in range(steps)]
+    want = []
+    for k in range(steps):
+        o, r, f = a.step_host(acts[k])
+        want.append((o.copy(), r.copy(), f.copy()))
+    const = b.obs_constants()
+    assert np.array_equal(const, want[0][0][0, 18:54])
+    got = []
+    b.step_host_begin(acts[0], compact=True)
+    for k in range(steps):
+        if k + 1 < steps:
+            b.step_host_begin(acts[k + 1], compact=(k % 2 == 1))      # two in flight; layouts may alternate
+        o, r, f = b.step_host_end()
+        full = b.expand_compact(o) if o.shape[1] == 101 else o
+        got.append((full.copy(), r.copy(), f.copy()))
+    for k in range(steps):
+        assert np.array_equal(got[k][0], want[k][0]) and np.array_equal(got[k][1], want[k][1])
+        assert np.array_equal(got[k][2], want[k][2])
+    with pytest.raises(Exception):
+        b.step_host_end()                                              # nothing in flight
+    b.step_host_begin(acts[0]); b.step_host_begin(acts[1])
+    with pytest.raises(Exception):
+        b.step_host_begin(acts[2])                                     # a third step would overwrite a buffer in flight
+    b.step_host_end(); b.step_host_end()
+    a.close(); b.close()
+
+
+def test_misaligned_buffers_are_rejected_not_faulted():
+    from pioneer_b200 import BatchedPioneerEnv, _cabi
+    n = 37
+    env = BatchedPioneerEnv(n, seed=1)
+    raw = torch.zeros(n * 137 + 8, device="cuda")
+    mis = raw[1:1 + n * 137].view(n, 137)                              # 4 bytes off a 16-byte boundary
+    lib, h, s = env._lib, env._h, env._stream()
+    assert lib.pnr_reset(h, None, n, None, None, mis.data_ptr(), s) != 0
+    assert lib.pnr_observe(h, None, n, mis.data_ptr(), s) != 0
+    act = torch.zeros((n, 6), device="cuda")
+    rew, flg = torch.zeros(n, device="cuda"), torch.zeros(n, dtype=torch.uint8, device="cuda")
+    assert lib.pnr_step(h, act.data_ptr(), mis.data_ptr(), rew.data_ptr(), flg.data_ptr(), s) != 0
+    torch.cuda.synchronize()                                            # no sticky fault: the device still works
+    assert env.observe().shape == (n, 137)
+    env.close()
+
+
+def test_filter_outlives_nothing_and_is_the_identity_before_its_first_sync():
+    from pioneer_b200 import BatchedPioneerEnv, _cabi
+    from pioneer_b200.obs_filter import MeanStdObsFilter
+    env = BatchedPioneerEnv(64, seed=1)
+    f = MeanStdObsFilter(env)
+    x = torch.randn((64, 137), device="cuda") * 3
+    y = f(x.clone())
+    assert torch.equal(y, x.clamp(-10, 10))                             # count == 0: identity (then clipped)
+    f.sync()
+    z = f(x.clone(), update=False)
+    assert float(z.mean().abs()) < 0.2 and abs(float(z.std()) - 1.0) < 0.2
+    sd = env.state_dict()
+    assert sd["obs_filter"]["count"] == 64
+    env.close()
+    with pytest.raises(_cabi.PioneerB200Error):
+        f(x)
+

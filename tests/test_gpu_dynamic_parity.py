@@ -1,0 +1,188 @@
+"""Dynamic (Tier-B) mode on the GPU against the compiled float64 oracle (oracle/dynamics_oracle.c) at BASELINE.json's
+full sizes: configs[2] = 65,536 envs with joint limits, PD position control, TimeLimit and auto-reset; configs[3] = 16,384
+envs with the demo obstacles.  PARITY UNPINNED vs PyBullet (the reference never runs Bullet's dynamics with non-zero
+inputs; see the oracle's header) -- the oracle is the float64 definition of this mode, checked on the CPU against the
+6x6-matrix Python oracle, CRBA + RNEA and Lagrange's equations.
+
+Method (lock step, see oracle/dynamics_oracle.c): every step the oracle advances from the float32 state the device held
+before the step, reports where its own float64 substeps arrive (compared with the device inside the bars below), then
+ADOPTS the device's float32 post-step state, so that the env layer -- reward, done / TimeLimit flags, observation,
+statistics, Philox auto-reset -- is compared on identical inputs: flags BIT-EXACT, like the kinematic mode.
+
+Bars per env step (10 substeps, float32 vs float64): |dq| <= 2e-5 + 2e-6 |q|,  |dqd| <= 2e-4 + 2e-5 |qd|;
+observation: value columns r, v, a bit-exact, every other column <= 1e-3 (pointer xyz <= 2e-4 + |dq| propagated);
+reward <= 2e-3; episode statistics: counts exact, sums to float32 accumulation."""
+import numpy as np
+import pytest
+
+torch = pytest.importorskip("torch")
+
+from oracle.c_dyn_oracle import CDynOracleBatch, DynEnvConfig
+
+pytestmark = pytest.mark.gpu
+
+PD = dict(gravity=9.81, kp=2000.0, kd=500.0, torque_scale=1e5)          # bench.py's dynamic-mode workload
+
+
+def make(n, obs_mode="terminal", limit=500, obstacles=(), penalty=0.0, random_box=False, seed=0, env_id_base=0, **dyn):
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv, SimulationConfig
+    bc = BatchConfig(mode="dynamic", kp=dyn.get("kp", 0.0), kd=dyn.get("kd", 0.0), torque_scale=dyn.get("torque_scale", 1.0),
+                     max_episode_steps=limit, auto_reset=True, obs_mode=obs_mode, obstacles=list(obstacles),
+                     contact_penalty=penalty, random_box=random_box)
+    env = BatchedPioneerEnv(n, batch_config=bc, simulation_config=SimulationConfig(gravity=dyn.get("gravity", 0.0)), seed=seed,
+                            env_id_base=env_id_base)
+    cfg = DynEnvConfig(gravity=dyn.get("gravity", 0.0), kp=bc.kp, kd=bc.kd, torque_scale=bc.torque_scale,
+                       max_episode_steps=limit, obstacles=tuple((o.kind, o.position, o.extent) for o in obstacles),
+                       contact_penalty=penalty,
+                       random_box=(bc.box_pos_lo, bc.box_pos_hi, bc.box_size_lo, bc.box_size_hi) if random_box else None)
+    orc = CDynOracleBatch(env.chain, n, cfg, env_id_base=env_id_base, seed=seed, obs_mode=obs_mode)
+    return env, orc
+
+
+def check_obs(obs, o_obs, worst):
+    """obs: device float32 [n,137]; o_obs: oracle float64 computed from the SAME float32 (q, qd, a)."""
+    d = np.abs(obs.astype(np.float64) - o_obs)
+    for cols in (slice(0, 6), slice(90, 96), slice(108, 114), slice(18, 24), slice(36, 42), slice(129, 132)):
+        assert not d[:, cols].any(), f"value columns {cols} must be bit-exact"
+    worst["trig"] = max(worst.get("trig", 0.0), float(d[:, 6:90].max()), float(d[:, 96:108].max()), float(d[:, 114:126].max()))
+    worst["ptr"] = max(worst.get("ptr", 0.0), float(d[:, 126:129].max()), float(d[:, 132:136].max()))
+    worst["pot"] = max(worst.get("pot", 0.0), float(d[:, 136].max()))
+
+
+def lockstep(env, orc, steps, action_fn, obs_mode="terminal", check_every=1):
+    n = env.n_envs
+    s0, o0 = env.state(), orc.state()
+    assert np.array_equal(s0["r"].cpu().numpy().astype(np.float64), o0["q"])         # same Philox reset draws
+    assert np.array_equal(s0["target"].cpu().numpy().astype(np.float64), o0["target"])
+    worst = {}
+    n_done = 0
+    for t in range(steps):
+        act = action_fn(t)
+        obs, reward, flags = env.step_tensor(torch.as_tensor(act).cuda())
+        obs, reward, flags = obs.cpu().numpy(), reward.cpu().numpy(), flags.cpu().numpy()
+        if obs_mode == "terminal":
+            q32, qd32, mask = obs[:, 0:6], obs[:, 90:96], None                        # the post-substep state of EVERY env
+        else:                                                                         # finished rows show the next episode
+            mask = (flags & 1) == 0
+            st = env.state()
+            q32, qd32 = st["r"].cpu().numpy(), st["v"].cpu().numpy()
+        out = orc.step(act, adopt=(q32, qd32, None if mask is None else mask.astype(np.uint8)), want_obs=(t % check_every == 0))
+        # ---- the dynamics: where float64 arrives from the same float32 start
+        sel = slice(None) if mask is None else mask
+        dq = np.abs(q32.astype(np.float64) - out["own_q"])[sel]
+        dqd = np.abs(qd32.astype(np.float64) - out["own_qd"])[sel]
+        bar_q = 2e-5 + 2e-6 * np.abs(out["own_q"][sel])
+        bar_qd = 2e-4 + 2e-5 * np.abs(out["own_qd"][sel])
+        assert (dq <= bar_q).all(), (t, float(dq.max()), np.unravel_index(np.argmax(dq - bar_q), dq.shape))
+        assert (dqd <= bar_qd).all(), (t, float(dqd.max()), float(np.abs(out["own_qd"]).max()))
+        worst["dq"] = max(worst.get("dq", 0.0), float(dq.max()))
+        worst["dqd"] = max(worst.get("dqd", 0.0), float(dqd.max()))
+        worst["qd_abs"] = max(worst.get("qd_abs", 0.0), float(np.abs(out["own_qd"]).max()))
+        # ---- the env layer on identical inputs
+        assert np.array_equal(flags, out["flags"]), (t, int((flags != out["flags"]).sum()))
+        dr = np.abs(reward.astype(np.float64) - out["reward"])
+        if mask is not None:
+            dr = dr[mask]                                                             # finished rows: the oracle used its own q
+        assert dr.max() <= 2e-3, (t, float(dr.max()))
+        worst["reward"] = max(worst.get("reward", 0.0), float(dr.max()))
+        if out["obs"] is not None:
+            check_obs(obs, out["obs"], worst)
+        n_done += int((flags & 1).sum())
+    assert worst.get("trig", 0.0) <= 1e-6 and worst.get("ptr", 0.0) <= 2e-4 and worst.get("pot", 0.0) <= 1e-3, worst
+    # ---- after the run: the reset envs carry the oracle's Philox draws, counters and statistics agree
+    s, o = env.state(), orc.state()
+    assert np.array_equal(s["t"].cpu().numpy(), o["t"])
+    assert np.array_equal(s["target"].cpu().numpy().astype(np.float64), o["target"])
+    assert np.array_equal(s["r"].cpu().numpy().astype(np.float64), o["q"])            # adopted or freshly reset: identical
+    assert np.abs(s["potential"].cpu().numpy() - o["potential"]).max() <= 1e-3
+    assert np.abs(s["ep_return"].cpu().numpy() - o["ep_return"]).max() <= 5e-2
+    st, os_ = env.episode_stats(), orc.stats
+    assert st["episodes"] == os_[0] == n_done and st["sum_length"] == os_[2] and st["env_steps"] == os_[6] == steps * n
+    assert st["reached_target"] == os_[7]
+    if n_done:
+        assert abs(st["sum_return"] - os_[1]) <= 5e-2 * n_done and abs(st["max_return"] - os_[4]) <= 5e-2
+        assert abs(st["min_return"] - os_[5]) <= 5e-2
+    return worst, n_done
+
+
+def setpoints(env, seed, hold=25):
+    """New PD set points every `hold` steps (uniform in the joint range): long transients, joints driven into the stops."""
+    rng = np.random.default_rng(seed)
+    cache = {}
+
+    def fn(t):
+        k = t // hold
+        if k not in cache:
+            cache.clear()
+            cache[k] = rng.uniform(env.r_lo, env.r_hi, size=(env.n_envs, 6)).astype(np.float32)
+        return cache[k]
+    return fn
+
+
+def test_config3_65536_envs_pd_control_timelimit_autoreset():
+    """BASELINE.json configs[2]: 65,536 envs, joint limits, PD position control, TimeLimit + in-kernel auto-reset; 200 steps
+    with TimeLimit 64 => every env goes through three episode ends and Philox resets."""
+    env, orc = make(65536, limit=64, seed=12, **PD)
+    worst, n_done = lockstep(env, orc, 200, setpoints(env, 1), check_every=10)
+    assert n_done == 3 * 65536
+    print("config3 dynamic parity, worst:", worst)
+    env.close()
+
+
+def test_autoreset_observation_mode_at_16384_envs():
+    env, orc = make(16384, obs_mode="autoreset", limit=40, seed=5, env_id_base=1 << 33, **PD)
+    worst, n_done = lockstep(env, orc, 100, setpoints(env, 2), obs_mode="autoreset", check_every=5)
+    assert n_done == 2 * 16384
+    env.close()
+
+
+def test_torque_control_with_gravity():
+    n = 8192
+    env, orc = make(n, limit=30, seed=3, gravity=9.81, torque_scale=40.0)
+    rng = np.random.default_rng(4)
+    tau_max = (np.asarray(env.chain.effort) * 40.0).astype(np.float32)
+    assert np.array_equal(env.action_space.high, tau_max)                            # the action space of this mode
+    worst, _ = lockstep(env, orc, 60, lambda t: (rng.uniform(-1.2, 1.2, size=(n, 6)) * tau_max).astype(np.float32))
+    env.close()
+
+
+def test_config4_16384_envs_with_the_demo_obstacles():
+    """BASELINE.json configs[3]: ground plane, the reference demo's box, a sphere; contact penalty in the reward."""
+    from pioneer_b200 import demo_obstacles
+    env, orc = make(16384, limit=50, obstacles=demo_obstacles(), penalty=0.5, seed=9, **PD)
+    worst, n_done = lockstep(env, orc, 100, setpoints(env, 3), check_every=5)
+    assert n_done == 2 * 16384
+    env.close()
+
+
+def test_per_env_random_box_in_dynamic_mode():
+    from pioneer_b200 import demo_obstacles
+    n = 4096
+    env, orc = make(n, limit=20, obstacles=demo_obstacles(), penalty=0.5, random_box=True, seed=21, **PD)
+    assert np.array_equal(env.boxes().cpu().numpy().astype(np.float64), orc.state()["box"])
+    worst, n_done = lockstep(env, orc, 45, setpoints(env, 5), check_every=5)
+    assert n_done == 2 * n
+    assert np.array_equal(env.boxes().cpu().numpy().astype(np.float64), orc.state()["box"])   # redrawn twice, same draws
+    env.close()
+
+
+def test_free_running_drift_is_bounded_under_pd_control():
+    """No adoption: the float64 oracle free-runs beside 8,192 envs for 300 steps (TimeLimit 100, auto-reset).  PD control
+    contracts, so the float32 trajectory stays within 2e-3 rad of the float64 one; flags may only differ where the distance
+    sits within that drift of the done threshold (never, for random targets)."""
+    n = 8192
+    env, orc = make(n, limit=100, seed=31, **PD)
+    fn = setpoints(env, 7, hold=50)
+    worst = 0.0
+    for t in range(300):
+        act = fn(t)
+        obs, reward, flags = env.step_tensor(torch.as_tensor(act).cuda())
+        out = orc.step(act, want_obs=False)
+        f = flags.cpu().numpy()
+        diff = f != out["flags"]
+        assert not diff.any(), (t, int(diff.sum()))
+        if t % 10 == 9:
+            q = obs[:, 0:6].cpu().numpy().astype(np.float64)
+            worst = max(worst, float(np.abs(q - out["own_q"]).max()))
+    assert worst <= 2e-3, worst
+    env.close()

@@ -69,6 +69,10 @@ def test_each_obstacle_kind_known_answers():
         ([Obstacle("box", (2.5, 0, 8), (2.0, 5.0, 1.0))], None),
         # far away: nothing
         ([Obstacle("sphere", (100, 100, 100), (1.0, 0, 0)), Obstacle("plane", (0, 0, -50), (0, 0, 1))], 0.0),
+        # a THIN box (1 wide, the demo box's footprint) crossed by arm2 (x from 0 to 9 at y = 1, z = 14, radius 0.9) between
+        # two of the former 8 sample points (x = 3.86 and 5.14): the axis passes through the box centre line, 0.5 deep,
+        # so the exact depth is 0.9 + 0.5 = 1.4 (the 8-sample rule saw 0.9 - 0.14 = 0.76)
+        ([Obstacle("box", (4.5, 1.0, 14.0), (0.5, 0.5, 5.0))], 1.4),
     ]
     for obstacles, expect in cases:
         env = make(4, obstacles, penalty=1.0)
@@ -85,6 +89,57 @@ def test_each_obstacle_kind_known_answers():
         if expect is not None:
             assert abs(want - expect) < 1e-6, (obstacles, want, expect)
         env.close(); plain.close()
+
+
+def test_box_distance_is_exact_between_the_former_sample_points():
+    """arm2 straddling the thin box above: the exact rule sees the full penetration, and sliding the box along the link
+    changes nothing (an 8-sample rule would oscillate with the box position)."""
+    from pioneer_b200 import Obstacle
+    depths = []
+    for x in np.linspace(3.0, 7.5, 10):
+        obstacles = [Obstacle("box", (float(x), 1.0, 14.0), (0.5, 0.5, 5.0))]
+        env, plain = make(2, obstacles, penalty=1.0), make(2, [], penalty=0.0)
+        q0, tg = np.zeros((2, 6), np.float32), np.tile(np.array([[20, 0, 4]], np.float32), (2, 1))
+        env.reset_world(q0, tg); plain.reset_world(q0, tg)
+        zero = torch.zeros((2, 6), device="cuda")
+        depths.append(float((plain.step_tensor(zero)[1] - env.step_tensor(zero)[1])[0]))
+        want = contact_depth(OracleChain.from_model(env.chain), q0[0], oracle_obstacles(obstacles))
+        assert abs(depths[-1] - want) < 1e-4
+        env.close(); plain.close()
+    assert max(depths) - min(depths) < 1e-4 and abs(depths[0] - 1.4) < 1e-4, depths
+
+
+@pytest.mark.parametrize("random_box", [False, True])
+def test_config4_16384_envs_against_the_compiled_oracle(random_box):
+    """BASELINE.json configs[3] in the kinematic mode: 16,384 envs x 60 steps with TimeLimit 25 (two auto-resets, which
+    redraw the per-env box when random_box is on) against oracle/reach_oracle.c: joint state and flags bit-exact, reward
+    (which carries the contact penalty) within 2e-3."""
+    from oracle.c_oracle import COracleBatch
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv
+    n, obstacles = 16384, demo_obstacles()
+    bc = BatchConfig(obstacles=obstacles, contact_penalty=PENALTY, max_episode_steps=25, auto_reset=True, random_box=random_box)
+    env = BatchedPioneerEnv(n, batch_config=bc, seed=77)
+    cfg = OracleConfig(obstacles=oracle_obstacles(obstacles), contact_penalty=PENALTY, max_episode_steps=25,
+                       random_box=(bc.box_pos_lo, bc.box_pos_hi, bc.box_size_lo, bc.box_size_hi) if random_box else None)
+    orc = COracleBatch(OracleChain.from_model(env.chain), n, cfg, seed=77)
+    if random_box:
+        assert np.array_equal(env.boxes().cpu().numpy().astype(np.float64), orc.boxes())
+    rng = np.random.default_rng(3)
+    worst = 0.0
+    for t in range(60):
+        act = (rng.uniform(-1, 1, size=(n, 6)) * env.a_max).astype(np.float32)
+        obs, reward, flags = env.step_tensor(torch.as_tensor(act).cuda())
+        _, o_reward, o_flags = orc.step(act, want_obs=False)
+        assert np.array_equal(flags.cpu().numpy(), o_flags)
+        worst = max(worst, float(np.abs(reward.cpu().numpy() - o_reward).max()))
+    s, o = env.state(), orc.state()
+    assert np.array_equal(s["r"].cpu().numpy(), o["r"]) and np.array_equal(s["v"].cpu().numpy(), o["v"])
+    assert worst <= 2e-3, worst
+    if random_box:
+        assert np.array_equal(env.boxes().cpu().numpy().astype(np.float64), orc.boxes())
+    st = env.episode_stats()
+    assert st["episodes"] == orc.stats[0] == 2 * n
+    env.close()
 
 
 def test_oracle_env_applies_the_penalty():

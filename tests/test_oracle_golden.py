@@ -44,6 +44,37 @@ def test_oracle_matches_reference_source(name):
     replay(golden_case(G, name))
 
 
+def test_sampled_reset_keeps_float64_until_the_first_step_and_rounds_once():
+    """The reference's own env.seed(123); env.reset() (pioneer_knm_env.py:80-94,107-109): np_random.uniform returns FLOAT64
+    joint angles, `r` stays float64 until the first act(), and because a = v = 0 after a reset that act() stores
+    float32(r0 + 0 + 0): the float64 start is rounded to float32 exactly once.  So rounding the sampled start to float32 at
+    reset time (what the CUDA path and this oracle do) reproduces the reference trajectory BIT FOR BIT."""
+    case = golden_case(G, "sampled")
+    assert list(case["r_dtype_before_first_step"]) == ["float64", "float64"]
+    assert not np.array_equal(case["q0_f64"][0].astype(np.float32).astype(np.float64), case["q0_f64"][0])   # really float64
+    env = OracleEnv(CHAIN, arith="np2")
+    rs = np.random.RandomState(int(case["seed"]))                       # gym.utils.seeding.np_random stand-in of the shim
+    ep = 0
+    for t, action in enumerate(case["actions"]):
+        if t in case["reset_at"]:
+            q0 = rs.uniform(env.r_lo, env.r_hi)                         # the reference's draw order and generator
+            tgt = rs.uniform(np.array(env.config.target_lo), np.array(env.config.target_hi))
+            assert np.array_equal(q0, case["q0_f64"][ep]) and np.array_equal(tgt.astype(np.float32), case["target_f64"][ep].astype(np.float32))
+            env.reset_world(q0, tgt)                                    # rounds the float64 start to float32
+            first = env.observe()
+            # the reset observation of the reference still carries the float64 angles: float32 agreement only
+            np.testing.assert_allclose(first[:126], case["reset_obs"][ep][:126], rtol=0, atol=6e-7)
+            np.testing.assert_allclose(first[126:], case["reset_obs"][ep][126:], rtol=0, atol=2e-5)
+            ep += 1
+        obs, reward, done, truncated = env.step(action)
+        assert np.array_equal(env.r, case["r"][t]) and np.array_equal(env.v, case["v"][t]), t
+        # the reference keeps the sampled TARGET as float64 too (it never passes through a float32 array); the device state
+        # is float32, so target / difference / distance / potential carry its rounding: |d target| <= ulp(25) / 2 = 9.5e-7
+        np.testing.assert_allclose(obs[126:137], case["tail"][t], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(reward, case["reward"][t], rtol=0, atol=2e-5)
+    assert np.array_equal(case["r"][0], case["q0_f64"][0].astype(np.float32))   # step 1 moved nothing: r1 = float32(r0)
+
+
 def test_oracle_reward_knobs():
     replay(golden_case(G, "knobs"), OracleConfig(award_potential_slope=4.0, award_done=7.5, penalty_step=0.02))
 
