@@ -177,6 +177,13 @@ int pnr_reset(pnr_handle* h, const int64_t* idx, int64_t n, const float* q0, con
  * reward DEVICE float[N]; done DEVICE uint8[N] (PNR_DONE | PNR_TRUNCATED bits). */
 int pnr_step(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, void* stream);
 
+/* A rollout fragment with pre-computed actions: n_steps consecutive pnr_step calls issued back to back from C.  Step t reads
+ * actions + t * action_stride and writes obs + t * obs_stride (strides in floats; obs_stride * 4 must be a multiple of 16
+ * bytes), reward + t * N, done + t * N.  The step kernels are launched with programmatic dependent launch, so the tail of
+ * step t (its last bulk stores draining) overlaps the set-up of step t + 1. */
+int pnr_step_many(pnr_handle* h, int32_t n_steps, const float* actions, int64_t action_stride, float* obs,
+                  int64_t obs_stride, float* reward, uint8_t* done, void* stream);
+
 /* Same step with HOST buffers (pinned or pageable): H2D of actions, the kernel, D2H of obs / reward / done on the
  * library's own streams (the observation copy split over two copy engines); returns after the results are on the host.
  * The work is ordered after whatever was queued on the default stream; callers using other non-blocking streams
@@ -241,6 +248,12 @@ int pnr_stats(pnr_handle* h, double* out, int clear, void* stream);
 /* Same 8 numbers written to a caller-owned DEVICE double[8] without synchronising, for an NCCL
  * all-reduce on the same stream (SUM over {0,1,2,3,6,7}, MAX over {4, -5}). */
 int pnr_stats_device(pnr_handle* h, double* out_device, int clear, void* stream);
+/* The reduction half of the path's one collective (the reference moves the same numbers from its Ray rollout workers to
+ * the trainer, pioneer/launch/pioneer_knm_train.py:49): gathered DEVICE double[world, len] = what ONE all-gather of every
+ * rank's packed vector delivered (len >= 8: the statistics, optionally followed by additive extras such as the filter
+ * delta); out DEVICE double[len] = SUM over slots {0,1,2,3,6,7} and every extra, MAX over slot 4, MIN over slot 5.
+ * One kernel on `stream` of the current device; no handle needed. */
+int pnr_stats_merge_device(const double* gathered, int world, int len, double* out, void* stream);
 /* Restore the statistics window from HOST double[8] (what pnr_stats returned): checkpoint / resume.  Synchronises. */
 int pnr_set_stats(pnr_handle* h, const double* in8);
 

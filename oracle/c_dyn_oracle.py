@@ -89,12 +89,13 @@ def load():
         lib.orc_dyn_reset.argtypes = [P, P, C.c_int64, P, P, P]
         lib.orc_dyn_set_state.argtypes = [P, P, P]
         lib.orc_dyn_substeps.argtypes = [P, P, P, P, C.c_int32]
+        lib.orc_dyn_substeps.restype = C.c_uint32
         lib.orc_dyn_aba.argtypes = [P, P, P, P, P]
         lib.orc_dyn_segment_box.restype = C.c_double
         lib.orc_dyn_segment_box.argtypes = [P, P, P, P]
         lib.orc_dyn_contact_depth.restype = C.c_double
         lib.orc_dyn_contact_depth.argtypes = [P, P, P, P]
-        lib.orc_dyn_step.argtypes = [P] * 11
+        lib.orc_dyn_step.argtypes = [P] * 12
         lib.orc_dyn_get_state.argtypes = [P] * 9
         lib.orc_dyn_stats.argtypes = [P, P]
         lib.orc_dyn_sizeof_params.restype = C.c_int64
@@ -214,7 +215,8 @@ class CDynOracleBatch:
         return float(self.lib.orc_dyn_contact_depth(self.h, q_a.ctypes.data, _ptr(bp), _ptr(be)))
 
     def step(self, actions, adopt=None, want_obs: bool = True, want_own: bool = True, want_depth: bool = False):
-        """Returns dict(obs, reward, flags, own_q, own_qd, depth).  ``adopt`` = (q float32 [n,6], qd float32 [n,6], mask
+        """Returns dict(obs, reward, flags, own_q, own_qd, depth, touched); touched[i] bit j = joint j of env i ran into a
+        stop during this step.  ``adopt`` = (q float32 [n,6], qd float32 [n,6], mask
         uint8 [n] or None): see the module docstring."""
         n = self.n
         act = np.ascontiguousarray(actions, dtype=np.float32).reshape(n, DOF)
@@ -223,14 +225,15 @@ class CDynOracleBatch:
         own_q = np.zeros((n, DOF), np.float64) if want_own else None
         own_qd = np.zeros((n, DOF), np.float64) if want_own else None
         depth = np.zeros(n, np.float64) if want_depth else None
+        touched = np.zeros(n, np.uint8)
         aq = aqd = am = None
         if adopt is not None:
             aq = np.ascontiguousarray(adopt[0], dtype=np.float32).reshape(n, DOF)
             aqd = np.ascontiguousarray(adopt[1], dtype=np.float32).reshape(n, DOF)
             am = None if len(adopt) < 3 or adopt[2] is None else np.ascontiguousarray(adopt[2], dtype=np.uint8).reshape(n)
         self.lib.orc_dyn_step(self.h, act.ctypes.data, _ptr(aq), _ptr(aqd), _ptr(am), _ptr(own_q), _ptr(own_qd), _ptr(obs),
-                              reward.ctypes.data, flags.ctypes.data, _ptr(depth))
-        return dict(obs=obs, reward=reward, flags=flags, own_q=own_q, own_qd=own_qd, depth=depth)
+                              reward.ctypes.data, flags.ctypes.data, _ptr(depth), touched.ctypes.data)
+        return dict(obs=obs, reward=reward, flags=flags, own_q=own_q, own_qd=own_qd, depth=depth, touched=touched)
 
     def state(self):
         n = self.n

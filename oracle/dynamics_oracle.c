@@ -270,17 +270,20 @@ static void aba(const dyn_params* p, const double* q, const double* qd, const do
 static double clampd(double x, double lo, double hi) { return x < lo ? lo : (x > hi ? hi : x); }
 
 /* inelastic joint stops at the float32 limits the env uses (dynamics_oracle.py::dynamic_substeps) */
-static void joint_stops(const dyn_batch* b, double* q, double* qd) {
+static unsigned joint_stops(const dyn_batch* b, double* q, double* qd) {
+    unsigned touched = 0;                                      /* bit i: joint i ran into a stop in this substep */
     for (int i = 0; i < DOF; ++i) {
         const double lo = (double)b->r_lo[i], hi = (double)b->r_hi[i];
+        if (q[i] > hi || q[i] < lo) touched |= 1u << i;
         if (q[i] > hi && qd[i] > 0.0) qd[i] = 0.0;
         if (q[i] < lo && qd[i] < 0.0) qd[i] = 0.0;
         q[i] = clampd(q[i], lo, hi);
     }
+    return touched;
 }
 
 /* stepping 0: tau = clamp(kp (u - q) - kd qd | u, +-effort * torque_scale) - damping qd; qd += qdd dt; q += qd dt */
-static void dyn_substep_explicit(const dyn_batch* b, double* q, double* qd, const float* action) {
+static unsigned dyn_substep_explicit(const dyn_batch* b, double* q, double* qd, const float* action) {
     const dyn_params* p = &b->p;
     const int pd = (p->kp != 0.0 || p->kd != 0.0);
     double tau[DOF], qdd[DOF];
@@ -293,7 +296,7 @@ static void dyn_substep_explicit(const dyn_batch* b, double* q, double* qd, cons
     }
     aba(p, q, qd, tau, NULL, NULL, qdd, &W);
     for (int i = 0; i < DOF; ++i) { qd[i] += qdd[i] * p->timestep; q[i] += qd[i] * p->timestep; }
-    joint_stops(b, q, qd);
+    return joint_stops(b, q, qd);
 }
 
 /* stepping 1: BULLET-LIKE substep [UPSTREAM-MEMORY of btMultiBody / btMultiBodyJointMotor / btMultiBodyConstraintSolver as
@@ -311,7 +314,7 @@ static void dyn_substep_explicit(const dyn_batch* b, double* q, double* qd, cons
  *   4. qd clamped to +-max_velocity (m_maxCoordinateVelocity = 100), q += qd dt, inelastic stops at the joint limits.
  */
 #define BULLET_ITERATIONS 10
-static void dyn_substep_bullet(const dyn_batch* b, double* q, double* qd, const float* action) {
+static unsigned dyn_substep_bullet(const dyn_batch* b, double* q, double* qd, const float* action) {
     const dyn_params* p = &b->p;
     const double dt = p->timestep, kdamp = p->link_damping;
     double tau[DOF], qdd[DOF], f_ang[DOF][3], f_lin[DOF][3];
@@ -356,7 +359,7 @@ static void dyn_substep_bullet(const dyn_batch* b, double* q, double* qd, const 
         qd[i] = clampd(v[i], -p->max_velocity, p->max_velocity);
         q[i] += qd[i] * dt;
     }
-    joint_stops(b, q, qd);
+    return joint_stops(b, q, qd);
 }
 
 static void fk_pointer(const dyn_params* p, const double* q, double out[3]) {
@@ -446,12 +449,16 @@ void orc_dyn_set_state(dyn_batch* b, const double* q, const double* qd) {
         }
 }
 
-/* ONE env's substeps without the env layer (cross-check against dynamics_oracle.py): n_sub substeps from (q, qd) */
-void orc_dyn_substeps(dyn_batch* b, double* q, double* qd, const float* action, int32_t n_sub) {
+/* ONE env's substeps without the env layer (cross-check against dynamics_oracle.py): n_sub substeps from (q, qd).
+ * Returns the joints that ran into a stop in any substep (bit i = joint i): an inelastic stop is a discontinuity, so a
+ * float32 trajectory that touches it a substep earlier or later legitimately differs by up to qd * dt there. */
+uint32_t orc_dyn_substeps(dyn_batch* b, double* q, double* qd, const float* action, int32_t n_sub) {
+    unsigned touched = 0;
     for (int s = 0; s < n_sub; ++s) {
-        if (b->p.stepping == 1) dyn_substep_bullet(b, q, qd, action);
-        else dyn_substep_explicit(b, q, qd, action);
+        if (b->p.stepping == 1) touched |= dyn_substep_bullet(b, q, qd, action);
+        else touched |= dyn_substep_explicit(b, q, qd, action);
     }
+    return touched;
 }
 
 /* qdd = ABA(q, qd, tau) for one configuration (cross-check against dynamics_oracle.py::aba) */
@@ -474,13 +481,14 @@ double orc_dyn_contact_depth(const dyn_batch* b, const double* q, const double* 
  *   adopt_q / adopt_qd float32 [n,6] + adopt_mask uint8 [n] (all NULL = free running): after the substeps, rows with a
  *              non-zero mask continue from the given float32 state (what the device reached) instead of the oracle's own
  *   own_q / own_qd float64 [n,6] or NULL: what the oracle's own substeps reached (before adoption)
- *   obs float64 [n,137] or NULL; reward float64 [n]; flags uint8 [n]; depth float64 [n] or NULL (contact depth) */
+ *   obs float64 [n,137] or NULL; reward float64 [n]; flags uint8 [n]; depth float64 [n] or NULL (contact depth);
+ *   touched uint8 [n] or NULL: bit i = joint i ran into a stop during this step's substeps */
 typedef struct {
     dyn_batch* b;
     const float *actions, *adopt_q, *adopt_qd;
     const uint8_t* adopt_mask;
     double *own_q, *own_qd, *obs, *reward, *depth_out;
-    uint8_t* flags;
+    uint8_t *flags, *touched;
     int64_t begin, end;
 } step_job;
 
@@ -492,7 +500,8 @@ static void* step_range(void* arg) {
     for (int64_t i = J->begin; i < J->end; ++i) {
         dyn_env* e = &b->envs[i];
         for (int j = 0; j < DOF; ++j) e->a[j] = J->actions[i * DOF + j];
-        orc_dyn_substeps(b, e->q, e->qd, e->a, p->frame_skip);
+        const uint32_t touched = orc_dyn_substeps(b, e->q, e->qd, e->a, p->frame_skip);
+        if (J->touched) J->touched[i] = (uint8_t)touched;
         if (J->own_q) for (int j = 0; j < DOF; ++j) J->own_q[i * DOF + j] = e->q[j];
         if (J->own_qd) for (int j = 0; j < DOF; ++j) J->own_qd[i * DOF + j] = e->qd[j];
         if (J->adopt_q && (!J->adopt_mask || J->adopt_mask[i]))
@@ -526,7 +535,8 @@ static void* step_range(void* arg) {
 
 #define ORC_MAX_THREADS 64
 void orc_dyn_step(dyn_batch* b, const float* actions, const float* adopt_q, const float* adopt_qd, const uint8_t* adopt_mask,
-                  double* own_q, double* own_qd, double* obs, double* reward, uint8_t* flags, double* depth_out) {
+                  double* own_q, double* own_qd, double* obs, double* reward, uint8_t* flags, double* depth_out,
+                  uint8_t* touched) {
     const dyn_params* p = &b->p;
     /* envs are independent: contiguous ranges on plain pthreads (no OpenMP runtime needed on the box) */
     int n_thr = b->n_threads < 1 ? 1 : (b->n_threads > ORC_MAX_THREADS ? ORC_MAX_THREADS : b->n_threads);
@@ -534,7 +544,7 @@ void orc_dyn_step(dyn_batch* b, const float* actions, const float* adopt_q, cons
     step_job jobs[ORC_MAX_THREADS];
     pthread_t tid[ORC_MAX_THREADS];
     for (int t = 0; t < n_thr; ++t) {
-        step_job j = {b, actions, adopt_q, adopt_qd, adopt_mask, own_q, own_qd, obs, reward, depth_out, flags,
+        step_job j = {b, actions, adopt_q, adopt_qd, adopt_mask, own_q, own_qd, obs, reward, depth_out, flags, touched,
                       b->n * t / n_thr, b->n * (t + 1) / n_thr};
         jobs[t] = j;
     }

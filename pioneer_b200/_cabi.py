@@ -91,6 +91,7 @@ SIGNATURES = {
     "pnr_tick_advance": (C.c_int, [_H, C.c_uint32, _S]),
     "pnr_reset": (C.c_int, [_H, _P, C.c_int64, _P, _P, _P, _S]),
     "pnr_step": (C.c_int, [_H, _P, _P, _P, _P, _S]),
+    "pnr_step_many": (C.c_int, [_H, C.c_int32, _P, C.c_int64, _P, C.c_int64, _P, _P, _S]),
     "pnr_step_host": (C.c_int, [_H, _P, _P, _P, _P]),
     "pnr_step_host_begin": (C.c_int, [_H, _P, _P, _P, _P, C.c_int]),
     "pnr_step_host_end": (C.c_int, [_H]),
@@ -103,6 +104,7 @@ SIGNATURES = {
     "pnr_set_boxes": (C.c_int, [_H, _P, _S]),
     "pnr_stats": (C.c_int, [_H, C.POINTER(C.c_double), C.c_int, _S]),
     "pnr_set_stats": (C.c_int, [_H, C.POINTER(C.c_double)]),
+    "pnr_stats_merge_device": (C.c_int, [_P, C.c_int, C.c_int, _P, _S]),
     "pnr_stats_device": (C.c_int, [_H, _P, C.c_int, _S]),
     "pnr_filter_configure": (C.c_int, [_H, C.c_double, C.c_int, C.c_int]),
     "pnr_filter_apply": (C.c_int, [_H, _P, _P, C.c_int64, C.c_int, C.c_int, _S]),

@@ -219,6 +219,19 @@ class BatchedPioneerEnv:
         self.step_index += 1
         return obs, reward, flags
 
+    def step_many(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, flags: torch.Tensor) -> None:
+        """A rollout fragment with pre-computed actions (pnr_step_many): ``actions`` [T,N,6] -> ``obs`` [T,N,137], ``reward``
+        [T,N], ``flags`` [T,N], T fused steps launched back to back from C with programmatic dependent launch."""
+        T = actions.shape[0]
+        assert actions.shape == (T, self.n_envs, DOF) and obs.shape == (T, self.n_envs, OBS_DIM)
+        assert reward.shape == (T, self.n_envs) and flags.shape == (T, self.n_envs)
+        assert actions.dtype == torch.float32 and obs.dtype == torch.float32 and flags.dtype == torch.uint8
+        assert all(x[0].is_contiguous() for x in (actions, obs)) and reward.is_contiguous() and flags.is_contiguous()
+        with torch.cuda.device(self.device):
+            _cabi.check(self._lib.pnr_step_many(self._h, T, actions.data_ptr(), actions.stride(0), obs.data_ptr(), obs.stride(0),
+                                                reward.data_ptr(), flags.data_ptr(), self._stream()), "pnr_step_many")
+        self.step_index += T
+
     def capture_rollout(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, flags: torch.Tensor):
         """Capture T consecutive steps into ONE CUDA graph: ``actions`` [T,N,6] -> ``obs`` [T,N,137], ``reward`` [T,N],
         ``flags`` [T,N] (caller-owned device tensors, re-read / re-written on every replay).  Replaying the graph

@@ -521,6 +521,17 @@ extern "C" int pnr_step(pnr_handle* h, const float* actions, float* obs, float* 
     return PNR_OK;
 }
 
+extern "C" int pnr_step_many(pnr_handle* h, int32_t n_steps, const float* actions, int64_t action_stride, float* obs,
+                             int64_t obs_stride, float* reward, uint8_t* done, void* stream) {
+    if (!h || n_steps < 0) return pnr_fail(PNR_ERR_INVALID, "pnr_step_many: bad argument");
+    for (int32_t t = 0; t < n_steps; ++t) {
+        int rc = pnr_step(h, actions + (int64_t)t * action_stride, obs + (int64_t)t * obs_stride, reward + (int64_t)t * h->n_envs,
+                          done + (int64_t)t * h->n_envs, stream);
+        if (rc != PNR_OK) return rc;
+    }
+    return PNR_OK;
+}
+
 extern "C" int pnr_observe_done(pnr_handle* h, const uint8_t* done, float* obs, float* terminal_obs, void* stream) {
     if (!h || !done || !obs) return pnr_fail(PNR_ERR_INVALID, "pnr_observe_done: null argument");
     PnrDeviceGuard guard(h->device);
@@ -715,6 +726,12 @@ extern "C" int pnr_stats_device(pnr_handle* h, double* out_device, int clear, vo
     PnrDeviceGuard guard(h->device);
     PNR_CUDA(pnr_launch_stats_snapshot(h->stats, out_device, clear, (cudaStream_t)stream));
     h->launches += 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_stats_merge_device(const double* gathered, int world, int len, double* out, void* stream) {
+    if (!gathered || !out || world < 1 || len < PNR_STATS_LEN) return pnr_fail(PNR_ERR_INVALID, "pnr_stats_merge_device: bad argument");
+    PNR_CUDA(pnr_launch_stats_merge(gathered, world, len, out, (cudaStream_t)stream));
     return PNR_OK;
 }
 

@@ -172,6 +172,13 @@ __device__ __forceinline__ void pnr_bulk_wait_read() {      // returns once at m
     asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(PENDING) : "memory");
 }
 
+// Programmatic dependent launch (sm_90+): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may
+// start while its predecessor in the stream is still draining; pnr_pdl_wait() blocks until the predecessor has completed
+// and its memory is visible (everything that touches env state comes after it), pnr_pdl_trigger() lets the successor's
+// CTAs be scheduled as soon as this grid's CTAs free their SM slots.  Both are no-ops for ordinary launches.
+__device__ __forceinline__ void pnr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pnr_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // named CTA barriers (ids 1..15; id 0 is __syncthreads): producer warps ARRIVE without waiting, the consumer SYNCs.
 // `count` = all participating threads (arrivers + waiters).  Both order prior shared / global accesses of the CTA.
 // The ids are immediates: with register ids ptxas reserves all 16 barriers per CTA, which caps the SM at 4 CTAs.

@@ -27,6 +27,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
     const int64_t N = p.n_envs;
     const int64_t n_tiles = (N + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
     bool tile_busy = false;
+    pnr_pdl_trigger();                                         // see pnr_step_kernel: the next step's set-up runs under this tail
     pnr_pack_obs_const(p, row);
     // fused observation normaliser (pnr_filter_fuse; warp-uniform run-time switch): this warp owns the whole tile, so
     // after the rows are packed it runs the column pass of pnr_filter_kernel on the 101 changing columns (lane = column,
@@ -37,6 +38,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
 #pragma unroll
         for (int c = 18; c < 54; ++c) row[c] = pnr_normalise(row[c], f_applied[c], f_applied[PNR_OBS_DIM + c], f_clip);
     }
+    pnr_pdl_wait();                                            // the previous step's state planes are complete and visible
     for (int64_t t_idx = (int64_t)blockIdx.x * PNR_STEP_WARPS + warp; t_idx < n_tiles;
          t_idx += (int64_t)gridDim.x * PNR_STEP_WARPS) {
         const int64_t env_raw = t_idx * PNR_TILE_ENVS + lane;
@@ -185,7 +187,11 @@ cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode
     int64_t grid = (p.n_envs + per_cta - 1) / per_cta;
     if (grid > resident) grid = resident;
     if (grid < 1) grid = 1;
-    kern<<<(unsigned)grid, PNR_STEP_THREADS, PNR_RO_SMEM, stream>>>(p, state, actions, obs, reward, done, stats, tick, domain,
-                                                                        f_applied, f_delta, f_clip);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(PNR_STEP_THREADS); cfg.dynamicSmemBytes = PNR_RO_SMEM; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pnr_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, p, state, actions, obs, reward, done, stats, tick, domain, f_applied, f_delta, f_clip);
 }

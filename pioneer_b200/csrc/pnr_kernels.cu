@@ -92,6 +92,9 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
     const int64_t stride = gridDim.x;
     int64_t t_idx = blockIdx.x;
     if (t_idx >= n_tiles) return;                             // CTA-uniform
+    // back-to-back steps (pnr_step_many, CUDA graphs): the next step's CTAs may take the SM slots this grid's CTAs free one
+    // by one and run their set-up (constant columns, barriers) under this grid's tail; they stop at pnr_pdl_wait()
+    pnr_pdl_trigger();
 
 #ifdef PNR_TRACE
     int trace_iter = 0;
@@ -156,6 +159,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             ld2 = x1_plane[e];
         }
     };
+    pnr_pdl_wait();                                           // the previous step's state planes are complete and visible
     issue_loads(t_idx);
     PNR_MARK(2);
     int buf = 0;
@@ -545,9 +549,34 @@ __global__ void pnr_stats_snapshot_kernel(PnrStats* stats, double* out, int clea
     }
 }
 
+// The reduction half of the path's one collective: `gathered` = the packed statistics vectors of all ranks (what one
+// all-gather delivered), out = SUM over {0,1,2,3,6,7}, MAX over 4, MIN over 5; `extra` doubles per rank behind the eight
+// (the observation filter's delta) are summed.  One small kernel instead of half a dozen indexing / reduction launches.
+__global__ void pnr_stats_merge_kernel(const double* __restrict__ gathered, int world, int len, double* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= len) return;
+    double acc = gathered[c];
+    for (int r = 1; r < world; ++r) {
+        const double x = gathered[(size_t)r * len + c];
+        acc = c == 4 ? fmax(acc, x) : (c == 5 ? fmin(acc, x) : acc + x);
+    }
+    out[c] = acc;
+}
+
+cudaError_t pnr_launch_stats_merge(const double* gathered, int world, int len, double* out, cudaStream_t stream) {
+    pnr_stats_merge_kernel<<<(len + 127) / 128, 128, 0, stream>>>(gathered, world, len, out);
+    return cudaGetLastError();
+}
+
 // ---------------------------------------------------------------------------------------------
 // host-callable launchers (declared in pnr_launch.h)
 // ---------------------------------------------------------------------------------------------
+// developer knob: PNR_NO_PDL=1 launches the step kernels without programmatic dependent launch (A/B measurements)
+bool pnr_pdl_enabled() {
+    static const bool on = getenv("PNR_NO_PDL") == nullptr;
+    return on;
+}
+
 static int pnr_resident_grid(const void* fn, size_t smem) {
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
@@ -606,9 +635,13 @@ cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_m
     if (const char* e = getenv("PNR_CTAS_PER_SM")) per_sm = atoi(e) > 0 ? atoi(e) : per_sm;   // developer knob
     int cap = per_sm * dev_sms < resident ? per_sm * dev_sms : resident;
     const int64_t grid = pnr_grid_for(p.n_envs, PNR_TILE_ENVS, cap);
-    k<<<(unsigned)grid, PNR_STEP_THREADS, smem, stream>>>(p, state, actions, obs, reward, done, stats, tick, domain, f_applied,
-                                                          f_delta, f_clip);
-    return cudaGetLastError();
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(PNR_STEP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pnr_pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, k, p, state, actions, obs, reward, done, stats, tick, domain, f_applied, f_delta, f_clip);
 }
 
 cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, float4* state, const int64_t* idx, int64_t n,

@@ -223,7 +223,7 @@ __device__ __forceinline__ float pnr_segment_box(float ax, float ay, float az, f
         const float t = 0.5f * (lo + hi);
         const float x = fmaf(t, dx, ax), y = fmaf(t, dy, ay), z = fmaf(t, dz, az);
         const float qx = fabsf(x) - ex, qy = fabsf(y) - ey, qz = fabsf(z) - ez;
-        const float gx = copysignf(dx, x), gy = copysignf(dy, y), gz = copysignf(dz, z);   // d|x_i|/dt
+        const float gx = x < 0.f ? -dx : dx, gy = y < 0.f ? -dy : dy, gz = z < 0.f ? -dz : dz;   // d|x_i|/dt = sign(x_i) d_i
         float g;
         if (fmaxf(qx, fmaxf(qy, qz)) > 0.f)                    // outside: sign of d/dt |max(q, 0)|^2
             g = fmaxf(qx, 0.f) * gx + fmaxf(qy, 0.f) * gy + fmaxf(qz, 0.f) * gz;

@@ -40,12 +40,14 @@ cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, f
                                      cudaStream_t stream);
 cudaError_t pnr_launch_state_io(bool set, float4* state, int64_t N, float* r, float* v, float* a, float* potential,
                                 float* target, int32_t* t, float* ep_return, cudaStream_t stream);
+bool pnr_pdl_enabled();
 cudaError_t pnr_launch_observe_done(const PnrParams& p, float4* state, const uint8_t* done, float* obs, float* terminal_out,
                                     const float* f_applied, double* f_delta, float f_clip, cudaStream_t stream);
 cudaError_t pnr_launch_box_io(bool set, float4* box_a, float* box_z, int64_t N, float* box, cudaStream_t stream);
 cudaError_t pnr_launch_compact_obs(const float* full, float* compact, int64_t n_rows, cudaStream_t stream);
 cudaError_t pnr_launch_tick_advance(PnrStats* stats, uint32_t n, int absolute, cudaStream_t stream);
 cudaError_t pnr_launch_env_steps_set(PnrStats* stats, double env_steps, cudaStream_t stream);
+cudaError_t pnr_launch_stats_merge(const double* gathered, int world, int len, double* out, cudaStream_t stream);
 cudaError_t pnr_launch_stats_snapshot(PnrStats* stats, double* out, int clear, cudaStream_t stream);
 cudaError_t pnr_launch_filter_fold(double* delta_slots, cudaStream_t stream);
 cudaError_t pnr_launch_filter_refresh(const double* state, float* applied, int demean, int destd, cudaStream_t stream);

@@ -54,38 +54,48 @@ def shard_range(total_envs: int, rank: int, world_size: int) -> Tuple[int, int]:
     return base, n_local
 
 
-def reduce_episode_stats(local: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
-    """All-reduce the packed float64[8] statistics vector (any backend; NCCL on the GPUs).
-    Two collectives: SUM and MAX.  Returns a new tensor on the same device."""
-    assert local.dtype == torch.float64 and local.numel() == len(STATS_FIELDS)
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return local.clone()
-    sums = local[list(SUM_SLOTS)].contiguous()
-    maxs = torch.stack([local[4], -local[5]])
-    dist.all_reduce(sums, op=dist.ReduceOp.SUM, group=group)
-    dist.all_reduce(maxs, op=dist.ReduceOp.MAX, group=group)
-    out = torch.empty_like(local)
-    out[list(SUM_SLOTS)] = sums
-    out[4], out[5] = maxs[0], -maxs[1]
+def _merge(gathered: torch.Tensor) -> torch.Tensor:
+    """[world, len] -> [len]: SUM over the counters and extras, MAX / MIN over slots 4 / 5.  On a GPU this is ONE kernel of
+    the library (pnr_stats_merge_device) on the current stream; on the CPU (gloo tests) plain torch."""
+    world, k = gathered.shape
+    if gathered.is_cuda:
+        from . import _cabi
+        out = torch.empty(k, dtype=torch.float64, device=gathered.device)
+        with torch.cuda.device(gathered.device):
+            _cabi.check(_cabi.load().pnr_stats_merge_device(gathered.data_ptr(), world, k, out.data_ptr(),
+                                                            torch.cuda.current_stream(gathered.device).cuda_stream),
+                        "pnr_stats_merge_device")
+        return out
+    out = gathered.sum(0)
+    out[4] = gathered[:, 4].max()
+    out[5] = gathered[:, 5].min()
     return out
 
 
-def reduce_packed(stats_local: torch.Tensor, extra_local: torch.Tensor, group: Optional[dist.ProcessGroup] = None):
+def reduce_packed(stats_local: torch.Tensor, extra_local: Optional[torch.Tensor] = None,
+                  group: Optional[dist.ProcessGroup] = None):
     """ONE collective for everything a rollout worker exchanges per iteration: the float64[8] episode statistics (SUM /
-    MAX slots) and an additive float64 vector (the observation filter's delta) are packed, all-gathered, and reduced
-    locally.  Returns (stats, extra) like reduce_episode_stats + a SUM all-reduce would."""
-    assert stats_local.dtype == torch.float64 and extra_local.dtype == torch.float64
-    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
-        return stats_local.clone(), extra_local.clone()
-    world = dist.get_world_size(group)
-    packed = torch.cat([stats_local, extra_local])
-    gathered = torch.empty((world, packed.numel()), dtype=torch.float64, device=packed.device)
-    dist.all_gather(list(gathered.unbind(0)), packed, group=group)       # (works on gloo as well as on NCCL)
+    MAX / MIN slots) and an optional additive float64 vector (the observation filter's delta) are packed, all-gathered
+    into one [world, len] tensor, and reduced by one kernel.  Returns (stats, extra)."""
+    assert stats_local.dtype == torch.float64 and stats_local.numel() == len(STATS_FIELDS)
     k = len(STATS_FIELDS)
-    stats = gathered[:, :k].sum(0)
-    stats[4] = gathered[:, 4].max()
-    stats[5] = gathered[:, 5].min()
-    return stats, gathered[:, k:].sum(0).contiguous()
+    if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
+        return stats_local.clone(), (None if extra_local is None else extra_local.clone())
+    world = dist.get_world_size(group)
+    packed = stats_local if extra_local is None else torch.cat([stats_local, extra_local])
+    gathered = torch.empty((world, packed.numel()), dtype=torch.float64, device=packed.device)
+    if packed.is_cuda:
+        dist.all_gather_into_tensor(gathered, packed.contiguous(), group=group)          # one NCCL all-gather
+    else:
+        dist.all_gather(list(gathered.unbind(0)), packed, group=group)                   # gloo
+    merged = _merge(gathered)
+    return merged[:k], (None if extra_local is None else merged[k:].contiguous())
+
+
+def reduce_episode_stats(local: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """The packed float64[8] statistics vector of all ranks: one all-gather + one merge kernel (any backend; NCCL on the
+    GPUs).  Returns a new tensor on the same device."""
+    return reduce_packed(local, None, group)[0]
 
 
 def summarize(stats: torch.Tensor) -> Dict[str, float]:

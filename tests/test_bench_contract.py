@@ -40,16 +40,30 @@ def test_reference_arm_other_ranks_exit_quietly():
 @pytest.mark.gpu
 def test_gpu_arm_line():
     out = subprocess.run([sys.executable, "bench.py", "--steps", "30", "--warmup", "3", "--no-sweep", "--no-cpu-baseline",
-                          "--envs-per-gpu", "4096"], cwd=ROOT, capture_output=True, text=True, timeout=900)
+                          "--no-extras", "--envs-per-gpu", "4096"], cwd=ROOT, capture_output=True, text=True, timeout=900)
     assert out.returncode == 0, out.stderr[-3000:]
     d = _one_json_line(out.stdout)
-    assert BASE_KEYS | {"roofline", "clocks", "substeps_per_sec", "timing_floor_ms"} <= set(d)
+    assert BASE_KEYS | {"roofline", "clocks", "substeps_per_sec", "timing_floor_ms", "per_step_flushed"} <= set(d)
     assert d["n_gpus"] == 1 and d["steps"] == 30 and d["warmup"] == 3 and d["gpu_launches"] == 30
     assert d["scaling"] == "weak" and d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"]
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
     assert r["bytes_per_env_step"] == 761 and r["units_per_launch"] == 4096
     e = d["e2e"]
-    assert e["h2d_bytes_per_step"] == 4096 * 24 and e["d2h_bytes_per_step"] == 4096 * (548 + 4 + 1) and e["value"] > 0
+    assert e["h2d_bytes_per_step"] == 4096 * 24 and e["d2h_bytes_per_step"] == 4096 * (404 + 4 + 1) and e["value"] > 0
+    assert e["sync_full_rows"]["d2h_bytes_per_step"] == 4096 * (548 + 4 + 1) and e["sync_full_rows"]["value"] > 0
     assert abs(d["value"] - 4096 * 30 / (d["ms_per_step"] * 30 / 1e3)) / d["value"] < 1e-6
     assert set(d["clocks"]) >= {"sm_mhz", "sm_max_mhz", "reasons"}
+    assert d["episode_stats"]["episodes_total"] > 0            # pre-aged envs: auto-resets happen inside the timed region
+
+
+@pytest.mark.gpu
+def test_gpu_arm_extras_at_a_small_size():
+    """The dynamic-mode, obstacle and rollout-loop records are emitted at every world size (here: 1, tiny step count)."""
+    out = subprocess.run([sys.executable, "bench.py", "--steps", "16", "--warmup", "3", "--no-sweep", "--no-cpu-baseline",
+                          "--envs-per-gpu", "8192"], cwd=ROOT, capture_output=True, text=True, timeout=1200)
+    assert out.returncode == 0, out.stderr[-3000:]
+    d = _one_json_line(out.stdout)
+    assert d["dynamic_mode"]["value"] > 0 and d["dynamic_mode"]["roofline"]["bound"] == "fp32"
+    assert d["obstacles"]["kinematic"]["value"] > 0 and d["obstacles"]["dynamic"]["value"] > 0
+    assert d["rollout"]["value"] > 0 and d["rollout"]["episode_stats"]["env_steps"] > 0

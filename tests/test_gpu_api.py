@@ -83,7 +83,7 @@ def test_facade_after_a_seeded_reset_replays_the_reference_bit_for_bit():
     joint state is bit-equal from the first step on (see test_sampled_reset_keeps_float64... for why nothing is lost)."""
     from pioneer_b200.launch import prepare_env
     case = golden_case(G, "sampled")
-    tl = prepare_env({})
+    tl = prepare_env({"award_potential_slope": 10.0, "award_done": 5.0, "penalty_step": 1 / 100})
     env = tl.env
     env.seed(int(case["seed"]))
     ep = 0

@@ -9,9 +9,13 @@ before the step, reports where its own float64 substeps arrive (compared with th
 ADOPTS the device's float32 post-step state, so that the env layer -- reward, done / TimeLimit flags, observation,
 statistics, Philox auto-reset -- is compared on identical inputs: flags BIT-EXACT, like the kinematic mode.
 
-Bars per env step (10 substeps, float32 vs float64): |dq| <= 2e-5 + 2e-6 |q|,  |dqd| <= 2e-4 + 2e-5 |qd|;
-observation: value columns r, v, a bit-exact, every other column <= 1e-3 (pointer xyz <= 2e-4 + |dq| propagated);
-reward <= 2e-3; episode statistics: counts exact, sums to float32 accumulation."""
+Bars per env step (10 substeps, float32 vs float64) for every env that stayed clear of the joint stops on both sides during
+the step: |dq| <= 5e-6 + 5e-7 |q|,  |dqd| <= 5e-5 + 5e-6 |qd|  (measured on B200 at 65,536 envs x 200 steps: 1.1e-6 and 2.0e-5
+with |qd| up to 26 rad/s).  An inelastic stop is a discontinuity (qd := 0): an env in which either side ran into one may
+differ by qd * dt in that step, so those (env, step) pairs -- 8 % under PD control with random set points -- are checked
+through the env layer only and their share is asserted.
+Observation: value columns r, v, a, r_lo, r_hi, target bit-exact; cos / sin columns <= 1e-6; pointer xyz / distance <= 2e-4;
+potential <= 1e-3; reward <= 2e-3; episode statistics: counts exact, sums to float32 accumulation."""
 import numpy as np
 import pytest
 
@@ -55,7 +59,7 @@ def lockstep(env, orc, steps, action_fn, obs_mode="terminal", check_every=1):
     assert np.array_equal(s0["r"].cpu().numpy().astype(np.float64), o0["q"])         # same Philox reset draws
     assert np.array_equal(s0["target"].cpu().numpy().astype(np.float64), o0["target"])
     worst = {}
-    n_done = 0
+    n_done = pairs = free_pairs = 0
     for t in range(steps):
         act = action_fn(t)
         obs, reward, flags = env.step_tensor(torch.as_tensor(act).cuda())
@@ -67,28 +71,43 @@ def lockstep(env, orc, steps, action_fn, obs_mode="terminal", check_every=1):
             st = env.state()
             q32, qd32 = st["r"].cpu().numpy(), st["v"].cpu().numpy()
         out = orc.step(act, adopt=(q32, qd32, None if mask is None else mask.astype(np.uint8)), want_obs=(t % check_every == 0))
-        # ---- the dynamics: where float64 arrives from the same float32 start
-        sel = slice(None) if mask is None else mask
-        dq = np.abs(q32.astype(np.float64) - out["own_q"])[sel]
-        dqd = np.abs(qd32.astype(np.float64) - out["own_qd"])[sel]
-        bar_q = 2e-5 + 2e-6 * np.abs(out["own_q"][sel])
-        bar_qd = 2e-4 + 2e-5 * np.abs(out["own_qd"][sel])
-        assert (dq <= bar_q).all(), (t, float(dq.max()), np.unravel_index(np.argmax(dq - bar_q), dq.shape))
-        assert (dqd <= bar_qd).all(), (t, float(dqd.max()), float(np.abs(out["own_qd"]).max()))
-        worst["dq"] = max(worst.get("dq", 0.0), float(dq.max()))
-        worst["dqd"] = max(worst.get("dqd", 0.0), float(dqd.max()))
-        worst["qd_abs"] = max(worst.get("qd_abs", 0.0), float(np.abs(out["own_qd"]).max()))
+        # ---- the dynamics: where float64 arrives from the same float32 start.  An inelastic joint stop is a discontinuity
+        # (qd := 0): an env in which either side ran into a stop during this step may legitimately differ by qd * dt, so the
+        # bars apply to the envs that stayed clear of the stops on both sides; the others are counted
+        at_stop = ((q32 <= env.r_lo) | (q32 >= env.r_hi)).any(axis=1)
+        free = (out["touched"] == 0) & ~at_stop
+        if mask is not None:
+            free &= mask
+        pairs += int(n if mask is None else mask.sum())
+        free_pairs += int(free.sum())
+        dq = np.abs(q32.astype(np.float64) - out["own_q"])[free]
+        dqd = np.abs(qd32.astype(np.float64) - out["own_qd"])[free]
+        if dq.size:
+            bar_q = 5e-6 + 5e-7 * np.abs(out["own_q"][free])
+            bar_qd = 5e-5 + 5e-6 * np.abs(out["own_qd"][free])
+            if not (dq <= bar_q).all() or not (dqd <= bar_qd).all():
+                i, j = np.unravel_index(np.argmax(dq / bar_q), dq.shape)
+                i2, j2 = np.unravel_index(np.argmax(dqd / bar_qd), dqd.shape)
+                rows = np.nonzero(free)[0]
+                raise AssertionError(f"step {t}: dq {dq[i, j]:.3e} (bar {bar_q[i, j]:.3e}) env {rows[i]} joint {j} qd "
+                                     f"{out['own_qd'][rows[i]]}; dqd {dqd[i2, j2]:.3e} (bar {bar_qd[i2, j2]:.3e}) env {rows[i2]} "
+                                     f"joint {j2} qd {out['own_qd'][rows[i2]]} q {out['own_q'][rows[i2]]} act {act[rows[i2]]}")
+            worst["dq"] = max(worst.get("dq", 0.0), float(dq.max()))
+            worst["dqd"] = max(worst.get("dqd", 0.0), float(dqd.max()))
+            worst["qd_abs"] = max(worst.get("qd_abs", 0.0), float(np.abs(out["own_qd"][free]).max()))
         # ---- the env layer on identical inputs
         assert np.array_equal(flags, out["flags"]), (t, int((flags != out["flags"]).sum()))
         dr = np.abs(reward.astype(np.float64) - out["reward"])
         if mask is not None:
             dr = dr[mask]                                                             # finished rows: the oracle used its own q
-        assert dr.max() <= 2e-3, (t, float(dr.max()))
-        worst["reward"] = max(worst.get("reward", 0.0), float(dr.max()))
+        if dr.size:
+            assert dr.max() <= 2e-3, (t, float(dr.max()))
+            worst["reward"] = max(worst.get("reward", 0.0), float(dr.max()))
         if out["obs"] is not None:
             check_obs(obs, out["obs"], worst)
         n_done += int((flags & 1).sum())
     assert worst.get("trig", 0.0) <= 1e-6 and worst.get("ptr", 0.0) <= 2e-4 and worst.get("pot", 0.0) <= 1e-3, worst
+    worst["free_fraction"] = free_pairs / max(pairs, 1)
     # ---- after the run: the reset envs carry the oracle's Philox draws, counters and statistics agree
     s, o = env.state(), orc.state()
     assert np.array_equal(s["t"].cpu().numpy(), o["t"])
@@ -124,7 +143,7 @@ def test_config3_65536_envs_pd_control_timelimit_autoreset():
     with TimeLimit 64 => every env goes through three episode ends and Philox resets."""
     env, orc = make(65536, limit=64, seed=12, **PD)
     worst, n_done = lockstep(env, orc, 200, setpoints(env, 1), check_every=10)
-    assert n_done == 3 * 65536
+    assert n_done == 3 * 65536 and worst["free_fraction"] > 0.85
     print("config3 dynamic parity, worst:", worst)
     env.close()
 
@@ -132,7 +151,8 @@ def test_config3_65536_envs_pd_control_timelimit_autoreset():
 def test_autoreset_observation_mode_at_16384_envs():
     env, orc = make(16384, obs_mode="autoreset", limit=40, seed=5, env_id_base=1 << 33, **PD)
     worst, n_done = lockstep(env, orc, 100, setpoints(env, 2), obs_mode="autoreset", check_every=5)
-    assert n_done == 2 * 16384
+    assert n_done == 2 * 16384 and worst["free_fraction"] > 0.85
+    print("autoreset mode, worst:", worst)
     env.close()
 
 
@@ -143,6 +163,8 @@ def test_torque_control_with_gravity():
     tau_max = (np.asarray(env.chain.effort) * 40.0).astype(np.float32)
     assert np.array_equal(env.action_space.high, tau_max)                            # the action space of this mode
     worst, _ = lockstep(env, orc, 60, lambda t: (rng.uniform(-1.2, 1.2, size=(n, 6)) * tau_max).astype(np.float32))
+    print("torque control, worst:", worst)
+    assert worst["free_fraction"] > 0.05          # under gravity most arms end up resting on a stop; the rest is compared
     env.close()
 
 
@@ -151,7 +173,8 @@ def test_config4_16384_envs_with_the_demo_obstacles():
     from pioneer_b200 import demo_obstacles
     env, orc = make(16384, limit=50, obstacles=demo_obstacles(), penalty=0.5, seed=9, **PD)
     worst, n_done = lockstep(env, orc, 100, setpoints(env, 3), check_every=5)
-    assert n_done == 2 * 16384
+    assert n_done == 2 * 16384 and worst["free_fraction"] > 0.85
+    print("config4 dynamic parity, worst:", worst)
     env.close()
 
 
@@ -168,12 +191,14 @@ def test_per_env_random_box_in_dynamic_mode():
 
 def test_free_running_drift_is_bounded_under_pd_control():
     """No adoption: the float64 oracle free-runs beside 8,192 envs for 300 steps (TimeLimit 100, auto-reset).  PD control
-    contracts, so the float32 trajectory stays within 2e-3 rad of the float64 one; flags may only differ where the distance
-    sits within that drift of the done threshold (never, for random targets)."""
+    contracts, so the float32 trajectory stays near the float64 one: 99.9 % of the envs within 2e-3 rad at every check, every
+    env within 5e-2 (an inelastic joint stop is a discontinuity: when one side touches it a substep earlier than the other
+    the two differ by up to qd * dt until the controller pulls them together again); flags may only differ where the
+    distance sits within that drift of the done threshold (never, for random targets)."""
     n = 8192
     env, orc = make(n, limit=100, seed=31, **PD)
     fn = setpoints(env, 7, hold=50)
-    worst = 0.0
+    worst, worst_q999 = 0.0, 0.0
     for t in range(300):
         act = fn(t)
         obs, reward, flags = env.step_tensor(torch.as_tensor(act).cuda())
@@ -183,6 +208,9 @@ def test_free_running_drift_is_bounded_under_pd_control():
         assert not diff.any(), (t, int(diff.sum()))
         if t % 10 == 9:
             q = obs[:, 0:6].cpu().numpy().astype(np.float64)
-            worst = max(worst, float(np.abs(q - out["own_q"]).max()))
-    assert worst <= 2e-3, worst
+            err = np.abs(q - out["own_q"]).max(axis=1)
+            worst = max(worst, float(err.max()))
+            worst_q999 = max(worst_q999, float(np.quantile(err, 0.999)))
+    print("free-running drift: worst", worst, "99.9 % quantile", worst_q999)
+    assert worst <= 5e-2 and worst_q999 <= 2e-3, (worst, worst_q999)
     env.close()
