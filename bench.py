@@ -554,7 +554,10 @@ def ours_arm(args):
         checksum += float(h_reward[0])
     torch.cuda.synchronize()
     e2e_sync_s = max_over_ranks(time.perf_counter() - t0)
-    env.step_host_begin(host_actions[0], compact=True)
+    env.step_host_begin(host_actions[0], compact=True)          # warm-up: both staging slots, both pinned buffer sets
+    for k in range(6):
+        env.step_host_begin(host_actions[(k + 1) % 4], compact=True)
+        env.step_host_end()
     env.step_host_end()
     barrier()
     t0 = time.perf_counter()
@@ -757,9 +760,10 @@ def rollout_loop(torch, dist, device, rank, world, max_over_ranks, barrier, n=13
     from pioneer_b200.distributed import summarize
     from pioneer_b200.rollout import RolloutWorker
     env = BatchedPioneerEnv(n, device=device, seed=0, env_id_base=rank * n, batch_config=BatchConfig(max_episode_steps=500))
-    pre_age(torch, env, 500, 11 + rank)
     torch.cuda.manual_seed(1234 + rank)
     worker = RolloutWorker(env, fragment_length=fragment, seed=rank, cuda_graph=True)
+    worker.collect()                               # the first fragment starts with env.reset()
+    pre_age(torch, env, 500, 11 + rank)            # ... then the envs get their steady-state ages
     for _ in range(3):
         worker.collect()
         worker.sync(summary=False)

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(LIB_DIR, "libpioneer_b200.so")
-SOURCES = ["pnr_kernels.cu", "pnr_dynamic.cu", "pnr_filter.cu", "pnr_api.cu"]
+SOURCES = ["pnr_kernels.cu", "pnr_dynamic.cu", "pnr_dynamic_bullet.cu", "pnr_filter.cu", "pnr_api.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "--threads", "4",
               "-Xcompiler", "-fPIC,-O2", "-shared"]
 

@@ -52,6 +52,11 @@ struct PnrParams {
     float dyn_tip_I[6], dyn_tip_H[9], dyn_tip_M[6], dyn_tip_ua[3], dyn_tip_ul[3], dyn_tip_dinv;
     float dyn_kp, dyn_kd, dyn_dt, dyn_gravity;
     int32_t dyn_frame_skip, dyn_use_pd;
+    // opt-in Bullet-like substep (PNR_STEPPING_BULLET; oracle/dynamics_oracle.c::dyn_substep_bullet)
+    int32_t dyn_stepping;
+    float dyn_com[PNR_DOF][3];      // centre of mass of each composite body, moving-frame coordinates
+    float dyn_icom[PNR_DOF][6];     // rotational inertia about the centre of mass: xx xy xz yy yz zz
+    float dyn_link_damping, dyn_max_velocity, dyn_motor_kp, dyn_motor_kd, dyn_motor_impulse;   // impulse = force * dt
     int32_t chain_kind;             // 1: axes Z Y Y X Y X, positive, identity origin rotations (the shipped robot)
     int32_t dyn_iso_links;          // 1: every link but the tip has its centre of mass on the frame origin and an isotropic inertia
     // obstacle variant: link capsules (moving-frame coordinates) against static plane / box / sphere obstacles
@@ -178,6 +183,39 @@ __device__ __forceinline__ void pnr_bulk_wait_read() {      // returns once at m
 // CTAs be scheduled as soon as this grid's CTAs free their SM slots.  Both are no-ops for ordinary launches.
 __device__ __forceinline__ void pnr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pnr_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Tile-level chaining of consecutive steps (pnr_step_many).  Envs are independent, so tile i of step t + 1 depends on tile
+// i of step t and on nothing else: instead of the grid-wide pnr_pdl_wait() a chained step spins, per tile, on a sequence
+// word that the previous step publishes (release) right after it has stored the tile's state planes.  With programmatic
+// dependent launch the next step's CTAs take the SM slots the current step frees one by one and start on their tiles at
+// once, so the ragged end of one step (wave quantisation: 2,048 tiles over 592 schedulers) is filled with the next step's
+// work.  `wait` / `publish` are (call epoch << 8 | step), unique per pnr_step_many call; 0 = not chained.
+struct PnrChain { uint32_t* seq; uint32_t wait, publish, late_trigger; };
+__device__ __forceinline__ void pnr_chain_wait(const PnrChain& c, int64_t tile, int lane) {
+    if (c.wait) {                                              // launch-uniform
+        if (lane == 0) {
+            const uint32_t* w = c.seq + tile;
+            uint32_t v;
+            for (;;) {
+                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
+                if (v == c.wait) break;
+#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 700
+                __nanosleep(64);
+#endif
+            }
+        }
+        __syncwarp();
+    }
+}
+__device__ __forceinline__ void pnr_chain_publish(const PnrChain& c, int64_t tile, int lane) {
+    if (c.publish) {
+        __syncwarp();                                          // every lane's state stores are ordered before the release
+        if (lane == 0) {
+            __threadfence();
+            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(c.seq + tile), "r"(c.publish) : "memory");
+        }
+    }
+}
 
 // named CTA barriers (ids 1..15; id 0 is __syncthreads): producer warps ARRIVE without waiting, the consumer SYNCs.
 // `count` = all participating threads (arrivers + waiters).  Both order prior shared / global accesses of the CTA.

@@ -198,9 +198,11 @@ struct PnrDynWork {                 // per-joint quantities kept between the thr
 // qdd = ABA(q, qd, tau); gravity acts along -z of the base frame.  Any serial 6-revolute chain (CHAIN = GENERIC reads the
 // axis codes at run time); with CHAIN = PIONEER this is the first specialisation (kept as the A/B baseline of
 // pnr_aba_pioneer below, tests/csrc/aba_check.cu).
-template <int CHAIN>
-PNR_HD void pnr_aba_general(const PnrParams& p, const float (&q)[PNR_DOF], const float (&qd)[PNR_DOF],
-                                        const float (&tau)[PNR_DOF], float (&qdd)[PNR_DOF]) {
+// LINKDAMP adds Bullet's per-link damping as an external force on every body (PNR_STEPPING_BULLET): at the centre of mass,
+// force -m v_com (k + k |v_com|) and torque -(I_com w) (k + k |w|), k = dyn_link_damping.
+template <int CHAIN, bool LINKDAMP>
+PNR_HD void pnr_aba_general_ext(const PnrParams& p, const float (&q)[PNR_DOF], const float (&qd)[PNR_DOF],
+                                const float (&tau)[PNR_DOF], float gravity, float (&qdd)[PNR_DOF]) {
     PnrDynWork w;
     // ---- pass 1 (base -> tip): velocities, velocity-product accelerations, bias forces
     V3 om = v3(0.f, 0.f, 0.f), vl = v3(0.f, 0.f, 0.f);
@@ -219,6 +221,17 @@ PNR_HD void pnr_aba_general(const PnrParams& p, const float (&q)[PNR_DOF], const
         const V3 f = vl * p.dyn_mass[i] - cross(mc, om);
         w.p_ang[i] = cross(om, n) + cross(vl, f);
         w.p_lin[i] = cross(om, f);
+        if (LINKDAMP) {
+            const float kd = p.dyn_link_damping;
+            const V3 com = v3(p.dyn_com[i][0], p.dyn_com[i][1], p.dyn_com[i][2]);
+            const V3 vc = vl + cross(om, com);
+            const float lin = fmaf(kd, sqrtf(dot(vc, vc)), kd), ang = fmaf(kd, sqrtf(dot(om, om)), kd);
+            const Sym3 Ic = {p.dyn_icom[i][0], p.dyn_icom[i][1], p.dyn_icom[i][2], p.dyn_icom[i][3], p.dyn_icom[i][4], p.dyn_icom[i][5]};
+            const V3 fe = vc * (-lin * p.dyn_mass[i]);
+            const V3 ne = symmul(Ic, om) * (-ang) + cross(com, fe);
+            w.p_ang[i] = w.p_ang[i] - ne;
+            w.p_lin[i] = w.p_lin[i] - fe;
+        }
     }
     // ---- pass 2 (tip -> base): articulated inertias and bias forces
     Sym3 I, M;
@@ -300,7 +313,7 @@ PNR_HD void pnr_aba_general(const PnrParams& p, const float (&q)[PNR_DOF], const
         }
     }
     // ---- pass 3 (base -> tip): accelerations.  The base "accelerates" by -g: a_lin = (0, 0, +gravity)
-    V3 aa = v3(0.f, 0.f, 0.f), al = v3(0.f, 0.f, p.dyn_gravity);
+    V3 aa = v3(0.f, 0.f, 0.f), al = v3(0.f, 0.f, gravity);
 #pragma unroll (CHAIN == 0 ? 1 : 6)   // GENERIC: rolled joint loops (the unrolled body does not fit the instruction cache)
     for (int i = 0; i < PNR_DOF; ++i) {
         const V3 t = al - pnr_origin_cross<CHAIN>(p, i, aa);
@@ -309,6 +322,12 @@ PNR_HD void pnr_aba_general(const PnrParams& p, const float (&q)[PNR_DOF], const
         qdd[i] = (w.u[i] - dot(w.u_ang[i], aa) - dot(w.u_lin[i], al)) * w.dinv[i];
         aa = aa + pnr_axis_scaled<CHAIN>(p, i, qdd[i]);
     }
+}
+
+template <int CHAIN>
+PNR_HD void pnr_aba_general(const PnrParams& p, const float (&q)[PNR_DOF], const float (&qd)[PNR_DOF],
+                            const float (&tau)[PNR_DOF], float (&qdd)[PNR_DOF]) {
+    pnr_aba_general_ext<CHAIN, false>(p, q, qd, tau, p.dyn_gravity, qdd);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -659,23 +678,83 @@ PNR_HD float pnr_control_torque(const PnrParams& p, int i, float action, float q
     return fmaf(-p.dyn_damping[i], qd, tau);
 }
 
-// frame_skip substeps of semi-implicit Euler: qd += qdd dt; q += qd dt; inelastic stops at the joint limits
+// inelastic stops at the joint limits
+PNR_HD void pnr_joint_stop(const PnrParams& p, int i, float& x, float& v) {
+    if (x > p.r_hi[i]) { x = p.r_hi[i]; if (v > 0.f) v = 0.f; }
+    if (x < p.r_lo[i]) { x = p.r_lo[i]; if (v < 0.f) v = 0.f; }
+}
+
+// PNR_STEPPING_BULLET: one Bullet-like substep, float32 twin of oracle/dynamics_oracle.c::dyn_substep_bullet (restated from
+// memory of btMultiBody / btMultiBodyJointMotor, unpinned): per-link damping + URDF joint damping -> unconstrained velocity;
+// POSITION_CONTROL motors as velocity-level constraints (target positionGain (u - q) / dt + (1 - velocityGain) v*, impulse
+// limit force * dt) solved by PNR_BULLET_ITERATIONS sweeps of projected Gauss-Seidel on A = M(q)^-1, whose columns are the
+// responses to unit joint impulses (one ABA call each: qd = 0, g = 0, tau = e_j); +-max_velocity clamp; stops.
+// Opt-in and seven ABA evaluations per substep: correctness first, the joint loop over the unit impulses is rolled.
+#define PNR_BULLET_ITERATIONS 10
 template <int CHAIN>
+PNR_HD void pnr_bullet_substep(const PnrParams& p, float (&q)[PNR_DOF], float (&qd)[PNR_DOF], const float (&action)[PNR_DOF]) {
+    float tau[PNR_DOF], qdd[PNR_DOF], v[PNR_DOF];
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) tau[i] = -p.dyn_damping[i] * qd[i];
+    pnr_aba_general_ext<CHAIN, true>(p, q, qd, tau, p.dyn_gravity, qdd);
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) v[i] = fmaf(qdd[i], p.dyn_dt, qd[i]);
+    if (p.dyn_motor_impulse > 0.f) {
+        float A[PNR_DOF][PNR_DOF], rhs[PNR_DOF], lam[PNR_DOF];
+        const float zero[PNR_DOF] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 1
+        for (int j = 0; j < PNR_DOF; ++j) {
+            float e[PNR_DOF], col[PNR_DOF];
+#pragma unroll
+            for (int i = 0; i < PNR_DOF; ++i) e[i] = i == j ? 1.f : 0.f;
+            pnr_aba_general_ext<CHAIN, false>(p, q, zero, e, 0.f, col);
+#pragma unroll
+            for (int i = 0; i < PNR_DOF; ++i) A[i][j] = col[i];
+            rhs[j] = fmaf(p.dyn_motor_kp / p.dyn_dt, action[j] - q[j], (1.f - p.dyn_motor_kd) * v[j]);
+            lam[j] = 0.f;
+        }
+        const float max_imp = p.dyn_motor_impulse;
+#pragma unroll 1
+        for (int it = 0; it < PNR_BULLET_ITERATIONS; ++it)
+#pragma unroll 1
+            for (int j = 0; j < PNR_DOF; ++j) {
+                float dl = (rhs[j] - v[j]) / A[j][j];
+                const float nl = fminf(fmaxf(lam[j] + dl, -max_imp), max_imp);
+                dl = nl - lam[j];
+                lam[j] = nl;
+#pragma unroll
+                for (int i = 0; i < PNR_DOF; ++i) v[i] = fmaf(A[i][j], dl, v[i]);
+            }
+    }
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) {
+        float vi = fminf(fmaxf(v[i], -p.dyn_max_velocity), p.dyn_max_velocity);
+        float x = fmaf(vi, p.dyn_dt, q[i]);
+        pnr_joint_stop(p, i, x, vi);
+        q[i] = x; qd[i] = vi;
+    }
+}
+
+// frame_skip substeps.  STEPPING = PNR_STEPPING_EXPLICIT: semi-implicit Euler, qd += qdd dt; q += qd dt, stops at the limits
+template <int CHAIN, int STEPPING = PNR_STEPPING_EXPLICIT>
 PNR_HD void pnr_dynamic_substeps(const PnrParams& p, float (&q)[PNR_DOF], float (&qd)[PNR_DOF],
                                                      const float (&action)[PNR_DOF]) {
 #pragma unroll 1
     for (int sub = 0; sub < p.dyn_frame_skip; ++sub) {
-        float tau[PNR_DOF], qdd[PNR_DOF];
+        if (STEPPING == PNR_STEPPING_BULLET) {
+            pnr_bullet_substep<CHAIN == PNR_CHAIN_PIONEER_ISO ? PNR_CHAIN_PIONEER : CHAIN>(p, q, qd, action);
+        } else {
+            float tau[PNR_DOF], qdd[PNR_DOF];
 #pragma unroll
-        for (int i = 0; i < PNR_DOF; ++i) tau[i] = pnr_control_torque(p, i, action[i], q[i], qd[i]);
-        pnr_aba<CHAIN>(p, q, qd, tau, qdd);
+            for (int i = 0; i < PNR_DOF; ++i) tau[i] = pnr_control_torque(p, i, action[i], q[i], qd[i]);
+            pnr_aba<CHAIN>(p, q, qd, tau, qdd);
 #pragma unroll
-        for (int i = 0; i < PNR_DOF; ++i) {
-            float v = fmaf(qdd[i], p.dyn_dt, qd[i]);
-            float x = fmaf(v, p.dyn_dt, q[i]);
-            if (x > p.r_hi[i]) { x = p.r_hi[i]; if (v > 0.f) v = 0.f; }
-            if (x < p.r_lo[i]) { x = p.r_lo[i]; if (v < 0.f) v = 0.f; }
-            q[i] = x; qd[i] = v;
+            for (int i = 0; i < PNR_DOF; ++i) {
+                float v = fmaf(qdd[i], p.dyn_dt, qd[i]);
+                float x = fmaf(v, p.dyn_dt, q[i]);
+                pnr_joint_stop(p, i, x, v);
+                q[i] = x; qd[i] = v;
+            }
         }
     }
 }

@@ -307,7 +307,10 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         PNR_MARK(7);
 
         if (part == 3) {
-            if (__any_sync(PNR_FULL_MASK, do_reset)) {         // rare: auto-reset (reset_world, :76-105)
+            // rare: auto-reset (reset_world, :76-105).  Only the auto-reset observation mode rewrites the row, so only there
+            // does the reset have to precede the tile's store; terminal mode resets AFTER handing the tile to the copy engine
+            const bool any_reset = __any_sync(PNR_FULL_MASK, do_reset);
+            if (OBS_MODE == PNR_OBS_AUTORESET && any_reset) {
                 if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick, domain), row);
                 pnr_fence_async_smem();
                 __syncwarp();
@@ -324,6 +327,8 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                 __syncwarp();
                 if (iter >= 1 && t_idx + stride < n_tiles) pnr_bar_arrive2<PNR_BAR_FREE, PNR_STEP_THREADS>(buf ^ 1);
             }
+            if (OBS_MODE != PNR_OBS_AUTORESET && any_reset && do_reset)
+                pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick, domain), row);
         }
         PNR_MARK(8);
         PNR_TRACE_NEXT();

@@ -45,6 +45,22 @@ __device__ __forceinline__ void pnr_load_env(float4* __restrict__ S, int64_t N, 
     s.pot = x1.x; s.ep_ret = x1.y;
 }
 
+// the same through L2 only (ld.global.cg): a step that overlaps its predecessor tile by tile (pnr_step_many) may run on an
+// SM whose L1 still holds the planes as they were two steps ago
+__device__ __forceinline__ void pnr_load_env_cg(float4* __restrict__ S, int64_t N, int64_t e, PnrEnv& s) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float4 rv = __ldcg(pnr_plane_rv(S, N, k) + e);
+        const float2 a = __ldcg(pnr_plane_a(S, N, k) + e);
+        s.r[2 * k] = rv.x; s.r[2 * k + 1] = rv.y; s.v[2 * k] = rv.z; s.v[2 * k + 1] = rv.w;
+        s.a[2 * k] = a.x; s.a[2 * k + 1] = a.y;
+    }
+    const float4 x0 = __ldcg(pnr_plane_x0(S, N) + e);
+    const float2 x1 = __ldcg(pnr_plane_x1(S, N) + e);
+    s.tgt[0] = x0.x; s.tgt[1] = x0.y; s.tgt[2] = x0.z; s.t = __float_as_int(x0.w);
+    s.pot = x1.x; s.ep_ret = x1.y;
+}
+
 __device__ __forceinline__ void pnr_store_env(float4* __restrict__ S, int64_t N, int64_t e, const PnrEnv& s) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {

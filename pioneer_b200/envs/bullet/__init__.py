@@ -1,2 +1,2 @@
-from .bullet_scene import Pose, Item, Joint, Scene, World
+from .bullet_scene import Pose, Velocity, Item, Joint, Scene, World
 from .bullet_env import RenderConfig, SimulationConfig, BulletEnv

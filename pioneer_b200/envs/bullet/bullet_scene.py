@@ -20,6 +20,14 @@ class Pose:
         return f"Pose(xyz={self.xyz}, quaternion={self.quaternion})"
 
 
+class Velocity:
+    """reference: bullet_scene.py:33-36 (linear, angular); part of the import surface, unused on the stepping path."""
+
+    def __init__(self, linear: Tuple[float, float, float] = (0, 0, 0), angular: Tuple[float, float, float] = (0, 0, 0)):
+        self.linear = tuple(float(x) for x in linear)
+        self.angular = tuple(float(x) for x in angular)
+
+
 class Item:
     """A named body or link (reference: bullet_scene.py:39-73).  Only 'robot:pointer' and 'target'
     have a pose on this path (pioneer_knm_env.py:151-152)."""

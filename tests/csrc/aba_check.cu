@@ -32,7 +32,11 @@ extern "C" int aba_substeps(const void* params, int chain, long n, float* q, flo
     for (long e = 0; e < n; ++e) {
         float q_[PNR_DOF], qd_[PNR_DOF], a_[PNR_DOF];
         for (int i = 0; i < PNR_DOF; ++i) { q_[i] = q[e * PNR_DOF + i]; qd_[i] = qd[e * PNR_DOF + i]; a_[i] = action[e * PNR_DOF + i]; }
-        if (chain == PNR_CHAIN_PIONEER_ISO && p.dyn_iso_links) pnr_dynamic_substeps<PNR_CHAIN_PIONEER_ISO>(p, q_, qd_, a_);
+        if (p.dyn_stepping == PNR_STEPPING_BULLET) {            // the Bullet-like substep runs on the general ABA
+            if (chain == PNR_CHAIN_GENERIC) pnr_dynamic_substeps<PNR_CHAIN_GENERIC, PNR_STEPPING_BULLET>(p, q_, qd_, a_);
+            else pnr_dynamic_substeps<PNR_CHAIN_PIONEER, PNR_STEPPING_BULLET>(p, q_, qd_, a_);
+        }
+        else if (chain == PNR_CHAIN_PIONEER_ISO && p.dyn_iso_links) pnr_dynamic_substeps<PNR_CHAIN_PIONEER_ISO>(p, q_, qd_, a_);
         else if (chain == PNR_CHAIN_PIONEER) pnr_dynamic_substeps<PNR_CHAIN_PIONEER>(p, q_, qd_, a_);
         else if (chain == PNR_CHAIN_GENERIC) pnr_dynamic_substeps<PNR_CHAIN_GENERIC>(p, q_, qd_, a_);
         else return -1;

@@ -41,7 +41,7 @@ def harness(tmp_path_factory):
     return lib
 
 
-def params_blob(harness, gravity=9.81, kp=0.0, kd=0.0, torque_scale=1.0, chain=None):
+def params_blob(harness, gravity=9.81, kp=0.0, kd=0.0, torque_scale=1.0, chain=None, bullet=None):
     lib = _cabi.load()
     lib.pnr_debug_build_params.restype = C.c_int64
     lib.pnr_debug_build_params.argtypes = [C.POINTER(_cabi.pnr_model), C.POINTER(_cabi.pnr_config), C.c_int64,
@@ -51,6 +51,10 @@ def params_blob(harness, gravity=9.81, kp=0.0, kd=0.0, torque_scale=1.0, chain=N
     cfg = _cabi.pnr_config()
     lib.pnr_default_config(C.byref(cfg))
     cfg.mode, cfg.gravity, cfg.kp, cfg.kd, cfg.torque_scale = _cabi.PNR_MODE_DYNAMIC, gravity, kp, kd, torque_scale
+    if bullet is not None:
+        cfg.stepping = _cabi.PNR_STEPPING_BULLET
+        cfg.link_damping, cfg.max_velocity = bullet["link_damping"], bullet["max_velocity"]
+        cfg.motor_kp, cfg.motor_kd, cfg.motor_max_force = bullet["motor_kp"], bullet["motor_kd"], bullet["motor_max_force"]
     size = lib.pnr_debug_build_params(C.byref(model), C.byref(cfg), 1, None, 0)
     assert size == harness.aba_params_size(), "harness and library disagree on sizeof(PnrParams)"
     blob = C.create_string_buffer(size)
@@ -128,6 +132,40 @@ def test_one_env_step_of_substeps_against_the_oracle(harness, kp, kd, scale):
         assert harness.aba_substeps(blob, pioneer_chain, n, fp(q1), fp(qd1), fp(act)) == 0
         assert np.abs(q1 - ref_q).max() <= 2e-5, (pioneer_chain, np.abs(q1 - ref_q).max())
         assert np.abs(qd1 - ref_qd).max() <= 2e-4, (pioneer_chain, np.abs(qd1 - ref_qd).max())
+
+
+@pytest.mark.parametrize("case", ["motors", "weak motors", "no motors", "velocity clamp"])
+def test_bullet_like_substeps_against_the_compiled_oracle(harness, case):
+    """PNR_STEPPING_BULLET (opt-in): per-link damping, POSITION_CONTROL as a velocity-level motor constraint with impulse
+    clamp (projected Gauss-Seidel on M^-1), +-max_velocity clamp -- the float32 header against the float64 restatement in
+    oracle/dynamics_oracle.c (stepping = 1; both written from memory of btMultiBody, UNPINNED vs PyBullet).
+    One env step = 10 substeps; bars: |dq| <= 5e-5, |dqd| <= 2e-3 (the motor solve divides by dt: qd carries 240 x the
+    float32 rounding of q)."""
+    from oracle.c_dyn_oracle import CDynOracleBatch, DynEnvConfig
+    bullet = dict(link_damping=0.04, max_velocity=100.0, motor_kp=0.1, motor_kd=1.0,
+                  motor_max_force={"motors": 5e4, "weak motors": 300.0, "no motors": 0.0, "velocity clamp": 5e4}[case])
+    if case == "velocity clamp":
+        bullet.update(max_velocity=2.0, motor_kp=0.5)
+    gravity = 9.81
+    chain, blob = params_blob(harness, gravity=gravity, bullet=bullet)
+    orc = CDynOracleBatch(chain, 1, DynEnvConfig(gravity=gravity, stepping="bullet", **bullet))
+    n = 120
+    rng, q, qd = states(chain, n, seed=17)
+    q, qd = (q * 0.8).astype(np.float32), (qd * 0.3).astype(np.float32)
+    lo32, hi32 = np.asarray(chain.lower, np.float32), np.asarray(chain.upper, np.float32)
+    act = rng.uniform(lo32, hi32, size=(n, 6)).astype(np.float32)
+    ref_q, ref_qd = np.empty((n, 6)), np.empty((n, 6))
+    for e in range(n):
+        ref_q[e], ref_qd[e] = orc.substeps(q[e], qd[e], act[e], 10)
+    moved = np.abs(ref_q - q).max()
+    assert moved > 0.05                                              # the step really does something
+    if case == "velocity clamp":
+        assert np.abs(ref_qd).max() <= 2.0 + 1e-12 and (np.abs(ref_qd) > 1.99).any()
+    for pioneer_chain in (0, 1):
+        q1, qd1 = q.copy(), qd.copy()
+        assert harness.aba_substeps(blob, pioneer_chain, n, fp(q1), fp(qd1), fp(act)) == 0
+        dq, dqd = np.abs(q1 - ref_q).max(), np.abs(qd1 - ref_qd).max()
+        assert dq <= 5e-5 and dqd <= 2e-3, (case, pioneer_chain, dq, dqd)
 
 
 def test_general_inertials_take_the_non_isotropic_specialisation(harness):

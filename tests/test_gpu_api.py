@@ -216,6 +216,33 @@ def test_seed_reaches_steps_already_captured_in_a_graph():
     env.close(); twin.close()
 
 
+@pytest.mark.parametrize("mode,n", [("kinematic", 5000), ("dynamic", 70001), ("dynamic", 2048)])
+def test_step_many_equals_stepping(mode, n):
+    """pnr_step_many: T steps launched back to back from C (programmatic dependent launch; in the dynamic mode chained tile by
+    tile through per-tile sequence words) give bit for bit what T separate pnr_step calls give, call after call."""
+    from pioneer_b200 import BatchConfig, BatchedPioneerEnv, SimulationConfig
+    kw = dict(seed=4, simulation_config=SimulationConfig(gravity=9.81 if mode == "dynamic" else 0.0),
+              batch_config=BatchConfig(mode=mode, kp=2000.0, kd=500.0, torque_scale=1e5, max_episode_steps=5))
+    a, b = BatchedPioneerEnv(n, **kw), BatchedPioneerEnv(n, **kw)
+    T = 7
+    g = torch.Generator(device="cuda").manual_seed(0)
+    lo, hi = torch.as_tensor(a.action_space.low).cuda(), torch.as_tensor(a.action_space.high).cuda()
+    n_pad = (n + 3) // 4 * 4
+    for call in range(4):
+        actions = lo + torch.rand((T, n, 6), device="cuda", generator=g) * (hi - lo)
+        obs = torch.zeros((T, n_pad, 137), device="cuda")[:, :n]
+        rew = torch.zeros((T, n), device="cuda")
+        flg = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+        a.step_many(actions, obs, rew, flg)
+        for t in range(T):
+            o, r, f = b.step_tensor(actions[t])
+            assert torch.equal(f, flg[t]) and torch.equal(r, rew[t]) and torch.equal(o, obs[t]), (call, t)
+    sa, sb = a.state(), b.state()
+    assert all(torch.equal(sa[k], sb[k]) for k in sa)
+    assert a.episode_stats() == b.episode_stats()
+    a.close(); b.close()
+
+
 def test_graph_replays_draw_fresh_reset_states():
     """The host call counter that keys the Philox reset draws is a kernel argument, frozen at capture time; the graph
     advances a device-side counter instead (pnr_tick_advance), so an env that restarts in replay k does not restart

@@ -28,16 +28,17 @@ pytestmark = pytest.mark.gpu
 PD = dict(gravity=9.81, kp=2000.0, kd=500.0, torque_scale=1e5)          # bench.py's dynamic-mode workload
 
 
-def make(n, obs_mode="terminal", limit=500, obstacles=(), penalty=0.0, random_box=False, seed=0, env_id_base=0, **dyn):
+def make(n, obs_mode="terminal", limit=500, obstacles=(), penalty=0.0, random_box=False, seed=0, env_id_base=0, bullet=None,
+         **dyn):
     from pioneer_b200 import BatchConfig, BatchedPioneerEnv, SimulationConfig
     bc = BatchConfig(mode="dynamic", kp=dyn.get("kp", 0.0), kd=dyn.get("kd", 0.0), torque_scale=dyn.get("torque_scale", 1.0),
                      max_episode_steps=limit, auto_reset=True, obs_mode=obs_mode, obstacles=list(obstacles),
-                     contact_penalty=penalty, random_box=random_box)
+                     contact_penalty=penalty, random_box=random_box, **({"stepping": "bullet", **bullet} if bullet else {}))
     env = BatchedPioneerEnv(n, batch_config=bc, simulation_config=SimulationConfig(gravity=dyn.get("gravity", 0.0)), seed=seed,
                             env_id_base=env_id_base)
     cfg = DynEnvConfig(gravity=dyn.get("gravity", 0.0), kp=bc.kp, kd=bc.kd, torque_scale=bc.torque_scale,
                        max_episode_steps=limit, obstacles=tuple((o.kind, o.position, o.extent) for o in obstacles),
-                       contact_penalty=penalty,
+                       contact_penalty=penalty, **({"stepping": "bullet", **bullet} if bullet else {}),
                        random_box=(bc.box_pos_lo, bc.box_pos_hi, bc.box_size_lo, bc.box_size_hi) if random_box else None)
     orc = CDynOracleBatch(env.chain, n, cfg, env_id_base=env_id_base, seed=seed, obs_mode=obs_mode)
     return env, orc
@@ -53,7 +54,7 @@ def check_obs(obs, o_obs, worst):
     worst["pot"] = max(worst.get("pot", 0.0), float(d[:, 136].max()))
 
 
-def lockstep(env, orc, steps, action_fn, obs_mode="terminal", check_every=1):
+def lockstep(env, orc, steps, action_fn, obs_mode="terminal", check_every=1, bars=(5e-6, 5e-7, 5e-5, 5e-6)):
     n = env.n_envs
     s0, o0 = env.state(), orc.state()
     assert np.array_equal(s0["r"].cpu().numpy().astype(np.float64), o0["q"])         # same Philox reset draws
@@ -83,8 +84,8 @@ def lockstep(env, orc, steps, action_fn, obs_mode="terminal", check_every=1):
         dq = np.abs(q32.astype(np.float64) - out["own_q"])[free]
         dqd = np.abs(qd32.astype(np.float64) - out["own_qd"])[free]
         if dq.size:
-            bar_q = 5e-6 + 5e-7 * np.abs(out["own_q"][free])
-            bar_qd = 5e-5 + 5e-6 * np.abs(out["own_qd"][free])
+            bar_q = bars[0] + bars[1] * np.abs(out["own_q"][free])
+            bar_qd = bars[2] + bars[3] * np.abs(out["own_qd"][free])
             if not (dq <= bar_q).all() or not (dqd <= bar_qd).all():
                 i, j = np.unravel_index(np.argmax(dq / bar_q), dq.shape)
                 i2, j2 = np.unravel_index(np.argmax(dqd / bar_qd), dqd.shape)
@@ -143,7 +144,7 @@ def test_config3_65536_envs_pd_control_timelimit_autoreset():
     with TimeLimit 64 => every env goes through three episode ends and Philox resets."""
     env, orc = make(65536, limit=64, seed=12, **PD)
     worst, n_done = lockstep(env, orc, 200, setpoints(env, 1), check_every=10)
-    assert n_done == 3 * 65536 and worst["free_fraction"] > 0.85
+    assert n_done >= 3 * 65536 and worst["free_fraction"] > 0.85
     print("config3 dynamic parity, worst:", worst)
     env.close()
 
@@ -151,7 +152,7 @@ def test_config3_65536_envs_pd_control_timelimit_autoreset():
 def test_autoreset_observation_mode_at_16384_envs():
     env, orc = make(16384, obs_mode="autoreset", limit=40, seed=5, env_id_base=1 << 33, **PD)
     worst, n_done = lockstep(env, orc, 100, setpoints(env, 2), obs_mode="autoreset", check_every=5)
-    assert n_done == 2 * 16384 and worst["free_fraction"] > 0.85
+    assert n_done >= 2 * 16384 and worst["free_fraction"] > 0.85   # (+ the rare env that reaches its target)
     print("autoreset mode, worst:", worst)
     env.close()
 
@@ -173,7 +174,7 @@ def test_config4_16384_envs_with_the_demo_obstacles():
     from pioneer_b200 import demo_obstacles
     env, orc = make(16384, limit=50, obstacles=demo_obstacles(), penalty=0.5, seed=9, **PD)
     worst, n_done = lockstep(env, orc, 100, setpoints(env, 3), check_every=5)
-    assert n_done == 2 * 16384 and worst["free_fraction"] > 0.85
+    assert n_done >= 2 * 16384 and worst["free_fraction"] > 0.85
     print("config4 dynamic parity, worst:", worst)
     env.close()
 
@@ -184,8 +185,23 @@ def test_per_env_random_box_in_dynamic_mode():
     env, orc = make(n, limit=20, obstacles=demo_obstacles(), penalty=0.5, random_box=True, seed=21, **PD)
     assert np.array_equal(env.boxes().cpu().numpy().astype(np.float64), orc.state()["box"])
     worst, n_done = lockstep(env, orc, 45, setpoints(env, 5), check_every=5)
-    assert n_done == 2 * n
+    assert n_done >= 2 * n
     assert np.array_equal(env.boxes().cpu().numpy().astype(np.float64), orc.state()["box"])   # redrawn twice, same draws
+    env.close()
+
+
+def test_bullet_like_stepping_against_the_compiled_oracle():
+    """PNR_STEPPING_BULLET (opt-in; restated from memory of btMultiBody, UNPINNED vs PyBullet): per-link damping, POSITION_CONTROL
+    motors as velocity-level constraints with impulse clamp, +-100 rad/s clamp -- the device against the float64 restatement
+    (oracle/dynamics_oracle.c, stepping = 1), 4,096 envs x 60 steps with gravity, TimeLimit 25 and auto-reset.  The motor solve
+    divides by dt, so qd carries 240 x the float32 rounding of q: bars |dq| <= 5e-5 + 5e-6 |q|, |dqd| <= 2e-3 + 2e-4 |qd|."""
+    n = 4096
+    bullet = dict(link_damping=0.04, max_velocity=100.0, motor_kp=0.1, motor_kd=1.0, motor_max_force=5e4)
+    env, orc = make(n, limit=25, seed=14, gravity=9.81, bullet=bullet)
+    assert np.array_equal(env.action_space.low, env.r_lo)                  # motor set points
+    worst, n_done = lockstep(env, orc, 60, setpoints(env, 9, hold=12), check_every=4, bars=(5e-5, 5e-6, 2e-3, 2e-4))
+    assert n_done >= 2 * n and worst["free_fraction"] > 0.5
+    print("bullet-like stepping, worst:", worst)
     env.close()
 
 
