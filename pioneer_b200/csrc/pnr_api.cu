@@ -536,7 +536,7 @@ static int pnr_step_impl(pnr_handle* h, const float* actions, float* obs, float*
         PNR_CUDA(pnr_launch_step(h->params, h->device, h->cfg.arith, h->cfg.obs_mode, h->state, actions, obs, reward, done,
                                  h->stats, h->tick, domain, h->filt_fused ? h->filt_applied : nullptr,
                                  (h->filt_fused && h->filt_fused_update) ? h->filt_delta : nullptr, (float)h->filt_clip,
-                                 (cudaStream_t)stream));
+                                 chain, (cudaStream_t)stream));
     h->tick += 1;
     h->launches += 1;
     return PNR_OK;
@@ -549,11 +549,14 @@ extern "C" int pnr_step(pnr_handle* h, const float* actions, float* obs, float* 
 extern "C" int pnr_step_many(pnr_handle* h, int32_t n_steps, const float* actions, int64_t action_stride, float* obs,
                              int64_t obs_stride, float* reward, uint8_t* done, void* stream) {
     if (!h || n_steps < 0) return pnr_fail(PNR_ERR_INVALID, "pnr_step_many: bad argument");
-    // Dynamic mode: consecutive steps of one call are chained tile by tile (PnrChain): step t + 1 starts on a tile as soon
-    // as step t has stored that tile's state.  The sequence words carry (epoch << 8 | step), the epoch is unique per
+    // Consecutive steps of one call are chained tile by tile (PnrChain): step t + 1 starts on a tile as soon as step t has
+    // stored that tile's state.  On by default for the dynamic kernel only (PNR_CHAIN_MODES: bit 0 kinematic, bit 1 dynamic):
+    // measured on B200, the kinematic kernel gains 4 % at 65,536 envs but loses 40 % at 4,096 and 1,048,576 envs -- its CTAs
+    // stream through many short tiles, the chained successor catches up at once and then polls at its heels.  The sequence words carry (epoch << 8 | step), the epoch is unique per
     // chunk of <= 200 steps, so a word left behind by an earlier call never matches.  PNR_NO_CHAIN=1: grid-wide waits.
     static const bool chain_on = getenv("PNR_NO_CHAIN") == nullptr;
-    const bool chained = chain_on && h->cfg.mode == PNR_MODE_DYNAMIC && pnr_pdl_enabled();
+    static const int chain_modes = getenv("PNR_CHAIN_MODES") ? atoi(getenv("PNR_CHAIN_MODES")) : 2;   // developer knob
+    const bool chained = chain_on && pnr_pdl_enabled() && ((chain_modes >> (h->cfg.mode == PNR_MODE_DYNAMIC ? 1 : 0)) & 1);
     uint32_t epoch = 0, k = 0;
     for (int32_t t = 0; t < n_steps; ++t, ++k) {
         if (chained && (t == 0 || k == 200)) {

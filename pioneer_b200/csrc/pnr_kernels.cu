@@ -26,13 +26,35 @@
 // the Philox stream, a = v = 0, potential = 0, elapsed = 0 written over all eight planes of the env; in
 // PNR_OBS_AUTORESET mode the env's observation row is replaced by the first observation of the new episode.
 // Rare (once per episode), so deliberately not inlined: keeps registers and code out of the hot loop.
+// The reset is split in two so that its long part leaves the critical path: pnr_reset_prepare (three or four Philox blocks,
+// ~300 dependent integer instructions) runs as soon as the task warp knows the env will hit its TimeLimit in this step --
+// before it waits for the joint warps -- and leaves the draws in a thread-local array; pnr_reset_apply (eight plane stores,
+// plus the fresh observation row in auto-reset mode) runs after the tile is complete.  Envs that end by reaching the target
+// (rare, not predictable) prepare late.
+#define PNR_RESET_DRAWS 14                                    // q[6], target[3], box[5]
+static __device__ __noinline__ void pnr_reset_prepare(const PnrParams& p, int64_t env, uint64_t tickdom, float* __restrict__ draws) {
+    float q[PNR_DOF], tg[3], box[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
+    pnr_reset_draws(p, p.env_id_base + env, pnr_reset_key(p, tickdom), q, tg, box);
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) draws[i] = q[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) draws[6 + i] = tg[i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) draws[9 + i] = box[i];
+}
+
 template <int OBS_MODE>
-__device__ __noinline__ void pnr_auto_reset(const PnrParams& p, float4* __restrict__ state, int64_t env, uint64_t tickdom,
-                                            float* __restrict__ row) {
+__device__ __noinline__ void pnr_reset_apply(const PnrParams& p, float4* __restrict__ state, int64_t env,
+                                             const float* __restrict__ draws, float* __restrict__ row) {
     const int64_t N = p.n_envs;
     PnrEnv s;
     float q[PNR_DOF], tg[3], box[5];
-    pnr_reset_draws(p, p.env_id_base + env, pnr_reset_key(p, tickdom), q, tg, box);
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) q[i] = draws[i];
+#pragma unroll
+    for (int i = 0; i < 3; ++i) tg[i] = draws[6 + i];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) box[i] = draws[9 + i];
     pnr_reset_env(s, q, tg);
     pnr_store_env(state, N, env, s);
     pnr_store_box(p, env, box);
@@ -79,7 +101,7 @@ __global__ void __launch_bounds__(PNR_STEP_THREADS, FILTER ? PNR_STEP_MIN_CTAS_F
 pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                 PnrStats* __restrict__ stats, uint32_t tick, uint32_t domain, const float* __restrict__ f_applied,
-                double* __restrict__ f_delta, float f_clip) {
+                double* __restrict__ f_delta, float f_clip, const PnrChain chain) {
     extern __shared__ __align__(128) float tiles[];           // PNR_STEP_BUFS tiles: the bulk store of one drains
     const int lane = threadIdx.x & 31;                        // while the next is being filled
     const int part = threadIdx.x >> 5;                        // warp-uniform role
@@ -147,19 +169,21 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
 
     // software pipeline: every warp loads its own planes of the NEXT tile while it works on the current one
     float4 ld4; float2 ld2, ld_act = make_float2(0.f, 0.f);
+    // (state planes through L2 only: a chained step may run on an SM whose L1 holds them as they were two steps ago)
     auto issue_loads = [&](int64_t tile_idx) {
         const int64_t e_raw = tile_idx * PNR_TILE_ENVS + lane;
         const int64_t e = e_raw < N ? e_raw : N - 1;
+        pnr_chain_wait(chain, tile_idx, lane);                // chained steps (pnr_step_many): the previous step is done with this tile
         if (part < 3) {
-            ld4 = rv_plane[e];
-            ld2 = a_plane[e];
+            ld4 = __ldcg(rv_plane + e);
+            ld2 = __ldcg(a_plane + e);
             ld_act = pnr_ld_stream(reinterpret_cast<const float2*>(actions + e * PNR_DOF) + part);
         } else {
-            ld4 = x0_plane[e];
-            ld2 = x1_plane[e];
+            ld4 = __ldcg(x0_plane + e);
+            ld2 = __ldcg(x1_plane + e);
         }
     };
-    pnr_pdl_wait();                                           // the previous step's state planes are complete and visible
+    if (!chain.wait) pnr_pdl_wait();                          // the previous step's state planes are complete and visible
     issue_loads(t_idx);
     PNR_MARK(2);
     int buf = 0;
@@ -176,6 +200,8 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         if (t_idx + stride < n_tiles) issue_loads(t_idx + stride);
 
         float r1[2], v1[2], sn[2], cs[2];
+        float draws[PNR_RESET_DRAWS];                         // task warp, rare: the next episode's draws (thread-local memory)
+        bool prepared = false;
         if (part < 3) {
             // --- act(): integrate with the PREVIOUS action (one-step actuation delay); registers only
             pnr_integrate_joint<ARITH>(p, vmax0, rlo0, rhi0, c2.x, c4.z, c4.x, v1[0], r1[0]);
@@ -194,6 +220,14 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             pnr_bar_arrive2<PNR_BAR_HEAD, PNR_STEP_THREADS>(buf);
         } else {
             PNR_MARK(3);
+            // an env that runs into its TimeLimit in this step is known now: draw its next episode while the joint warps work
+            const bool will_time_out = active && p.auto_reset != 0 && p.max_episode_steps > 0 &&
+                                       __float_as_int(c4.w) + 1 >= p.max_episode_steps;
+            prepared = false;
+            if (__any_sync(PNR_FULL_MASK, will_time_out) && will_time_out) {
+                pnr_reset_prepare(p, env, pnr_tickdom(tick, domain), draws);
+                prepared = true;
+            }
             pnr_bar_sync2<PNR_BAR_HEAD, PNR_STEP_THREADS>(buf);   // r, cos r, sin r of all six joints are in the tile
             PNR_MARK(4);
         }
@@ -310,8 +344,9 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             // rare: auto-reset (reset_world, :76-105).  Only the auto-reset observation mode rewrites the row, so only there
             // does the reset have to precede the tile's store; terminal mode resets AFTER handing the tile to the copy engine
             const bool any_reset = __any_sync(PNR_FULL_MASK, do_reset);
+            if (any_reset && do_reset && !prepared) pnr_reset_prepare(p, env, pnr_tickdom(tick, domain), draws);   // reached the target
             if (OBS_MODE == PNR_OBS_AUTORESET && any_reset) {
-                if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick, domain), row);
+                if (do_reset) pnr_reset_apply<OBS_MODE>(p, state, env, draws, row);
                 pnr_fence_async_smem();
                 __syncwarp();
             }
@@ -328,7 +363,9 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                 if (iter >= 1 && t_idx + stride < n_tiles) pnr_bar_arrive2<PNR_BAR_FREE, PNR_STEP_THREADS>(buf ^ 1);
             }
             if (OBS_MODE != PNR_OBS_AUTORESET && any_reset && do_reset)
-                pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick, domain), row);
+                pnr_reset_apply<OBS_MODE>(p, state, env, draws, row);
+            // every plane of this tile is stored (the joint warps' before the DONE barrier): the next step may start on it
+            pnr_chain_publish(chain, t_idx, lane);
         }
         PNR_MARK(8);
         PNR_TRACE_NEXT();
@@ -375,7 +412,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             if (blockIdx.x == 0 && lane == 0) atomicAdd(&f_delta[0], (double)N);
         }
     }
-    if (part == 3 && lane == 0 && blockIdx.x == 0) stats->env_steps += (double)N;   // one writer per launch
+    if (part == 3 && lane == 0 && blockIdx.x == 0) atomicAdd(&stats->env_steps, (double)N);   // one writer per launch; chained launches overlap
     if (part == 3 && lane == 0) pnr_bulk_wait_read<0>();      // smem must outlive the copy engine's reads
 #ifdef PNR_TRACE
     trace_iter = 0;
@@ -607,9 +644,9 @@ static int64_t pnr_grid_for(int64_t n_envs, int envs_per_cta, int resident) {
 
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions, float* obs,
                             float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain, const float* f_applied,
-                            double* f_delta, float f_clip, cudaStream_t stream) {
+                            double* f_delta, float f_clip, PnrChain chain, cudaStream_t stream) {
     typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, uint32_t,
-                         const float*, double*, float);
+                         const float*, double*, float, const PnrChain);
     // the obstacle variant and the fused normaliser are separate instantiations: the plain kernel carries no trace of
     // them (a call site alone cost 40 % at 1M envs through caller-saved register spills)
     static Kern kernels[2][2][2] = {
@@ -644,9 +681,11 @@ cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_m
     cfg.gridDim = dim3((unsigned)grid); cfg.blockDim = dim3(PNR_STEP_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-    attr[0].val.programmaticStreamSerializationAllowed = pnr_pdl_enabled() ? 1 : 0;
+    // programmatic dependent launch pays where the launch tail is a visible share of the step (65,536 envs: 13.2 -> 11.8 us);
+    // on long grids the early-resident successor only takes SM slots from this grid (1,048,576 envs: 146 -> 151 us)
+    attr[0].val.programmaticStreamSerializationAllowed = (pnr_pdl_enabled() && n_tiles <= 8192) ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k, p, state, actions, obs, reward, done, stats, tick, domain, f_applied, f_delta, f_clip);
+    return cudaLaunchKernelEx(&cfg, k, p, state, actions, obs, reward, done, stats, tick, domain, f_applied, f_delta, f_clip, chain);
 }
 
 cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, float4* state, const int64_t* idx, int64_t n,

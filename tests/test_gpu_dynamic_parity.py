@@ -208,8 +208,8 @@ def test_bullet_like_stepping_against_the_compiled_oracle():
 def test_free_running_drift_is_bounded_under_pd_control():
     """No adoption: the float64 oracle free-runs beside 8,192 envs for 300 steps (TimeLimit 100, auto-reset).  PD control
     contracts, so the float32 trajectory stays near the float64 one: 99.9 % of the envs within 2e-3 rad at every check, every
-    env within 5e-2 (an inelastic joint stop is a discontinuity: when one side touches it a substep earlier than the other
-    the two differ by up to qd * dt until the controller pulls them together again); flags may only differ where the
+    env within 0.25 (an inelastic joint stop is a discontinuity: when one side touches it a substep earlier than the other
+    the two differ by up to qd * dt -- 26 rad/s x 1/240 s = 0.11 rad -- until the controller pulls them together again); flags may only differ where the
     distance sits within that drift of the done threshold (never, for random targets)."""
     n = 8192
     env, orc = make(n, limit=100, seed=31, **PD)
@@ -228,5 +228,5 @@ def test_free_running_drift_is_bounded_under_pd_control():
             worst = max(worst, float(err.max()))
             worst_q999 = max(worst_q999, float(np.quantile(err, 0.999)))
     print("free-running drift: worst", worst, "99.9 % quantile", worst_q999)
-    assert worst <= 5e-2 and worst_q999 <= 2e-3, (worst, worst_q999)
+    assert worst <= 0.25 and worst_q999 <= 2e-3, (worst, worst_q999)
     env.close()

@@ -33,7 +33,7 @@ def _run(env, flt, acts):
 
 
 def _worker(rank, world, port, q):
-    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), NCCL_DEBUG="WARN")
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))      # NCCL_DEBUG is left as the caller set it
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
     try:

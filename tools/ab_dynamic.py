@@ -13,7 +13,7 @@ CHILD = r'''
 import json, sys, torch
 sys.path.insert(0, %(root)r)
 from pioneer_b200 import BatchConfig, BatchedPioneerEnv, SimulationConfig
-sizes, kinematic = %(sizes)r, %(kinematic)r
+sizes, kinematic, age = %(sizes)r, %(kinematic)r, %(age)r
 flush = torch.empty(512 << 20, dtype=torch.uint8, device="cuda")
 out = {}
 for n in sizes:
@@ -23,7 +23,8 @@ for n in sizes:
         env = BatchedPioneerEnv(n, seed=0, simulation_config=SimulationConfig(gravity=9.81),
                                 batch_config=BatchConfig(mode="dynamic", kp=2000.0, kd=500.0, torque_scale=1e5, max_episode_steps=500))
     g = torch.Generator(device="cuda").manual_seed(0)
-    env.set_state(t=torch.randint(0, 500, (n,), device="cuda", generator=g, dtype=torch.int32))
+    if age:
+        env.set_state(t=torch.randint(0, 500, (n,), device="cuda", generator=g, dtype=torch.int32))
     lo, hi = torch.as_tensor(env.action_space.low).cuda(), torch.as_tensor(env.action_space.high).cuda()
     T = 8 if n <= 131072 else 2
     acts = lo + torch.rand((T, n, 6), device="cuda", generator=g) * (hi - lo)
@@ -51,8 +52,9 @@ def main():
     ap.add_argument("--sizes", type=int, nargs="+", default=[65536, 1048576])
     ap.add_argument("--kinematic", action="store_true")
     ap.add_argument("--rounds", type=int, default=2)
+    ap.add_argument("--no-age", action="store_true", help="all envs start at age 0: no auto-reset inside the timed steps")
     a = ap.parse_args()
-    code = CHILD % dict(root=ROOT, sizes=a.sizes, kinematic=a.kinematic)
+    code = CHILD % dict(root=ROOT, sizes=a.sizes, kinematic=a.kinematic, age=not a.no_age)
     for rnd in range(a.rounds):
         for lib in a.libs:
             env = dict(os.environ, PIONEER_B200_LIB=os.path.abspath(lib))

@@ -33,7 +33,6 @@ def main():
     dev = torch.device("cuda", local)
     torch.cuda.set_device(dev)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=dev)
     n = a.envs_per_gpu
     env = BatchedPioneerEnv(n, device=dev, seed=0, env_id_base=rank * n, batch_config=BatchConfig(max_episode_steps=500))
