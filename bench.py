@@ -41,12 +41,12 @@ BYTES_PER_ENV_STEP = BYTES_IO + BYTES_STATE          # 761
 FRAME_SKIP = 10
 FALLBACK_HBM_GBS = 6650.0                            # /opt/skills/guides/B200_PROFILING.md fallback
 L2_FLUSH_BYTES = 512 << 20                           # > 4x the 126 MB L2
-# Tier-B dynamic kernel, from the committed ncu capture (profiles/r01_dyn_v5_step_dynamic_65536.md): 11,094,016 FFMA +
-# 5,150,720 FMUL + 2,359,296 FADD warp instructions per 2,048-tile launch = FFMA 5,417 + FMUL 2,515 + FADD 1,152 thread
-# instructions per env-step (10 ABA substeps) = 14,501 flop; FP32 FMA peak measured on this pool's B200 with
-# tools/fma_peak.py = 72.6 TFLOP/s (nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)
-DYN_FLOP_PER_ENV_STEP = 2 * 5417 + 2515 + 1152
-DYN_FP_INSTR_PER_ENV_STEP = 5417 + 2515 + 1152
+# Tier-B dynamic kernel, from the committed ncu capture (profiles/r02_a_step_dynamic_65536.md): 11,051,008 FFMA + 5,173,670
+# FMUL + 2,451,910 FADD warp instructions per 2,048-tile launch = FFMA 5,396 + FMUL 2,526 + FADD 1,197 thread instructions
+# per env-step (10 ABA substeps) = 14,515 flop; FP32 FMA peak measured on this pool's B200 with tools/fma_peak.py =
+# 72.6 TFLOP/s (nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)
+DYN_FLOP_PER_ENV_STEP = 2 * 5396 + 2526 + 1197
+DYN_FP_INSTR_PER_ENV_STEP = 5396 + 2526 + 1197
 FP32_PEAK_TFLOPS = 72.6
 
 def parse_args():

@@ -294,7 +294,8 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
     p.award_done = (float)c.award_done;
     p.max_episode_steps = c.max_episode_steps;
     p.auto_reset = c.auto_reset;
-    (void)seed;                                  // the reset key lives in device memory (PnrStats::seed_*)
+    p.seed_lo = (uint32_t)seed;                  // eager launches; graph-captured ones read PnrStats::seed_*
+    p.seed_hi = (uint32_t)(seed >> 32);
     p.random_box = -1;
     if (c.random_box) {
         for (int i = 0; i < c.n_obstacles && p.random_box < 0; ++i)
@@ -478,6 +479,8 @@ extern "C" int pnr_seed(pnr_handle* h, uint64_t seed) {
     PNR_CUDA(cudaDeviceSynchronize());            // steps in flight keep the old key
     PNR_CUDA(cudaMemcpy(reinterpret_cast<char*>(h->stats) + offsetof(PnrStats, seed_lo), key, sizeof(key), cudaMemcpyHostToDevice));
     h->seed = seed;
+    h->params.seed_lo = key[0];
+    h->params.seed_hi = key[1];
     return PNR_OK;
 }
 

@@ -73,7 +73,8 @@ struct PnrParams {
     float box_pos_lo[2], box_pos_hi[2], box_size_lo[3], box_size_hi[3];
     float4* box_a;
     float* box_z;
-    const struct PnrStats* stats_ro;   // the handle's PnrStats (reset key: seed, device-side tick advance), for the rare reset paths
+    const struct PnrStats* stats_ro;   // the handle's PnrStats (reset key of graph-captured launches: seed, device-side tick advance)
+    uint32_t seed_lo, seed_hi;         // the reset key of eager launches (the host keeps it current; no global load on that path)
     int64_t env_id_base;
     int64_t n_envs;
 };
@@ -196,12 +197,16 @@ __device__ __forceinline__ void pnr_chain_wait(const PnrChain& c, int64_t tile, 
         if (lane == 0) {
             const uint32_t* w = c.seq + tile;
             uint32_t v;
-            for (;;) {
+            // The predecessor is earlier in the same stream and never waits for anything, and a chained launch cannot start
+            // before every CTA of its predecessor is resident (the PDL trigger is the first thing a CTA executes), so this
+            // wait always ends.  The bound (about two seconds) turns a broken invariant into an error instead of a hang.
+            for (uint32_t spins = 0;; ++spins) {
                 asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
                 if (v == c.wait) break;
 #if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 700
                 __nanosleep(64);
 #endif
+                if (spins > (1u << 24)) __trap();
             }
         }
         __syncwarp();
@@ -261,11 +266,16 @@ struct PnrStats {
 };
 // tickdom = domain << 32 | host call counter: ONE 64-bit argument for the rare, non-inlined reset paths
 __device__ __forceinline__ PnrResetKey pnr_reset_key(const PnrParams& p, uint64_t tickdom) {
-    const PnrStats* __restrict__ stats = p.stats_ro;
     PnrResetKey k;
     k.domain = (uint32_t)(tickdom >> 32);
-    k.seed_lo = stats->seed_lo; k.seed_hi = stats->seed_hi;
-    k.tick = k.domain ? (uint32_t)tickdom + stats->tick_offset : (uint32_t)tickdom;
+    if (k.domain) {                 // captured in a CUDA graph: the parameter block is frozen, seed and advance live in memory
+        const PnrStats* __restrict__ stats = p.stats_ro;
+        k.seed_lo = stats->seed_lo; k.seed_hi = stats->seed_hi;
+        k.tick = (uint32_t)tickdom + stats->tick_offset;
+    } else {
+        k.seed_lo = p.seed_lo; k.seed_hi = p.seed_hi;
+        k.tick = (uint32_t)tickdom;
+    }
     return k;
 }
 __device__ __forceinline__ uint64_t pnr_tickdom(uint32_t tick, uint32_t domain) { return ((uint64_t)domain << 32) | tick; }

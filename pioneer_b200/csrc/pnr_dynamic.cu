@@ -39,7 +39,9 @@ cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode
     // Tile-level chaining pays when a CTA works through several tiles (the next step then fills the ragged end of this one:
     // 131,072 envs 68.6 -> 56.6 us per step); when every warp owns exactly one tile the chain of a tile is strictly serial
     // and early-launched successors only take slots (65,536 envs 37.7 -> 46.9 us): such launches wait grid-wide instead.
-    if ((p.n_envs + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS <= (int64_t)resident * PNR_DYN_WARPS) chain_seq.wait = 0;
+    // (the decision depends on the batch size only, so every launch of a call takes the same one; not publishing either saves
+    // the release fence: 3 % of the stall samples of a 65,536-env launch, profiles/r02_a_step_dynamic_65536.md)
+    if ((p.n_envs + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS <= (int64_t)resident * PNR_DYN_WARPS) chain_seq.wait = chain_seq.publish = 0;
     const int64_t per_cta = PNR_TILE_ENVS * PNR_DYN_WARPS;
     int64_t grid = (p.n_envs + per_cta - 1) / per_cta;
     if (grid > resident) grid = resident;

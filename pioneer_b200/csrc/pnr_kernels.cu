@@ -26,35 +26,20 @@
 // the Philox stream, a = v = 0, potential = 0, elapsed = 0 written over all eight planes of the env; in
 // PNR_OBS_AUTORESET mode the env's observation row is replaced by the first observation of the new episode.
 // Rare (once per episode), so deliberately not inlined: keeps registers and code out of the hot loop.
-// The reset is split in two so that its long part leaves the critical path: pnr_reset_prepare (three or four Philox blocks,
-// ~300 dependent integer instructions) runs as soon as the task warp knows the env will hit its TimeLimit in this step --
-// before it waits for the joint warps -- and leaves the draws in a thread-local array; pnr_reset_apply (eight plane stores,
-// plus the fresh observation row in auto-reset mode) runs after the tile is complete.  Envs that end by reaching the target
-// (rare, not predictable) prepare late.
-#define PNR_RESET_DRAWS 14                                    // q[6], target[3], box[5]
-static __device__ __noinline__ void pnr_reset_prepare(const PnrParams& p, int64_t env, uint64_t tickdom, float* __restrict__ draws) {
-    float q[PNR_DOF], tg[3], box[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
-    pnr_reset_draws(p, p.env_id_base + env, pnr_reset_key(p, tickdom), q, tg, box);
-#pragma unroll
-    for (int i = 0; i < PNR_DOF; ++i) draws[i] = q[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) draws[6 + i] = tg[i];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) draws[9 + i] = box[i];
-}
-
+// In-kernel auto-reset of ONE env by the task warp after the tile is complete: new joint angles and target from
+// the Philox stream, a = v = 0, potential = 0, elapsed = 0 written over all eight planes of the env; in
+// PNR_OBS_AUTORESET mode the env's observation row is replaced by the first observation of the new episode.
+// Rare (once per episode), so deliberately not inlined: keeps registers and code out of the hot loop.
+// (Tried and dropped: drawing the next episode as soon as the TimeLimit hit is known, before the task warp waits for the
+// joint warps -- the divergent Philox lane delays the whole task warp, which IS the critical path there: 11.8 -> 12.9 us
+// per 65,536-env step.)
 template <int OBS_MODE>
-__device__ __noinline__ void pnr_reset_apply(const PnrParams& p, float4* __restrict__ state, int64_t env,
-                                             const float* __restrict__ draws, float* __restrict__ row) {
+__device__ __noinline__ void pnr_auto_reset(const PnrParams& p, float4* __restrict__ state, int64_t env, uint64_t tickdom,
+                                            float* __restrict__ row) {
     const int64_t N = p.n_envs;
     PnrEnv s;
     float q[PNR_DOF], tg[3], box[5];
-#pragma unroll
-    for (int i = 0; i < PNR_DOF; ++i) q[i] = draws[i];
-#pragma unroll
-    for (int i = 0; i < 3; ++i) tg[i] = draws[6 + i];
-#pragma unroll
-    for (int i = 0; i < 5; ++i) box[i] = draws[9 + i];
+    pnr_reset_draws(p, p.env_id_base + env, pnr_reset_key(p, tickdom), q, tg, box);
     pnr_reset_env(s, q, tg);
     pnr_store_env(state, N, env, s);
     pnr_store_box(p, env, box);
@@ -200,8 +185,6 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         if (t_idx + stride < n_tiles) issue_loads(t_idx + stride);
 
         float r1[2], v1[2], sn[2], cs[2];
-        float draws[PNR_RESET_DRAWS];                         // task warp, rare: the next episode's draws (thread-local memory)
-        bool prepared = false;
         if (part < 3) {
             // --- act(): integrate with the PREVIOUS action (one-step actuation delay); registers only
             pnr_integrate_joint<ARITH>(p, vmax0, rlo0, rhi0, c2.x, c4.z, c4.x, v1[0], r1[0]);
@@ -220,14 +203,6 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             pnr_bar_arrive2<PNR_BAR_HEAD, PNR_STEP_THREADS>(buf);
         } else {
             PNR_MARK(3);
-            // an env that runs into its TimeLimit in this step is known now: draw its next episode while the joint warps work
-            const bool will_time_out = active && p.auto_reset != 0 && p.max_episode_steps > 0 &&
-                                       __float_as_int(c4.w) + 1 >= p.max_episode_steps;
-            prepared = false;
-            if (__any_sync(PNR_FULL_MASK, will_time_out) && will_time_out) {
-                pnr_reset_prepare(p, env, pnr_tickdom(tick, domain), draws);
-                prepared = true;
-            }
             pnr_bar_sync2<PNR_BAR_HEAD, PNR_STEP_THREADS>(buf);   // r, cos r, sin r of all six joints are in the tile
             PNR_MARK(4);
         }
@@ -344,9 +319,8 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             // rare: auto-reset (reset_world, :76-105).  Only the auto-reset observation mode rewrites the row, so only there
             // does the reset have to precede the tile's store; terminal mode resets AFTER handing the tile to the copy engine
             const bool any_reset = __any_sync(PNR_FULL_MASK, do_reset);
-            if (any_reset && do_reset && !prepared) pnr_reset_prepare(p, env, pnr_tickdom(tick, domain), draws);   // reached the target
             if (OBS_MODE == PNR_OBS_AUTORESET && any_reset) {
-                if (do_reset) pnr_reset_apply<OBS_MODE>(p, state, env, draws, row);
+                if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick, domain), row);
                 pnr_fence_async_smem();
                 __syncwarp();
             }
@@ -363,7 +337,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                 if (iter >= 1 && t_idx + stride < n_tiles) pnr_bar_arrive2<PNR_BAR_FREE, PNR_STEP_THREADS>(buf ^ 1);
             }
             if (OBS_MODE != PNR_OBS_AUTORESET && any_reset && do_reset)
-                pnr_reset_apply<OBS_MODE>(p, state, env, draws, row);
+                pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick, domain), row);
             // every plane of this tile is stored (the joint warps' before the DONE barrier): the next step may start on it
             pnr_chain_publish(chain, t_idx, lane);
         }
