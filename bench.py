@@ -514,17 +514,21 @@ def ours_arm(args):
     total_envs = n * world
     value = total_envs * args.steps / (kernel_ms_max / 1e3)
     clocks = sampler.finish() if sampler else None
-    # the path's one collective: episode statistics, once per iteration.  One all-gather + one merge kernel; timed after the
-    # warm-up above, median of 20
+    # the path's one collective: episode statistics, once per iteration.  Snapshot kernel + ONE all-gather + one merge kernel
+    # with static buffers, replayed from a CUDA graph (distributed.IterationSync); timed after warm-up, median of 20
+    from pioneer_b200.distributed import IterationSync
+    stats = reduce_episode_stats(env.episode_stats_tensor()).clone()       # the window of the timed region, for the line
+    it_sync = IterationSync(env, None, None, clear=False, cuda_graph=True)
     evs = []
     for _ in range(20):
         a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a_.record()
-        stats = reduce_episode_stats(env.episode_stats_tensor())
+        it_sync()
         b_.record()
         evs.append((a_, b_))
     torch.cuda.synchronize()
     stats_ms = sorted(a_.elapsed_time(b_) for a_, b_ in evs)[10]
+    assert torch.equal(it_sync.merged[:8], stats), "graph-replayed collective disagrees with the eager one"
 
     # ---- the round-1 method on the same env: one event pair and one flush per STEP ----------------------
     k1 = min(args.steps, 1000)

@@ -98,6 +98,72 @@ def reduce_episode_stats(local: torch.Tensor, group: Optional[dist.ProcessGroup]
     return reduce_packed(local, None, group)[0]
 
 
+class IterationSync:
+    """Everything a rollout worker exchanges once per training iteration, as ONE collective with static buffers:
+
+        snapshot of the episode statistics (pnr_stats_device, optionally clearing the window)
+        [+ the observation filter's delta (pnr_filter_delta_device)]           -> packed float64[8 (+ 275)]
+        all_gather_into_tensor(packed)                                          -> gathered [world, len]   (NCCL)
+        pnr_stats_merge_device                                                  -> merged   [len]          (one kernel)
+        [+ pnr_filter_sync_device(merged[8:])]
+
+    With ``cuda_graph=True`` the whole sequence (NCCL included) is captured once and replayed: one graph launch per
+    iteration instead of five host calls.  ``__call__`` returns the merged float64[8] statistics tensor (device, not
+    synchronised; valid until the next call)."""
+
+    def __init__(self, env, obs_filter=None, group: Optional[dist.ProcessGroup] = None, clear: bool = True,
+                 cuda_graph: bool = False):
+        from . import _cabi
+        self.env, self.filter, self.group, self.clear = env, obs_filter, group, bool(clear)
+        self._cabi, self._lib = _cabi, env._lib
+        k = len(STATS_FIELDS)
+        self.k = k
+        self.len = k + (_cabi.PNR_FILTER_DELTA_LEN if obs_filter is not None else 0)
+        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        dev = env.device
+        self.packed = torch.zeros(self.len, dtype=torch.float64, device=dev)
+        self.gathered = torch.zeros((self.world, self.len), dtype=torch.float64, device=dev)
+        self.merged = torch.zeros(self.len, dtype=torch.float64, device=dev)
+        self._graph = None
+        if cuda_graph:
+            with torch.cuda.device(dev):
+                for _ in range(3):                          # communicator and kernels warm before the capture
+                    self._run()
+                torch.cuda.synchronize(dev)
+                try:
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g):
+                        self._run()
+                    self._graph = g
+                except Exception:  # noqa: BLE001 - capture of the collective is not available: stay eager
+                    self._graph = None
+                    torch.cuda.synchronize(dev)
+
+    def _run(self) -> None:
+        env, c, lib = self.env, self._cabi, self._lib
+        s = env._stream()
+        c.check(lib.pnr_stats_device(env._h, self.packed.data_ptr(), 1 if self.clear else 0, s), "pnr_stats_device")
+        if self.filter is not None:
+            c.check(lib.pnr_filter_delta_device(env._h, self.packed.data_ptr() + 8 * self.k, s), "pnr_filter_delta_device")
+        if self.world > 1:
+            dist.all_gather_into_tensor(self.gathered, self.packed, group=self.group)
+            src = self.gathered
+        else:
+            src = self.packed
+        c.check(lib.pnr_stats_merge_device(src.data_ptr(), self.world, self.len, self.merged.data_ptr(), s),
+                "pnr_stats_merge_device")
+        if self.filter is not None:
+            c.check(lib.pnr_filter_sync_device(env._h, self.merged.data_ptr() + 8 * self.k, s), "pnr_filter_sync_device")
+
+    def __call__(self) -> torch.Tensor:
+        with torch.cuda.device(self.env.device):
+            if self._graph is not None:
+                self._graph.replay()
+            else:
+                self._run()
+        return self.merged[:self.k]
+
+
 def summarize(stats: torch.Tensor) -> Dict[str, float]:
     """episode_reward_max/min/mean, episode_len_mean, episodes_total (cli.py:32-38) from the packed vector."""
     s = [float(x) for x in stats.tolist()]

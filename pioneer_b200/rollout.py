@@ -17,7 +17,7 @@ import torch
 import torch.nn as nn
 
 from .batched_env import DOF, OBS_DIM, BatchedPioneerEnv
-from .distributed import reduce_episode_stats, reduce_packed, summarize
+from .distributed import IterationSync, summarize
 from .obs_filter import MeanStdObsFilter
 
 
@@ -88,6 +88,7 @@ class RolloutWorker:
         self.reward = torch.empty((self.T, n), **f32)
         self.flags = torch.empty((self.T, n), dtype=torch.uint8, device=dev)
         self._have_first = False
+        self._sync: Optional[IterationSync] = None
         self._last_done: Optional[torch.Tensor] = None
         # terminal-observation envs with in-kernel auto-reset need their done rows patched; 'autoreset' envs already return
         # the fresh observation (and have no terminal one to offer)
@@ -165,13 +166,11 @@ class RolloutWorker:
         return out
 
     def sync(self, group=None, summary: bool = True):
-        """Once per training iteration: episode statistics and filter statistics of all ranks.  ``summary=False`` returns
-        the reduced float64[8] statistics tensor without reading it back, so the loop never waits for the GPU (the filter
-        synchronisation stays on the device as well)."""
-        local = self.env.episode_stats_tensor(clear=True)
-        if self.filter is not None:                       # one collective for both (all-gather + local reduction)
-            stats, merged = reduce_packed(local, self.filter.delta(), group)
-            self.filter.apply_merged(merged)
-        else:
-            stats = reduce_episode_stats(local, group)
+        """Once per training iteration: episode statistics and filter statistics of all ranks in ONE collective
+        (``distributed.IterationSync``: snapshot + filter delta -> one all-gather -> one merge kernel -> filter merge, all on
+        the device; replayed from a CUDA graph when the worker runs its fragments from one).  ``summary=False`` returns the
+        reduced float64[8] statistics tensor without reading it back, so the loop never waits for the GPU."""
+        if self._sync is None or self._sync.group is not group:
+            self._sync = IterationSync(self.env, self.filter, group, clear=True, cuda_graph=self.use_graph)
+        stats = self._sync()
         return summarize(stats) if summary else stats

@@ -28,6 +28,11 @@ def _run(env, flt, acts):
         flt.push(obs)
         outs.append((obs.clone(), rew.clone(), flg.clone()))
     stats = reduce_episode_stats(env.episode_stats_tensor())
+    # the same reduction as ONE graph-replayed collective with static buffers (what the rollout loop and bench.py use)
+    from pioneer_b200.distributed import IterationSync
+    for graph in (False, True):
+        again = IterationSync(env, None, None, clear=False, cuda_graph=graph)()
+        assert torch.equal(again, stats), graph
     flt.sync()
     return outs, stats.cpu().numpy(), flt.n, flt.mean, flt.var
 
