@@ -127,8 +127,11 @@ class IterationSync:
         self._graph = None
         if cuda_graph:
             with torch.cuda.device(dev):
-                for _ in range(3):                          # communicator and kernels warm before the capture
-                    self._run()
+                # the communicator must exist before the capture; warm it with the (still empty) static buffers -- NOT with
+                # _run(), which clears the statistics window and merges the filter delta
+                if self.world > 1:
+                    for _ in range(2):
+                        dist.all_gather_into_tensor(self.gathered, self.packed, group=self.group)
                 torch.cuda.synchronize(dev)
                 try:
                     g = torch.cuda.CUDAGraph()
