@@ -511,7 +511,7 @@ extern "C" int pnr_observe(pnr_handle* h, const int64_t* idx, int64_t n, float* 
 }
 
 static int pnr_step_impl(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, void* stream,
-                         uint32_t chain_wait, uint32_t chain_publish, bool* capturing) {
+                         uint32_t chain_wait, uint32_t chain_publish, bool* capturing, PnrMulti multi = PnrMulti{1, 0, 0}) {
     if (!h || !actions || !obs || !reward || !done) return pnr_fail(PNR_ERR_INVALID, "pnr_step: null argument");
     if ((reinterpret_cast<uintptr_t>(obs) & 15) || (reinterpret_cast<uintptr_t>(actions) & 7))
         return pnr_fail(PNR_ERR_INVALID, "pnr_step: obs must be 16-byte and actions 8-byte aligned");
@@ -539,8 +539,8 @@ static int pnr_step_impl(pnr_handle* h, const float* actions, float* obs, float*
         PNR_CUDA(pnr_launch_step(h->params, h->device, h->cfg.arith, h->cfg.obs_mode, h->state, actions, obs, reward, done,
                                  h->stats, h->tick, domain, h->filt_fused ? h->filt_applied : nullptr,
                                  (h->filt_fused && h->filt_fused_update) ? h->filt_delta : nullptr, (float)h->filt_clip,
-                                 chain, (cudaStream_t)stream));
-    h->tick += 1;
+                                 chain, multi, (cudaStream_t)stream));
+    h->tick += (uint32_t)multi.n_steps;
     h->launches += 1;
     return PNR_OK;
 }
@@ -555,9 +555,19 @@ extern "C" int pnr_step_many(pnr_handle* h, int32_t n_steps, const float* action
     // Consecutive steps of one call are chained tile by tile (PnrChain): step t + 1 starts on a tile as soon as step t has
     // stored that tile's state.  On by default for the dynamic kernel only (PNR_CHAIN_MODES: bit 0 kinematic, bit 1 dynamic):
     // measured on B200, the kinematic kernel gains 4 % at 65,536 envs but loses 40 % at 4,096 and 1,048,576 envs -- its CTAs
-    // stream through many short tiles, the chained successor catches up at once and then polls at its heels.  The sequence words carry (epoch << 8 | step), the epoch is unique per
-    // chunk of <= 200 steps, so a word left behind by an earlier call never matches.  PNR_NO_CHAIN=1: grid-wide waits.
+    // stream through many short tiles, the chained successor catches up at once and then polls at its heels.
+    // The sequence words carry (epoch << 8 | step), the epoch is unique per chunk of <= 200 steps, so a word left behind by an earlier call never matches.  PNR_NO_CHAIN=1: grid-wide waits.
     static const bool chain_on = getenv("PNR_NO_CHAIN") == nullptr;
+    // Kinematic mode: the whole fragment is ONE launch (PnrMulti): every CTA runs the n_steps steps on its own tiles with a
+    // CTA barrier between them -- no launch gap, no grid-wide wait (PNR_NO_FUSE=1: one launch per step).
+    static const bool fuse_on = getenv("PNR_NO_FUSE") == nullptr;
+    if (fuse_on && h->cfg.mode == PNR_MODE_KINEMATIC && n_steps > 1) {
+        if ((reinterpret_cast<uintptr_t>(obs) & 15) || ((obs_stride * sizeof(float)) & 15))
+            return pnr_fail(PNR_ERR_INVALID, "pnr_step_many: obs and obs_stride * 4 must be multiples of 16 bytes");
+        if ((action_stride * sizeof(float)) & 7)
+            return pnr_fail(PNR_ERR_INVALID, "pnr_step_many: action_stride * 4 must be a multiple of 8 bytes");
+        return pnr_step_impl(h, actions, obs, reward, done, stream, 0u, 0u, nullptr, PnrMulti{n_steps, action_stride, obs_stride});
+    }
     static const int chain_modes = getenv("PNR_CHAIN_MODES") ? atoi(getenv("PNR_CHAIN_MODES")) : 2;   // developer knob
     const bool chained = chain_on && pnr_pdl_enabled() && ((chain_modes >> (h->cfg.mode == PNR_MODE_DYNAMIC ? 1 : 0)) & 1);
     uint32_t epoch = 0, k = 0;

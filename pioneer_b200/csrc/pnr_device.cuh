@@ -222,6 +222,12 @@ __device__ __forceinline__ void pnr_chain_publish(const PnrChain& c, int64_t til
     }
 }
 
+// A rollout fragment in ONE launch of the kinematic step kernel (pnr_step_many): the CTA keeps its tiles and runs n_steps
+// consecutive steps on them -- tiles never depend on each other, so no grid-wide synchronisation is needed between the
+// steps, only a CTA barrier.  Step s reads actions + s * act_stride and writes obs + s * obs_stride (floats), reward / done
+// + s * N.  n_steps = 1 for an ordinary pnr_step.
+struct PnrMulti { int32_t n_steps; int64_t act_stride, obs_stride; };
+
 // named CTA barriers (ids 1..15; id 0 is __syncthreads): producer warps ARRIVE without waiting, the consumer SYNCs.
 // `count` = all participating threads (arrivers + waiters).  Both order prior shared / global accesses of the CTA.
 // The ids are immediates: with register ids ptxas reserves all 16 barriers per CTA, which caps the SM at 4 CTAs.

@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(PNR_STEP_THREADS, FILTER ? PNR_STEP_MIN_CTAS_F
 pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                 PnrStats* __restrict__ stats, uint32_t tick, uint32_t domain, const float* __restrict__ f_applied,
-                double* __restrict__ f_delta, float f_clip, const PnrChain chain) {
+                double* __restrict__ f_delta, float f_clip, const PnrChain chain, const PnrMulti multi) {
     extern __shared__ __align__(128) float tiles[];           // PNR_STEP_BUFS tiles: the bulk store of one drains
     const int lane = threadIdx.x & 31;                        // while the next is being filled
     const int part = threadIdx.x >> 5;                        // warp-uniform role
@@ -155,25 +155,41 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
     // software pipeline: every warp loads its own planes of the NEXT tile while it works on the current one
     float4 ld4; float2 ld2, ld_act = make_float2(0.f, 0.f);
     // (state planes through L2 only: a chained step may run on an SM whose L1 holds them as they were two steps ago)
-    auto issue_loads = [&](int64_t tile_idx) {
+    auto issue_loads = [&](int64_t tile_idx, const float* __restrict__ act) {
         const int64_t e_raw = tile_idx * PNR_TILE_ENVS + lane;
         const int64_t e = e_raw < N ? e_raw : N - 1;
         pnr_chain_wait(chain, tile_idx, lane);                // chained steps (pnr_step_many): the previous step is done with this tile
         if (part < 3) {
             ld4 = __ldcg(rv_plane + e);
             ld2 = __ldcg(a_plane + e);
-            ld_act = pnr_ld_stream(reinterpret_cast<const float2*>(actions + e * PNR_DOF) + part);
+            ld_act = pnr_ld_stream(reinterpret_cast<const float2*>(act + e * PNR_DOF) + part);
         } else {
             ld4 = __ldcg(x0_plane + e);
             ld2 = __ldcg(x1_plane + e);
         }
     };
     if (!chain.wait) pnr_pdl_wait();                          // the previous step's state planes are complete and visible
-    issue_loads(t_idx);
+    issue_loads(t_idx, actions);
     PNR_MARK(2);
     int buf = 0;
     int64_t iter = 0;                                         // tiles this CTA has started
 
+    // n_steps consecutive steps on this CTA's own tiles (PnrMulti; 1 for an ordinary step).  Between two steps the warps of
+    // the CTA meet at a barrier: the task warp may have reset an env of the tile, which rewrites planes the joint warps
+    // are about to load again.
+    for (int32_t step = 0; step < multi.n_steps; ++step) {
+    const bool more_steps = step + 1 < multi.n_steps;
+    // this step's buffers (launch-uniform: the bases stay in the constant bank)
+    const float* __restrict__ const act_s = actions + (int64_t)step * multi.act_stride;
+    float* __restrict__ const obs_s = obs + (int64_t)step * multi.obs_stride;
+    float* __restrict__ const reward_s = reward + (int64_t)step * N;
+    uint8_t* __restrict__ const done_s = done + (int64_t)step * N;
+    const uint32_t tick_s = tick + (uint32_t)step;
+    if (step > 0) {
+        __syncthreads();
+        t_idx = blockIdx.x;
+        issue_loads(t_idx, act_s);
+    }
     for (; t_idx < n_tiles; t_idx += stride) {
         const int64_t env_raw = t_idx * PNR_TILE_ENVS + lane;
         const bool active = env_raw < N;
@@ -182,7 +198,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         const int rows_valid = rows_left < PNR_TILE_ENVS ? (int)rows_left : PNR_TILE_ENVS;
         const float4 c4 = ld4;
         const float2 c2 = ld2, c_act = ld_act;
-        if (t_idx + stride < n_tiles) issue_loads(t_idx + stride);
+        if (t_idx + stride < n_tiles) issue_loads(t_idx + stride, act_s);
 
         float r1[2], v1[2], sn[2], cs[2];
         if (part < 3) {
@@ -282,8 +298,8 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             const bool is_done = reached || timeout;
             const uint8_t flags = (is_done ? PNR_DONE : 0) | ((timeout && !reached) ? PNR_TRUNCATED : 0);
             if (active) {
-                reward[env] = rew;
-                done[env] = flags;
+                reward_s[env] = rew;
+                done_s[env] = flags;
             }
             pnr_episode_stats(stats, is_done && active, reached && active, ep_ret, t, lane);
 
@@ -320,13 +336,13 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             // does the reset have to precede the tile's store; terminal mode resets AFTER handing the tile to the copy engine
             const bool any_reset = __any_sync(PNR_FULL_MASK, do_reset);
             if (OBS_MODE == PNR_OBS_AUTORESET && any_reset) {
-                if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick, domain), row);
+                if (do_reset) pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick_s, domain), row);
                 pnr_fence_async_smem();
                 __syncwarp();
             }
             if (bulk) {
                 if (lane == 0) {
-                    pnr_bulk_store(obs + t_idx * (int64_t)PNR_TILE_FLOATS, tile,
+                    pnr_bulk_store(obs_s + t_idx * (int64_t)PNR_TILE_FLOATS, tile,
                                    (uint32_t)(rows_valid * PNR_OBS_DIM * sizeof(float)));
                     pnr_bulk_commit();
                     // every store but the one just committed has finished READING its buffer: the previous tile's
@@ -334,18 +350,23 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                     if (iter >= 1) pnr_bulk_wait_read<1>();
                 }
                 __syncwarp();
-                if (iter >= 1 && t_idx + stride < n_tiles) pnr_bar_arrive2<PNR_BAR_FREE, PNR_STEP_THREADS>(buf ^ 1);
+                if (iter >= 1 && (t_idx + stride < n_tiles || more_steps)) pnr_bar_arrive2<PNR_BAR_FREE, PNR_STEP_THREADS>(buf ^ 1);
             }
             if (OBS_MODE != PNR_OBS_AUTORESET && any_reset && do_reset)
-                pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick, domain), row);
+                pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick_s, domain), row);
             // every plane of this tile is stored (the joint warps' before the DONE barrier): the next step may start on it
             pnr_chain_publish(chain, t_idx, lane);
         }
         PNR_MARK(8);
         PNR_TRACE_NEXT();
         if (!bulk) {                                          // ragged last tile: all 128 threads stream it out
+            if (part == 3 && iter >= 1 && more_steps) {       // (another step follows: keep the buffer protocol going)
+                if (lane == 0) pnr_bulk_wait_read<0>();
+                __syncwarp();
+                pnr_bar_arrive2<PNR_BAR_FREE, PNR_STEP_THREADS>(buf ^ 1);
+            }
             __syncthreads();
-            pnr_emit_tile_manual(tile, obs + t_idx * (int64_t)PNR_TILE_FLOATS, rows_valid, threadIdx.x, PNR_STEP_THREADS);
+            pnr_emit_tile_manual(tile, obs_s + t_idx * (int64_t)PNR_TILE_FLOATS, rows_valid, threadIdx.x, PNR_STEP_THREADS);
         }
         buf ^= 1;                                             // next tile goes into the other buffer
         ++iter;
@@ -354,6 +375,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         rowj = row + j0;
         if (FILTER) srow = scratch + buf * PNR_FSCRATCH_FLOATS + lane * PNR_FSCRATCH_STRIDE;
     }
+    }                                                         // steps
     if (FILTER && f_delta != nullptr) {                       // column statistics of this CTA's rows, into copy blockIdx % SLOTS
         double* f_slot = f_delta + (size_t)(blockIdx.x & (PNR_FILTER_SLOTS - 1)) * PNR_FILTER_DELTA_LEN;
         if (part < 3) {
@@ -366,8 +388,8 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                 const float x = g == 0 ? p.r_lo[j] : g == 1 ? p.cos_r_lo[j] : g == 2 ? p.sin_r_lo[j]
                               : g == 3 ? p.r_hi[j] : g == 4 ? p.cos_r_hi[j] : p.sin_r_hi[j];
                 const double d = (double)(x - f_applied[c]);
-                atomicAdd(&f_delta[1 + c], (double)N * d);
-                atomicAdd(&f_delta[1 + PNR_OBS_DIM + c], (double)N * d * d);
+                atomicAdd(&f_delta[1 + c], (double)N * multi.n_steps * d);
+                atomicAdd(&f_delta[1 + PNR_OBS_DIM + c], (double)N * multi.n_steps * d * d);
             }
         } else {
 #pragma unroll
@@ -383,10 +405,10 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
                     atomicAdd(&f_slot[1 + PNR_OBS_DIM + 126 + i], (double)b);
                 }
             }
-            if (blockIdx.x == 0 && lane == 0) atomicAdd(&f_delta[0], (double)N);
+            if (blockIdx.x == 0 && lane == 0) atomicAdd(&f_delta[0], (double)N * multi.n_steps);
         }
     }
-    if (part == 3 && lane == 0 && blockIdx.x == 0) atomicAdd(&stats->env_steps, (double)N);   // one writer per launch; chained launches overlap
+    if (part == 3 && lane == 0 && blockIdx.x == 0) atomicAdd(&stats->env_steps, (double)N * multi.n_steps);   // one writer per launch; chained launches overlap
     if (part == 3 && lane == 0) pnr_bulk_wait_read<0>();      // smem must outlive the copy engine's reads
 #ifdef PNR_TRACE
     trace_iter = 0;
@@ -618,9 +640,9 @@ static int64_t pnr_grid_for(int64_t n_envs, int envs_per_cta, int resident) {
 
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions, float* obs,
                             float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain, const float* f_applied,
-                            double* f_delta, float f_clip, PnrChain chain, cudaStream_t stream) {
+                            double* f_delta, float f_clip, PnrChain chain, PnrMulti multi, cudaStream_t stream) {
     typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, uint32_t,
-                         const float*, double*, float, const PnrChain);
+                         const float*, double*, float, const PnrChain, const PnrMulti);
     // the obstacle variant and the fused normaliser are separate instantiations: the plain kernel carries no trace of
     // them (a call site alone cost 40 % at 1M envs through caller-saved register spills)
     static Kern kernels[2][2][2] = {
@@ -659,7 +681,7 @@ cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_m
     // on long grids the early-resident successor only takes SM slots from this grid (1,048,576 envs: 146 -> 151 us)
     attr[0].val.programmaticStreamSerializationAllowed = (pnr_pdl_enabled() && n_tiles <= 8192) ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k, p, state, actions, obs, reward, done, stats, tick, domain, f_applied, f_delta, f_clip, chain);
+    return cudaLaunchKernelEx(&cfg, k, p, state, actions, obs, reward, done, stats, tick, domain, f_applied, f_delta, f_clip, chain, multi);
 }
 
 cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, float4* state, const int64_t* idx, int64_t n,
