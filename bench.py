@@ -48,6 +48,11 @@ L2_FLUSH_BYTES = 512 << 20                           # > 4x the 126 MB L2
 DYN_FLOP_PER_ENV_STEP = 2 * 5396 + 2526 + 1197
 DYN_FP_INSTR_PER_ENV_STEP = 5396 + 2526 + 1197
 FP32_PEAK_TFLOPS = 72.6
+# measured with tools/fp32_forms.py (profiles/r02_fp32_forms.md): a stream of THREE-REGISTER FFMAs issues at 0.711 warp
+# instructions per clock per SM sub-partition (operand delivery), two-register FMUL / FADD at 0.976: the FP32 instructions of
+# one K2 env-step alone need this many clocks per 32-env tile per sub-partition
+DYN_OPERAND_BOUND_CLOCKS = 5396 / 0.711 + (2526 + 1197) / 0.976
+SM_SUBPARTITIONS, SM_CLOCK_HZ = 148 * 4, 1.965e9
 
 def parse_args():
     ap = argparse.ArgumentParser()
@@ -662,7 +667,13 @@ def ours_arm(args):
                 "roofline": {"bound": "fp32", "achieved": tf, "peak": FP32_PEAK_TFLOPS, "unit": "TFLOP/s",
                              "frac": tf / FP32_PEAK_TFLOPS, "flop_per_env_step": DYN_FLOP_PER_ENV_STEP,
                              "fp32_issue_frac": (v / world) * DYN_FP_INSTR_PER_ENV_STEP / (FP32_PEAK_TFLOPS / 2 * 1e12),
-                             "peak_source": "tools/fma_peak.py on this pool's B200 (FMA = 2 flop)", "kernel": kernel}}
+                             "peak_source": "tools/fma_peak.py on this pool's B200 (FMA = 2 flop)", "kernel": kernel,
+                             # context: the same kernel against what its own FP32 instruction stream can issue at best,
+                             # given the measured three-register FFMA rate (profiles/r02_fp32_forms.md)
+                             "operand_bound": {
+                                 "env_steps_per_s": SM_SUBPARTITIONS * SM_CLOCK_HZ / DYN_OPERAND_BOUND_CLOCKS * 32,
+                                 "frac": (v / world) / (SM_SUBPARTITIONS * SM_CLOCK_HZ / DYN_OPERAND_BOUND_CLOCKS * 32),
+                                 "three_register_ffma_per_clock_per_smsp": 0.711}}}
 
     if not args.no_extras:
         line["dynamic_mode"] = dyn_record(n, timed_extra(dyn_env(n), 2), "pnr_step_dynamic_kernel<TERMINAL,false,PIONEER_ISO>")

@@ -534,7 +534,7 @@ static int pnr_step_impl(pnr_handle* h, const float* actions, float* obs, float*
         PNR_CUDA(pnr_launch_step_dynamic(h->params, h->device, h->cfg.obs_mode, h->state, actions, obs, reward, done,
                                          h->stats, h->tick, domain, h->filt_fused ? h->filt_applied : nullptr,
                                          (h->filt_fused && h->filt_fused_update) ? h->filt_delta : nullptr,
-                                         (float)h->filt_clip, chain, (cudaStream_t)stream));
+                                         (float)h->filt_clip, chain, multi, (cudaStream_t)stream));
     else
         PNR_CUDA(pnr_launch_step(h->params, h->device, h->cfg.arith, h->cfg.obs_mode, h->state, actions, obs, reward, done,
                                  h->stats, h->tick, domain, h->filt_fused ? h->filt_applied : nullptr,
@@ -558,10 +558,12 @@ extern "C" int pnr_step_many(pnr_handle* h, int32_t n_steps, const float* action
     // stream through many short tiles, the chained successor catches up at once and then polls at its heels.
     // The sequence words carry (epoch << 8 | step), the epoch is unique per chunk of <= 200 steps, so a word left behind by an earlier call never matches.  PNR_NO_CHAIN=1: grid-wide waits.
     static const bool chain_on = getenv("PNR_NO_CHAIN") == nullptr;
-    // Kinematic mode: the whole fragment is ONE launch (PnrMulti): every CTA runs the n_steps steps on its own tiles with a
-    // CTA barrier between them -- no launch gap, no grid-wide wait (PNR_NO_FUSE=1: one launch per step).
+    // The whole fragment is ONE launch (PnrMulti): every CTA (kinematic kernel; a CTA barrier between the steps) or warp
+    // (dynamic kernel; the env state stays in registers) runs the n_steps steps on its own tiles -- no launch gap, no
+    // grid-wide wait (PNR_NO_FUSE=1: one launch per step; PNR_FUSE_MODES: bit 0 kinematic, bit 1 dynamic).
     static const bool fuse_on = getenv("PNR_NO_FUSE") == nullptr;
-    if (fuse_on && h->cfg.mode == PNR_MODE_KINEMATIC && n_steps > 1) {
+    static const int fuse_modes = getenv("PNR_FUSE_MODES") ? atoi(getenv("PNR_FUSE_MODES")) : 3;      // bit 0 kinematic, bit 1 dynamic
+    if (fuse_on && ((fuse_modes >> (h->cfg.mode == PNR_MODE_DYNAMIC ? 1 : 0)) & 1) && n_steps > 1) {
         if ((reinterpret_cast<uintptr_t>(obs) & 15) || ((obs_stride * sizeof(float)) & 15))
             return pnr_fail(PNR_ERR_INVALID, "pnr_step_many: obs and obs_stride * 4 must be multiples of 16 bytes");
         if ((action_stride * sizeof(float)) & 7)

@@ -16,7 +16,8 @@ static int pnr_dyn_resident(const void* fn) {
 
 cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode, float4* state, const float* actions,
                                     float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain,
-                                    const float* f_applied, double* f_delta, float f_clip, PnrChain chain_seq, cudaStream_t stream) {
+                                    const float* f_applied, double* f_delta, float f_clip, PnrChain chain_seq, PnrMulti multi,
+                                    cudaStream_t stream) {
     typedef PnrDynKernel Kern;
 #define PNR_DYN_ROW(CH, ST) \
     {{pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, false, CH, ST>, pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, true, CH, ST>}, \
@@ -53,5 +54,5 @@ cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode
     attr[0].val.programmaticStreamSerializationAllowed = pnr_pdl_enabled() ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, p, state, actions, obs, reward, done, stats, tick, domain, f_applied, f_delta, f_clip,
-                              chain_seq);
+                              chain_seq, multi);
 }

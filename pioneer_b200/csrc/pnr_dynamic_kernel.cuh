@@ -6,7 +6,7 @@
 #include "pnr_launch.h"
 
 typedef void (*PnrDynKernel)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, uint32_t,
-                             const float*, double*, float, const PnrChain);
+                             const float*, double*, float, const PnrChain, const PnrMulti);
 // [chain][obs_mode][obstacles] of the Bullet-like instantiations (pnr_dynamic_bullet.cu)
 PnrDynKernel pnr_dynamic_bullet_kernel(int chain, int obs_mode, int obst);
 
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(PNR_DYN_THREADS, STEPPING == PNR_STEPPING_BULL
 pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                         float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                         PnrStats* __restrict__ stats, uint32_t tick, uint32_t domain, const float* __restrict__ f_applied,
-                        double* __restrict__ f_delta, float f_clip, const PnrChain chain) {
+                        double* __restrict__ f_delta, float f_clip, const PnrChain chain, const PnrMulti multi) {
     extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int hl = lane & 15;                                  // row of the half tile this lane packs
@@ -79,7 +79,16 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         PnrEnv s;
         pnr_chain_wait(chain, t_idx, lane);
         pnr_load_env_cg(state, N, env, s);
-        const float2* a2 = reinterpret_cast<const float2*>(actions + env * PNR_DOF);
+        // a rollout fragment in ONE launch (PnrMulti, pnr_step_many): the warp keeps its tile and runs n_steps consecutive
+        // steps on it with the env state in registers -- tiles never depend on each other (1 for an ordinary pnr_step)
+#pragma unroll 1
+        for (int32_t step = 0; step < multi.n_steps; ++step) {
+        const float* __restrict__ const act_s = actions + (int64_t)step * multi.act_stride;
+        float* __restrict__ const obs_s = obs + (int64_t)step * multi.obs_stride;
+        float* __restrict__ const reward_s = reward + (int64_t)step * N;
+        uint8_t* __restrict__ const done_s = done + (int64_t)step * N;
+        const uint32_t tick_s = tick + (uint32_t)step;
+        const float2* a2 = reinterpret_cast<const float2*>(act_s + env * PNR_DOF);
         const float2 act01 = pnr_ld_stream(a2), act23 = pnr_ld_stream(a2 + 1), act45 = pnr_ld_stream(a2 + 2);
         // the action drives THIS step's substeps (a motor target, not the kinematic env's delayed acceleration)
         s.a[0] = act01.x; s.a[1] = act01.y; s.a[2] = act23.x; s.a[3] = act23.y; s.a[4] = act45.x; s.a[5] = act45.y;
@@ -106,8 +115,8 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         const bool is_done = reached || timeout;
         const uint8_t flags = (is_done ? PNR_DONE : 0) | ((timeout && !reached) ? PNR_TRUNCATED : 0);
         if (active) {
-            reward[env] = rew;
-            done[env] = flags;
+            reward_s[env] = rew;
+            done_s[env] = flags;
         }
         pnr_episode_stats(stats, is_done && active, reached && active, s.ep_ret, s.t, lane);
 
@@ -120,7 +129,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         PnrEnv so = s;
         if (do_reset) {
             float q[PNR_DOF], tg[3], box[5];
-            pnr_reset_draws(p, p.env_id_base + env, pnr_reset_key(p, pnr_tickdom(tick, domain)), q, tg, box);
+            pnr_reset_draws(p, p.env_id_base + env, pnr_reset_key(p, pnr_tickdom(tick_s, domain)), q, tg, box);
             pnr_reset_env(s, q, tg);
             if (active) pnr_store_box(p, env, box);
         }
@@ -131,8 +140,10 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
                 if (do_reset) { o = o2; so = s; fast = true; }
             }
         }
-        if (active) pnr_store_env(state, N, env, s);
-        pnr_chain_publish(chain, t_idx, lane);                  // the next step may start on this tile now
+        if (step + 1 == multi.n_steps) {                        // the state goes back to memory after the tile's last step
+            if (active) pnr_store_env(state, N, env, s);
+            pnr_chain_publish(chain, t_idx, lane);              // the next (chained) launch may start on this tile now
+        }
 
         // ---- observation: two half tiles of 16 rows; in round h the lane pair (l, l + 16) packs env 16 h + l
         // the partner lane receives joints 3..5 of its pair's env (one exchange serves both rounds)
@@ -204,22 +215,23 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
                     }
                 }
             }
-            pnr_emit_tile(tile, obs + t_idx * (int64_t)PNR_TILE_FLOATS + (int64_t)h * PNR_HALF_FLOATS, rows_half, lane);
+            pnr_emit_tile(tile, obs_s + t_idx * (int64_t)PNR_TILE_FLOATS + (int64_t)h * PNR_HALF_FLOATS, rows_half, lane);
             tile_busy = true;
         }
+        }                                                       // steps of the fragment
     }
     if (filt && f_delta && blockIdx.x == 0 && warp == 0) {         // rows pushed + the constant columns of all N rows
-        if (lane == 0) atomicAdd(&f_delta[0], (double)N);
+        if (lane == 0) atomicAdd(&f_delta[0], (double)N * multi.n_steps);
         for (int c = 18 + lane; c < 54; c += 32) {
             const int g = (c - 18) / PNR_DOF, j = (c - 18) % PNR_DOF;
             const float x = g == 0 ? p.r_lo[j] : g == 1 ? p.cos_r_lo[j] : g == 2 ? p.sin_r_lo[j]
                           : g == 3 ? p.r_hi[j] : g == 4 ? p.cos_r_hi[j] : p.sin_r_hi[j];
             const double d = (double)(x - f_applied[c]);
-            atomicAdd(&f_delta[1 + c], (double)N * d);
-            atomicAdd(&f_delta[1 + PNR_OBS_DIM + c], (double)N * d * d);
+            atomicAdd(&f_delta[1 + c], (double)N * multi.n_steps * d);
+            atomicAdd(&f_delta[1 + PNR_OBS_DIM + c], (double)N * multi.n_steps * d * d);
         }
     }
-    if (blockIdx.x == 0 && warp == 0 && lane == 0) atomicAdd(&stats->env_steps, (double)N);   // one writer per launch; chained launches overlap
+    if (blockIdx.x == 0 && warp == 0 && lane == 0) atomicAdd(&stats->env_steps, (double)N * multi.n_steps);   // one writer per launch; chained launches overlap
     if (lane == 0) pnr_bulk_wait_read<0>();
 }
 
