@@ -338,10 +338,10 @@ def ncu_traffic(lib, n):
 
 
 def time_fragments(torch, env, actions, obs_ring, reward, flags, steps, warmup, flush, fragment=FRAGMENT):
-    """EXACTLY `steps` env steps, launched as rollout fragments of `fragment` steps back to back (pnr_step_many: the kernels
-    overlap by programmatic dependent launch, consecutive steps write different slots of the observation ring); an untimed
-    L2 flush (512 MiB memset) runs between fragments and every fragment is bracketed by its own CUDA-event pair on the
-    launching stream.  Returns (sum of fragment ms, list of (ms, steps) per fragment)."""
+    """EXACTLY `steps` env steps, launched as rollout fragments of `fragment` steps (pnr_step_many: ONE kernel launch per
+    fragment, every CTA / warp runs the fragment's steps on its own tiles; consecutive steps write different slots of the
+    observation ring); an untimed L2 flush (512 MiB memset) runs between fragments and every fragment is bracketed by its
+    own CUDA-event pair on the launching stream.  Returns (sum of fragment ms, list of (ms, steps) per fragment)."""
     T = min(fragment, obs_ring.shape[0], actions.shape[0])
     done, k = 0, 0
     while done < warmup:
@@ -357,6 +357,7 @@ def time_fragments(torch, env, actions, obs_ring, reward, flags, steps, warmup, 
     starts = [torch.cuda.Event(enable_timing=True) for _ in plan]
     stops = [torch.cuda.Event(enable_timing=True) for _ in plan]
     torch.cuda.synchronize()
+    launches0 = env.launch_count
     for k, t in enumerate(plan):
         if flush is not None:
             flush()
@@ -364,6 +365,7 @@ def time_fragments(torch, env, actions, obs_ring, reward, flags, steps, warmup, 
         env.step_many(actions[:t], obs_ring[:t], reward[:t], flags[:t])
         stops[k].record()
     torch.cuda.synchronize()
+    time_fragments.launches = env.launch_count - launches0        # kernels of this library inside the timed region
     per = [(s.elapsed_time(e), t) for s, e, t in zip(starts, stops, plan)]
     return sum(ms for ms, _ in per), per
 
@@ -509,10 +511,9 @@ def ours_arm(args):
     barrier()
     if sampler:
         sampler.start()
-    launches0 = env.launch_count
     wall0 = time.perf_counter()
     kernel_ms, per_frag = time_fragments(torch, env, actions, obs_ring, reward, flags, args.steps, args.warmup, flush)
-    launches = env.launch_count - launches0 - args.warmup
+    launches = time_fragments.launches
     barrier()
     wall_s = time.perf_counter() - wall0
     kernel_ms_max = max_over_ranks(kernel_ms)
@@ -597,8 +598,8 @@ def ours_arm(args):
                    "l2": ("NOT FLUSHED (profiling run, not a bench value); " if args.flush == "none" else
                           f"flushed between timed fragments ({L2_FLUSH_BYTES >> 20} MiB memset"
                           + (" then a 512 MiB read sweep" if args.flush != "write" else "") + ", untimed); ")
-                         + f"a fragment = {FRAGMENT} consecutive steps launched back to back (pnr_step_many, programmatic "
-                           "dependent launch), each fragment timed by its own CUDA-event pair on the launching stream; within a "
+                         + f"a fragment = {FRAGMENT} consecutive steps in ONE kernel launch (pnr_step_many: every CTA runs the "
+                           "steps on its own tiles), each fragment timed by its own CUDA-event pair on the launching stream; within a "
                            f"fragment the {n * 96 // 1000000} MB of env state stay L2-resident as in any rollout loop, the "
                            f"{obs_ring.shape[0]} x {n * OBS_DIM * 4 // 1000000} MB observation slots do not fit",
                    "parallelism": f"env-sharded x{world}, no data-path collective; one stats all-gather per iteration"},

@@ -177,10 +177,11 @@ int pnr_reset(pnr_handle* h, const int64_t* idx, int64_t n, const float* q0, con
  * reward DEVICE float[N]; done DEVICE uint8[N] (PNR_DONE | PNR_TRUNCATED bits). */
 int pnr_step(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, void* stream);
 
-/* A rollout fragment with pre-computed actions: n_steps consecutive pnr_step calls issued back to back from C.  Step t reads
+/* A rollout fragment with pre-computed actions: n_steps consecutive steps in ONE kernel launch.  Step t reads
  * actions + t * action_stride and writes obs + t * obs_stride (strides in floats; obs_stride * 4 must be a multiple of 16
- * bytes), reward + t * N, done + t * N.  The step kernels are launched with programmatic dependent launch, so the tail of
- * step t (its last bulk stores draining) overlaps the set-up of step t + 1. */
+ * bytes, action_stride * 4 of 8), reward + t * N, done + t * N; results are those of n_steps pnr_step calls, bit for bit.
+ * Envs never depend on each other, so inside the launch every CTA (kinematic mode) or warp (dynamic mode, env state kept in
+ * registers) runs the n_steps steps on its own 32-env tiles: no launch gap and no grid-wide wait between the steps. */
 int pnr_step_many(pnr_handle* h, int32_t n_steps, const float* actions, int64_t action_stride, float* obs,
                   int64_t obs_stride, float* reward, uint8_t* done, void* stream);
 

@@ -221,7 +221,8 @@ class BatchedPioneerEnv:
 
     def step_many(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, flags: torch.Tensor) -> None:
         """A rollout fragment with pre-computed actions (pnr_step_many): ``actions`` [T,N,6] -> ``obs`` [T,N,137], ``reward``
-        [T,N], ``flags`` [T,N], T fused steps launched back to back from C with programmatic dependent launch."""
+        [T,N], ``flags`` [T,N]: T steps in ONE kernel launch (every CTA / warp runs the T steps on its own tiles), bit for
+        bit what T ``step_tensor`` calls return."""
         T = actions.shape[0]
         assert actions.shape == (T, self.n_envs, DOF) and obs.shape == (T, self.n_envs, OBS_DIM)
         assert reward.shape == (T, self.n_envs) and flags.shape == (T, self.n_envs)
@@ -234,9 +235,8 @@ class BatchedPioneerEnv:
 
     def capture_rollout(self, actions: torch.Tensor, obs: torch.Tensor, reward: torch.Tensor, flags: torch.Tensor):
         """Capture T consecutive steps into ONE CUDA graph: ``actions`` [T,N,6] -> ``obs`` [T,N,137], ``reward`` [T,N],
-        ``flags`` [T,N] (caller-owned device tensors, re-read / re-written on every replay).  Replaying the graph
-        costs one launch for T fused kernels, which removes the host's per-step launch cost from a rollout
-        fragment whose actions are produced on the device.  Returns the torch.cuda.CUDAGraph; ``graph.replay()``
+        ``flags`` [T,N] (caller-owned device tensors, re-read / re-written on every replay).  The graph holds two nodes:
+        the counter advance and one pnr_step_many launch that runs the T steps.  Returns the torch.cuda.CUDAGraph; ``graph.replay()``
         advances every env by T steps.  The host-side call counter that keys the reset generator is frozen into the
         graph, so the graph's first node advances a device-side counter by T (pnr_tick_advance): every replay draws
         fresh reset states."""
@@ -255,8 +255,7 @@ class BatchedPioneerEnv:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 _cabi.check(self._lib.pnr_tick_advance(self._h, T, self._stream()), "pnr_tick_advance")
-                for t in range(T):
-                    self.step_tensor(actions[t], out=(obs[t], reward[t], flags[t]))
+                self.step_many(actions, obs, reward, flags)                     # the T steps are ONE kernel node
         return graph
 
     def advance_reset_counter(self, n: int) -> None:

@@ -38,8 +38,6 @@ struct pnr_handle {
     uint64_t seed = 0;              // host copy of the key in PnrStats::seed_*
     uint32_t n_graphs = 0;          // CUDA graphs this handle's steps were captured into: each gets its own reset-key domain
     unsigned long long capture_id = 0;
-    uint32_t* tile_seq = nullptr;   // per-tile sequence words of chained steps (PnrChain), one per 32 envs
-    uint32_t chain_epoch = 0;
     float4* box_a = nullptr;        // per-env random box (cfg.random_box): centre x y | half extents x y
     float* box_z = nullptr;         //                                      half height = centre z
     int64_t launches = 0;
@@ -383,11 +381,6 @@ extern "C" int pnr_create(const pnr_model* model, const pnr_config* cfg, int64_t
         h->params.box_z = h->box_z;
     }
     if ((e = cudaMalloc(&h->stats_out, sizeof(double) * PNR_STATS_LEN)) != cudaSuccess) return bail(e, "cudaMalloc(stats_out)");
-    {
-        const size_t n_tiles = ((size_t)n_envs + 31) / 32;
-        if ((e = cudaMalloc(&h->tile_seq, sizeof(uint32_t) * n_tiles)) != cudaSuccess) return bail(e, "cudaMalloc(tile_seq)");
-        if ((e = cudaMemset(h->tile_seq, 0, sizeof(uint32_t) * n_tiles)) != cudaSuccess) return bail(e, "cudaMemset(tile_seq)");
-    }
     if ((e = cudaMallocHost(&h->stats_host, sizeof(double) * PNR_STATS_LEN)) != cudaSuccess) return bail(e, "cudaMallocHost");
     // clear statistics, then reset every env (reset_world) with tick 0
     if ((e = pnr_launch_stats_snapshot(h->stats, h->stats_out, 1, nullptr)) != cudaSuccess) return bail(e, "stats init");
@@ -410,7 +403,7 @@ extern "C" void pnr_destroy(pnr_handle* h) {
         for (cudaEvent_t ev : {sl.kernel_done, sl.copy1_done, sl.copy2_done}) if (ev) cudaEventDestroy(ev);
         cudaFree(sl.actions); cudaFree(sl.obs); cudaFree(sl.reward); cudaFree(sl.compact); cudaFree(sl.done);
     }
-    cudaFree(h->state); cudaFree(h->stats); cudaFree(h->stats_out); cudaFree(h->box_a); cudaFree(h->box_z); cudaFree(h->tile_seq);
+    cudaFree(h->state); cudaFree(h->stats); cudaFree(h->stats_out); cudaFree(h->box_a); cudaFree(h->box_z);
     cudaFree(h->filt_delta); cudaFree(h->filt_applied); cudaFree(h->filt_state); cudaFree(h->filt_merged);
     if (h->stats_host) cudaFreeHost(h->stats_host);
     delete h;
@@ -511,7 +504,7 @@ extern "C" int pnr_observe(pnr_handle* h, const int64_t* idx, int64_t n, float* 
 }
 
 static int pnr_step_impl(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, void* stream,
-                         uint32_t chain_wait, uint32_t chain_publish, bool* capturing, PnrMulti multi = PnrMulti{1, 0, 0}) {
+                         PnrMulti multi = PnrMulti{1, 0, 0}) {
     if (!h || !actions || !obs || !reward || !done) return pnr_fail(PNR_ERR_INVALID, "pnr_step: null argument");
     if ((reinterpret_cast<uintptr_t>(obs) & 15) || (reinterpret_cast<uintptr_t>(actions) & 7))
         return pnr_fail(PNR_ERR_INVALID, "pnr_step: obs must be 16-byte and actions 8-byte aligned");
@@ -526,63 +519,43 @@ static int pnr_step_impl(pnr_handle* h, const float* actions, float* obs, float*
             domain = h->n_graphs;
         }
     }
-    if (capturing) *capturing = domain != 0;
-    if (domain != 0) chain_wait = chain_publish = 0;             // a graph replays: the per-call epoch would be stale
-    static const uint32_t late = getenv("PNR_CHAIN_LATE") ? 1u : 0u;   // developer knob: trigger the dependent launch late
-    const PnrChain chain = {h->tile_seq, chain_wait, chain_publish, late};
     if (h->cfg.mode == PNR_MODE_DYNAMIC)
         PNR_CUDA(pnr_launch_step_dynamic(h->params, h->device, h->cfg.obs_mode, h->state, actions, obs, reward, done,
                                          h->stats, h->tick, domain, h->filt_fused ? h->filt_applied : nullptr,
                                          (h->filt_fused && h->filt_fused_update) ? h->filt_delta : nullptr,
-                                         (float)h->filt_clip, chain, multi, (cudaStream_t)stream));
+                                         (float)h->filt_clip, multi, (cudaStream_t)stream));
     else
         PNR_CUDA(pnr_launch_step(h->params, h->device, h->cfg.arith, h->cfg.obs_mode, h->state, actions, obs, reward, done,
                                  h->stats, h->tick, domain, h->filt_fused ? h->filt_applied : nullptr,
                                  (h->filt_fused && h->filt_fused_update) ? h->filt_delta : nullptr, (float)h->filt_clip,
-                                 chain, multi, (cudaStream_t)stream));
+                                 multi, (cudaStream_t)stream));
     h->tick += (uint32_t)multi.n_steps;
     h->launches += 1;
     return PNR_OK;
 }
 
 extern "C" int pnr_step(pnr_handle* h, const float* actions, float* obs, float* reward, uint8_t* done, void* stream) {
-    return pnr_step_impl(h, actions, obs, reward, done, stream, 0u, 0u, nullptr);
+    return pnr_step_impl(h, actions, obs, reward, done, stream);
 }
 
 extern "C" int pnr_step_many(pnr_handle* h, int32_t n_steps, const float* actions, int64_t action_stride, float* obs,
                              int64_t obs_stride, float* reward, uint8_t* done, void* stream) {
     if (!h || n_steps < 0) return pnr_fail(PNR_ERR_INVALID, "pnr_step_many: bad argument");
-    // Consecutive steps of one call are chained tile by tile (PnrChain): step t + 1 starts on a tile as soon as step t has
-    // stored that tile's state.  On by default for the dynamic kernel only (PNR_CHAIN_MODES: bit 0 kinematic, bit 1 dynamic):
-    // measured on B200, the kinematic kernel gains 4 % at 65,536 envs but loses 40 % at 4,096 and 1,048,576 envs -- its CTAs
-    // stream through many short tiles, the chained successor catches up at once and then polls at its heels.
-    // The sequence words carry (epoch << 8 | step), the epoch is unique per chunk of <= 200 steps, so a word left behind by an earlier call never matches.  PNR_NO_CHAIN=1: grid-wide waits.
-    static const bool chain_on = getenv("PNR_NO_CHAIN") == nullptr;
     // The whole fragment is ONE launch (PnrMulti): every CTA (kinematic kernel; a CTA barrier between the steps) or warp
-    // (dynamic kernel; the env state stays in registers) runs the n_steps steps on its own tiles -- no launch gap, no
-    // grid-wide wait (PNR_NO_FUSE=1: one launch per step; PNR_FUSE_MODES: bit 0 kinematic, bit 1 dynamic).
+    // (dynamic kernel; the env state stays in registers) runs the n_steps steps on its own tiles -- tiles never depend on each
+    // other, so there is no launch gap and no grid-wide wait between the steps.  PNR_NO_FUSE=1 (developer knob): one launch
+    // per step, overlapped by programmatic dependent launch only.
     static const bool fuse_on = getenv("PNR_NO_FUSE") == nullptr;
-    static const int fuse_modes = getenv("PNR_FUSE_MODES") ? atoi(getenv("PNR_FUSE_MODES")) : 3;      // bit 0 kinematic, bit 1 dynamic
-    if (fuse_on && ((fuse_modes >> (h->cfg.mode == PNR_MODE_DYNAMIC ? 1 : 0)) & 1) && n_steps > 1) {
+    if (fuse_on && n_steps > 1) {
         if ((reinterpret_cast<uintptr_t>(obs) & 15) || ((obs_stride * sizeof(float)) & 15))
             return pnr_fail(PNR_ERR_INVALID, "pnr_step_many: obs and obs_stride * 4 must be multiples of 16 bytes");
         if ((action_stride * sizeof(float)) & 7)
             return pnr_fail(PNR_ERR_INVALID, "pnr_step_many: action_stride * 4 must be a multiple of 8 bytes");
-        return pnr_step_impl(h, actions, obs, reward, done, stream, 0u, 0u, nullptr, PnrMulti{n_steps, action_stride, obs_stride});
+        return pnr_step_impl(h, actions, obs, reward, done, stream, PnrMulti{n_steps, action_stride, obs_stride});
     }
-    static const int chain_modes = getenv("PNR_CHAIN_MODES") ? atoi(getenv("PNR_CHAIN_MODES")) : 2;   // developer knob
-    const bool chained = chain_on && pnr_pdl_enabled() && ((chain_modes >> (h->cfg.mode == PNR_MODE_DYNAMIC ? 1 : 0)) & 1);
-    uint32_t epoch = 0, k = 0;
-    for (int32_t t = 0; t < n_steps; ++t, ++k) {
-        if (chained && (t == 0 || k == 200)) {
-            h->chain_epoch = (h->chain_epoch % 0xFFFFFFu) + 1;   // 1 .. 2^24 - 1, never 0
-            epoch = h->chain_epoch << 8;
-            k = 0;
-        }
-        bool capturing = false;
+    for (int32_t t = 0; t < n_steps; ++t) {
         int rc = pnr_step_impl(h, actions + (int64_t)t * action_stride, obs + (int64_t)t * obs_stride,
-                               reward + (int64_t)t * h->n_envs, done + (int64_t)t * h->n_envs, stream,
-                               (chained && k > 0) ? (epoch | k) : 0u, chained ? (epoch | (k + 1)) : 0u, &capturing);
+                               reward + (int64_t)t * h->n_envs, done + (int64_t)t * h->n_envs, stream);
         if (rc != PNR_OK) return rc;
     }
     return PNR_OK;

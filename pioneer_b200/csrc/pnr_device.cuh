@@ -185,43 +185,6 @@ __device__ __forceinline__ void pnr_bulk_wait_read() {      // returns once at m
 __device__ __forceinline__ void pnr_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pnr_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Tile-level chaining of consecutive steps (pnr_step_many).  Envs are independent, so tile i of step t + 1 depends on tile
-// i of step t and on nothing else: instead of the grid-wide pnr_pdl_wait() a chained step spins, per tile, on a sequence
-// word that the previous step publishes (release) right after it has stored the tile's state planes.  With programmatic
-// dependent launch the next step's CTAs take the SM slots the current step frees one by one and start on their tiles at
-// once, so the ragged end of one step (wave quantisation: 2,048 tiles over 592 schedulers) is filled with the next step's
-// work.  `wait` / `publish` are (call epoch << 8 | step), unique per pnr_step_many call; 0 = not chained.
-struct PnrChain { uint32_t* seq; uint32_t wait, publish, late_trigger; };
-__device__ __forceinline__ void pnr_chain_wait(const PnrChain& c, int64_t tile, int lane) {
-    if (c.wait) {                                              // launch-uniform
-        if (lane == 0) {
-            const uint32_t* w = c.seq + tile;
-            uint32_t v;
-            // The predecessor is earlier in the same stream and never waits for anything, and a chained launch cannot start
-            // before every CTA of its predecessor is resident (the PDL trigger is the first thing a CTA executes), so this
-            // wait always ends.  The bound (about two seconds) turns a broken invariant into an error instead of a hang.
-            for (uint32_t spins = 0;; ++spins) {
-                asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(w) : "memory");
-                if (v == c.wait) break;
-#if defined(__CUDA_ARCH__) && __CUDA_ARCH__ >= 700
-                __nanosleep(64);
-#endif
-                if (spins > (1u << 24)) __trap();
-            }
-        }
-        __syncwarp();
-    }
-}
-__device__ __forceinline__ void pnr_chain_publish(const PnrChain& c, int64_t tile, int lane) {
-    if (c.publish) {
-        __syncwarp();                                          // every lane's state stores are ordered before the release
-        if (lane == 0) {
-            __threadfence();
-            asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(c.seq + tile), "r"(c.publish) : "memory");
-        }
-    }
-}
-
 // A rollout fragment in ONE launch of the kinematic step kernel (pnr_step_many): the CTA keeps its tiles and runs n_steps
 // consecutive steps on them -- tiles never depend on each other, so no grid-wide synchronisation is needed between the
 // steps, only a CTA barrier.  Step s reads actions + s * act_stride and writes obs + s * obs_stride (floats), reward / done

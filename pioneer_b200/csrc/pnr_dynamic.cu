@@ -16,8 +16,7 @@ static int pnr_dyn_resident(const void* fn) {
 
 cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode, float4* state, const float* actions,
                                     float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain,
-                                    const float* f_applied, double* f_delta, float f_clip, PnrChain chain_seq, PnrMulti multi,
-                                    cudaStream_t stream) {
+                                    const float* f_applied, double* f_delta, float f_clip, PnrMulti multi, cudaStream_t stream) {
     typedef PnrDynKernel Kern;
 #define PNR_DYN_ROW(CH, ST) \
     {{pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, false, CH, ST>, pnr_step_dynamic_kernel<PNR_OBS_TERMINAL, true, CH, ST>}, \
@@ -37,12 +36,6 @@ cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode
         if (e != cudaSuccess) return e;
         resident = pnr_dyn_resident((const void*)kern);
     }
-    // Tile-level chaining pays when a CTA works through several tiles (the next step then fills the ragged end of this one:
-    // 131,072 envs 68.6 -> 56.6 us per step); when every warp owns exactly one tile the chain of a tile is strictly serial
-    // and early-launched successors only take slots (65,536 envs 37.7 -> 46.9 us): such launches wait grid-wide instead.
-    // (the decision depends on the batch size only, so every launch of a call takes the same one; not publishing either saves
-    // the release fence: 3 % of the stall samples of a 65,536-env launch, profiles/r02_a_step_dynamic_65536.md)
-    if ((p.n_envs + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS <= (int64_t)resident * PNR_DYN_WARPS) chain_seq.wait = chain_seq.publish = 0;
     const int64_t per_cta = PNR_TILE_ENVS * PNR_DYN_WARPS;
     int64_t grid = (p.n_envs + per_cta - 1) / per_cta;
     if (grid > resident) grid = resident;
@@ -54,5 +47,5 @@ cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode
     attr[0].val.programmaticStreamSerializationAllowed = pnr_pdl_enabled() ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
     return cudaLaunchKernelEx(&cfg, kern, p, state, actions, obs, reward, done, stats, tick, domain, f_applied, f_delta, f_clip,
-                              chain_seq, multi);
+                              multi);
 }

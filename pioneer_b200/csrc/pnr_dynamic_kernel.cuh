@@ -6,7 +6,7 @@
 #include "pnr_launch.h"
 
 typedef void (*PnrDynKernel)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, uint32_t,
-                             const float*, double*, float, const PnrChain, const PnrMulti);
+                             const float*, double*, float, const PnrMulti);
 // [chain][obs_mode][obstacles] of the Bullet-like instantiations (pnr_dynamic_bullet.cu)
 PnrDynKernel pnr_dynamic_bullet_kernel(int chain, int obs_mode, int obst);
 
@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(PNR_DYN_THREADS, STEPPING == PNR_STEPPING_BULL
 pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                         float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                         PnrStats* __restrict__ stats, uint32_t tick, uint32_t domain, const float* __restrict__ f_applied,
-                        double* __restrict__ f_delta, float f_clip, const PnrChain chain, const PnrMulti multi) {
+                        double* __restrict__ f_delta, float f_clip, const PnrMulti multi) {
     extern __shared__ __align__(128) float smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int hl = lane & 15;                                  // row of the half tile this lane packs
@@ -49,7 +49,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
     const int64_t N = p.n_envs;
     const int64_t n_tiles = (N + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
     bool tile_busy = false;
-    if (!chain.late_trigger) pnr_pdl_trigger();                // see pnr_step_kernel: the next step's set-up runs under this tail
+    pnr_pdl_trigger();                                         // see pnr_step_kernel: the next step's set-up runs under this tail
     // obs[18:54] never change: written once per warp; the lane pair of a row shares them (r_lo block / r_hi block)
 #pragma unroll
     for (int i = 0; i < PNR_DOF; ++i) {
@@ -68,8 +68,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         for (int c = 0; c < 18; ++c)
             row[c0 + c] = pnr_normalise(row[c0 + c], f_applied[c0 + c], f_applied[PNR_OBS_DIM + c0 + c], f_clip);
     }
-    // a chained step (pnr_step_many) waits per tile instead: see PnrChain
-    if (!chain.wait) pnr_pdl_wait();                           // the previous step's state planes are complete and visible
+    pnr_pdl_wait();                                            // the previous step's state planes are complete and visible
     for (int64_t t_idx = (int64_t)blockIdx.x * PNR_DYN_WARPS + warp; t_idx < n_tiles;
          t_idx += (int64_t)gridDim.x * PNR_DYN_WARPS) {
         const int64_t env_raw = t_idx * PNR_TILE_ENVS + lane;
@@ -77,23 +76,21 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         const int64_t env = active ? env_raw : N - 1;
 
         PnrEnv s;
-        pnr_chain_wait(chain, t_idx, lane);
         pnr_load_env_cg(state, N, env, s);
         // a rollout fragment in ONE launch (PnrMulti, pnr_step_many): the warp keeps its tile and runs n_steps consecutive
         // steps on it with the env state in registers -- tiles never depend on each other (1 for an ordinary pnr_step)
 #pragma unroll 1
         for (int32_t step = 0; step < multi.n_steps; ++step) {
-        const float* __restrict__ const act_s = actions + (int64_t)step * multi.act_stride;
-        float* __restrict__ const obs_s = obs + (int64_t)step * multi.obs_stride;
-        float* __restrict__ const reward_s = reward + (int64_t)step * N;
-        uint8_t* __restrict__ const done_s = done + (int64_t)step * N;
-        const uint32_t tick_s = tick + (uint32_t)step;
-        const float2* a2 = reinterpret_cast<const float2*>(act_s + env * PNR_DOF);
+        const float2* a2 = reinterpret_cast<const float2*>(actions + (int64_t)step * multi.act_stride + env * PNR_DOF);
         const float2 act01 = pnr_ld_stream(a2), act23 = pnr_ld_stream(a2 + 1), act45 = pnr_ld_stream(a2 + 2);
         // the action drives THIS step's substeps (a motor target, not the kinematic env's delayed acceleration)
         s.a[0] = act01.x; s.a[1] = act01.y; s.a[2] = act23.x; s.a[3] = act23.y; s.a[4] = act45.x; s.a[5] = act45.y;
         pnr_dynamic_substeps<CHAIN, STEPPING>(p, s.r, s.v, s.a);
-        if (chain.late_trigger && t_idx + (int64_t)gridDim.x * PNR_DYN_WARPS >= n_tiles) pnr_pdl_trigger();   // last tile of this warp
+        // this step's output buffers (launch-uniform; formed after the substep loop so that nothing but `step` lives across it)
+        float* __restrict__ const obs_s = obs + (int64_t)step * multi.obs_stride;
+        float* __restrict__ const reward_s = reward + (int64_t)step * N;
+        uint8_t* __restrict__ const done_s = done + (int64_t)step * N;
+        const uint32_t tick_s = tick + (uint32_t)step;
 
         PnrPose o;
         pnr_pose<true>(p, s, o);                               // q is inside the joint limits
@@ -142,7 +139,6 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
         }
         if (step + 1 == multi.n_steps) {                        // the state goes back to memory after the tile's last step
             if (active) pnr_store_env(state, N, env, s);
-            pnr_chain_publish(chain, t_idx, lane);              // the next (chained) launch may start on this tile now
         }
 
         // ---- observation: two half tiles of 16 rows; in round h the lane pair (l, l + 16) packs env 16 h + l
@@ -231,7 +227,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
             atomicAdd(&f_delta[1 + PNR_OBS_DIM + c], (double)N * multi.n_steps * d * d);
         }
     }
-    if (blockIdx.x == 0 && warp == 0 && lane == 0) atomicAdd(&stats->env_steps, (double)N * multi.n_steps);   // one writer per launch; chained launches overlap
+    if (blockIdx.x == 0 && warp == 0 && lane == 0) atomicAdd(&stats->env_steps, (double)N * multi.n_steps);   // one writer per launch
     if (lane == 0) pnr_bulk_wait_read<0>();
 }
 

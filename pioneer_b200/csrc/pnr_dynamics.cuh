@@ -752,7 +752,9 @@ PNR_HD void pnr_dynamic_substeps(const PnrParams& p, float (&q)[PNR_DOF], float 
             for (int i = 0; i < PNR_DOF; ++i) {
                 float v = fmaf(qdd[i], p.dyn_dt, qd[i]);
                 float x = fmaf(v, p.dyn_dt, q[i]);
-                pnr_joint_stop(p, i, x, v);
+                // (spelled out, not pnr_joint_stop: through the helper's references ptxas emits branches instead of selects)
+                if (x > p.r_hi[i]) { x = p.r_hi[i]; if (v > 0.f) v = 0.f; }
+                if (x < p.r_lo[i]) { x = p.r_lo[i]; if (v < 0.f) v = 0.f; }
                 q[i] = x; qd[i] = v;
             }
         }

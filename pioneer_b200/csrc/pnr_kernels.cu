@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(PNR_STEP_THREADS, FILTER ? PNR_STEP_MIN_CTAS_F
 pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state, const float* __restrict__ actions,
                 float* __restrict__ obs, float* __restrict__ reward, uint8_t* __restrict__ done,
                 PnrStats* __restrict__ stats, uint32_t tick, uint32_t domain, const float* __restrict__ f_applied,
-                double* __restrict__ f_delta, float f_clip, const PnrChain chain, const PnrMulti multi) {
+                double* __restrict__ f_delta, float f_clip, const PnrMulti multi) {
     extern __shared__ __align__(128) float tiles[];           // PNR_STEP_BUFS tiles: the bulk store of one drains
     const int lane = threadIdx.x & 31;                        // while the next is being filled
     const int part = threadIdx.x >> 5;                        // warp-uniform role
@@ -154,11 +154,11 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
 
     // software pipeline: every warp loads its own planes of the NEXT tile while it works on the current one
     float4 ld4; float2 ld2, ld_act = make_float2(0.f, 0.f);
-    // (state planes through L2 only: a chained step may run on an SM whose L1 holds them as they were two steps ago)
+    // (state planes through L2 only: with programmatic dependent launch this CTA may have started on an SM before the previous
+    // step finished elsewhere; nothing is re-read, so L1 would buy nothing)
     auto issue_loads = [&](int64_t tile_idx, const float* __restrict__ act) {
         const int64_t e_raw = tile_idx * PNR_TILE_ENVS + lane;
         const int64_t e = e_raw < N ? e_raw : N - 1;
-        pnr_chain_wait(chain, tile_idx, lane);                // chained steps (pnr_step_many): the previous step is done with this tile
         if (part < 3) {
             ld4 = __ldcg(rv_plane + e);
             ld2 = __ldcg(a_plane + e);
@@ -168,7 +168,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             ld2 = __ldcg(x1_plane + e);
         }
     };
-    if (!chain.wait) pnr_pdl_wait();                          // the previous step's state planes are complete and visible
+    pnr_pdl_wait();                                           // the previous step's state planes are complete and visible
     issue_loads(t_idx, actions);
     PNR_MARK(2);
     int buf = 0;
@@ -354,8 +354,6 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             }
             if (OBS_MODE != PNR_OBS_AUTORESET && any_reset && do_reset)
                 pnr_auto_reset<OBS_MODE>(p, state, env, pnr_tickdom(tick_s, domain), row);
-            // every plane of this tile is stored (the joint warps' before the DONE barrier): the next step may start on it
-            pnr_chain_publish(chain, t_idx, lane);
         }
         PNR_MARK(8);
         PNR_TRACE_NEXT();
@@ -408,7 +406,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             if (blockIdx.x == 0 && lane == 0) atomicAdd(&f_delta[0], (double)N * multi.n_steps);
         }
     }
-    if (part == 3 && lane == 0 && blockIdx.x == 0) atomicAdd(&stats->env_steps, (double)N * multi.n_steps);   // one writer per launch; chained launches overlap
+    if (part == 3 && lane == 0 && blockIdx.x == 0) atomicAdd(&stats->env_steps, (double)N * multi.n_steps);   // one writer per launch
     if (part == 3 && lane == 0) pnr_bulk_wait_read<0>();      // smem must outlive the copy engine's reads
 #ifdef PNR_TRACE
     trace_iter = 0;
@@ -640,9 +638,9 @@ static int64_t pnr_grid_for(int64_t n_envs, int envs_per_cta, int resident) {
 
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions, float* obs,
                             float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain, const float* f_applied,
-                            double* f_delta, float f_clip, PnrChain chain, PnrMulti multi, cudaStream_t stream) {
+                            double* f_delta, float f_clip, PnrMulti multi, cudaStream_t stream) {
     typedef void (*Kern)(const PnrParams, float4*, const float*, float*, float*, uint8_t*, PnrStats*, uint32_t, uint32_t,
-                         const float*, double*, float, const PnrChain, const PnrMulti);
+                         const float*, double*, float, const PnrMulti);
     // the obstacle variant and the fused normaliser are separate instantiations: the plain kernel carries no trace of
     // them (a call site alone cost 40 % at 1M envs through caller-saved register spills)
     static Kern kernels[2][2][2] = {
@@ -681,7 +679,7 @@ cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_m
     // on long grids the early-resident successor only takes SM slots from this grid (1,048,576 envs: 146 -> 151 us)
     attr[0].val.programmaticStreamSerializationAllowed = (pnr_pdl_enabled() && n_tiles <= 8192) ? 1 : 0;
     cfg.attrs = attr; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, k, p, state, actions, obs, reward, done, stats, tick, domain, f_applied, f_delta, f_clip, chain, multi);
+    return cudaLaunchKernelEx(&cfg, k, p, state, actions, obs, reward, done, stats, tick, domain, f_applied, f_delta, f_clip, multi);
 }
 
 cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, float4* state, const int64_t* idx, int64_t n,

@@ -45,8 +45,8 @@ __device__ __forceinline__ void pnr_load_env(float4* __restrict__ S, int64_t N, 
     s.pot = x1.x; s.ep_ret = x1.y;
 }
 
-// the same through L2 only (ld.global.cg): a step that overlaps its predecessor tile by tile (pnr_step_many) may run on an
-// SM whose L1 still holds the planes as they were two steps ago
+// the same through L2 only (ld.global.cg): the planes are read once per launch, and a step launched with programmatic
+// dependent launch may sit on its SM before the previous step has finished elsewhere
 __device__ __forceinline__ void pnr_load_env_cg(float4* __restrict__ S, int64_t N, int64_t e, PnrEnv& s) {
 #pragma unroll
     for (int k = 0; k < 3; ++k) {

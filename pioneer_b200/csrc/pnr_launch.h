@@ -31,12 +31,10 @@
 // observations only; dynamic: a run-time switch, both observation modes); f_delta may be NULL (normalise, no statistics)
 cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_mode, float4* state, const float* actions,
                             float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain,
-                            const float* f_applied, double* f_delta, float f_clip, PnrChain chain, PnrMulti multi,
-                            cudaStream_t stream);
+                            const float* f_applied, double* f_delta, float f_clip, PnrMulti multi, cudaStream_t stream);
 cudaError_t pnr_launch_step_dynamic(const PnrParams& p, int device, int obs_mode, float4* state, const float* actions,
                                     float* obs, float* reward, uint8_t* done, PnrStats* stats, uint32_t tick, uint32_t domain,
-                                    const float* f_applied, double* f_delta, float f_clip, PnrChain chain, PnrMulti multi,
-                                    cudaStream_t stream);
+                                    const float* f_applied, double* f_delta, float f_clip, PnrMulti multi, cudaStream_t stream);
 cudaError_t pnr_launch_reset_observe(const PnrParams& p, int device, int mode, float4* state, const int64_t* idx,
                                      int64_t n, const float* q0, const float* target, float* obs_out, uint32_t tick,
                                      cudaStream_t stream);

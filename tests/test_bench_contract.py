@@ -44,7 +44,8 @@ def test_gpu_arm_line():
     assert out.returncode == 0, out.stderr[-3000:]
     d = _one_json_line(out.stdout)
     assert BASE_KEYS | {"roofline", "clocks", "substeps_per_sec", "timing_floor_ms", "per_step_flushed"} <= set(d)
-    assert d["n_gpus"] == 1 and d["steps"] == 30 and d["warmup"] == 3 and d["gpu_launches"] == 30
+    assert d["n_gpus"] == 1 and d["steps"] == 30 and d["warmup"] == 3
+    assert d["gpu_launches"] == 4 and d["fragment_steps"] == 8      # 30 steps = 3 fragments of 8 + one of 6, one launch each
     assert d["scaling"] == "weak" and d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"]
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
