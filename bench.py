@@ -41,17 +41,17 @@ BYTES_PER_ENV_STEP = BYTES_IO + BYTES_STATE          # 761
 FRAME_SKIP = 10
 FALLBACK_HBM_GBS = 6650.0                            # /opt/skills/guides/B200_PROFILING.md fallback
 L2_FLUSH_BYTES = 512 << 20                           # > 4x the 126 MB L2
-# Tier-B dynamic kernel, from the committed ncu capture (profiles/r02_a_step_dynamic_65536.md): 11,051,008 FFMA + 5,173,670
-# FMUL + 2,451,910 FADD warp instructions per 2,048-tile launch = FFMA 5,396 + FMUL 2,526 + FADD 1,197 thread instructions
-# per env-step (10 ABA substeps) = 14,515 flop; FP32 FMA peak measured on this pool's B200 with tools/fma_peak.py =
-# 72.6 TFLOP/s (nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)
-DYN_FLOP_PER_ENV_STEP = 2 * 5396 + 2526 + 1197
-DYN_FP_INSTR_PER_ENV_STEP = 5396 + 2526 + 1197
+# Tier-B dynamic kernel, from the committed ncu capture (profiles/r02_step_dynamic_1m.md): 356,253,696 FFMA + 164,900,085
+# FMUL + 75,836,005 FADD warp instructions per launch of 2 steps x 32,768 tiles = FFMA 5,436 + FMUL 2,516 + FADD 1,157 thread
+# instructions per env-step (10 ABA substeps) = 14,545 flop; FP32 FMA peak measured on this pool's B200 with
+# tools/fma_peak.py = 72.6 TFLOP/s (nominal 148 SMs x 128 lanes x 2 x 1.965 GHz = 74.4)
+DYN_FLOP_PER_ENV_STEP = 2 * 5436 + 2516 + 1157
+DYN_FP_INSTR_PER_ENV_STEP = 5436 + 2516 + 1157
 FP32_PEAK_TFLOPS = 72.6
 # measured with tools/fp32_forms.py (profiles/r02_fp32_forms.md): a stream of THREE-REGISTER FFMAs issues at 0.711 warp
 # instructions per clock per SM sub-partition (operand delivery), two-register FMUL / FADD at 0.976: the FP32 instructions of
 # one K2 env-step alone need this many clocks per 32-env tile per sub-partition
-DYN_OPERAND_BOUND_CLOCKS = 5396 / 0.711 + (2526 + 1197) / 0.976
+DYN_OPERAND_BOUND_CLOCKS = 5436 / 0.711 + (2516 + 1157) / 0.976
 SM_SUBPARTITIONS, SM_CLOCK_HZ = 148 * 4, 1.965e9
 
 def parse_args():
@@ -322,19 +322,22 @@ def measured_hbm_peak():
 
 
 def ncu_traffic(lib, n):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the step kernel from an `ncu --set full` capture of THIS
-    build: profiles/r02_traffic.json is keyed by the library's source hash (pnr_source_hash), so a number captured from
-    other code is never reported -- null instead."""
+    """dram__bytes_read.sum + dram__bytes_write.sum per LAUNCH of the step kernel (one launch = one rollout fragment) from an
+    `ncu --set full` capture of THIS build: profiles/r02_traffic.json is keyed by the library's source hash
+    (pnr_source_hash), so a number captured from other code is never reported -- null instead.
+    Returns (bytes per launch, steps per launch in that capture, capture file, source hash)."""
     try:
         import ctypes
         lib.pnr_source_hash.restype = ctypes.c_char_p
         h = lib.pnr_source_hash().decode().split(":", 1)[1]
         with open(os.path.join(ROOT, "profiles", "r02_traffic.json")) as f:
             table = json.load(f)
-        ent = table.get(h, {})
-        return ent.get(str(n)), (ent.get("capture") if str(n) in ent else None), h
+        ent = table.get(h, {}).get(str(n))
+        if ent is None:
+            return None, None, None, h
+        return ent["bytes_per_launch"], ent["steps_per_launch"], ent["capture"], h
     except Exception:  # noqa: BLE001
-        return None, None, None
+        return None, None, None, None
 
 
 def time_fragments(torch, env, actions, obs_ring, reward, flags, steps, warmup, flush, fragment=FRAGMENT):
@@ -584,7 +587,7 @@ def ours_arm(args):
     peak, peak_src = measured_hbm_peak()
     avg_ms = kernel_ms / args.steps                      # this rank's kernel, per launch
     achieved = BYTES_PER_ENV_STEP * n / (avg_ms / 1e3) / 1e9
-    traffic, traffic_src, src_hash = ncu_traffic(env._lib, n)
+    traffic, traffic_steps, traffic_src, src_hash = ncu_traffic(env._lib, n)
     frag_ms = sorted(ms / t for ms, t in per_frag)
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -631,7 +634,12 @@ def ours_arm(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_capture": traffic_src, "source_hash": src_hash,
                      "kernel": "pnr_step_kernel<F32,TERMINAL>",
-                     "bytes_per_env_step": BYTES_PER_ENV_STEP, "units_per_launch": n, "peak_source": peak_src},
+                     # one launch = one rollout fragment: `achieved` = algorithmic bytes of a launch / its duration, which is
+                     # bytes_per_env_step * envs / ms_per_step; `traffic` is ncu's DRAM bytes of one such launch
+                     "bytes_per_env_step": BYTES_PER_ENV_STEP, "units_per_launch": n * min(FRAGMENT, args.steps),
+                     "steps_per_launch": min(FRAGMENT, args.steps), "traffic_steps_per_launch": traffic_steps,
+                     "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * min(FRAGMENT, args.steps),
+                     "peak_source": peak_src},
     }
     env.close()
     del obs_ring, actions
@@ -712,11 +720,12 @@ def ours_arm(args):
             del a, o, r, f
         line["sweep"] = sweep
         big = sweep[-1]
-        tr, tr_src, _ = ncu_traffic(env._lib, big["envs"])
+        tr, tr_steps, tr_src, _ = ncu_traffic(env._lib, big["envs"])
         line["roofline_large_batch"] = {
             "bound": "hbm", "achieved": big["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": big["frac"],
-            "traffic": tr, "traffic_capture": tr_src, "kernel": "pnr_step_kernel<F32,TERMINAL>",
-            "bytes_per_env_step": BYTES_PER_ENV_STEP, "units_per_launch": big["envs"], "peak_source": peak_src}
+            "traffic": tr, "traffic_capture": tr_src, "traffic_steps_per_launch": tr_steps,
+            "kernel": "pnr_step_kernel<F32,TERMINAL>", "bytes_per_env_step": BYTES_PER_ENV_STEP,
+            "units_per_launch": big["envs"] * 2, "steps_per_launch": 2, "peak_source": peak_src}
         ms_big = timed_extra(dyn_env(1048576), 6, steps=min(args.steps, 64))
         line["dynamic_mode_large_batch"] = dyn_record(1048576, ms_big, "pnr_step_dynamic_kernel<TERMINAL,false,PIONEER_ISO>")
 

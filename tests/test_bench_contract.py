@@ -49,7 +49,7 @@ def test_gpu_arm_line():
     assert d["scaling"] == "weak" and d["dtype"] == "f32" and d["data"] == "synthetic" and "workload" in d["config"]
     r = d["roofline"]
     assert r["bound"] == "hbm" and r["unit"] == "GB/s" and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
-    assert r["bytes_per_env_step"] == 761 and r["units_per_launch"] == 4096
+    assert r["bytes_per_env_step"] == 761 and r["units_per_launch"] == 4096 * 8 and r["steps_per_launch"] == 8
     e = d["e2e"]
     assert e["h2d_bytes_per_step"] == 4096 * 24 and e["d2h_bytes_per_step"] == 4096 * (404 + 4 + 1) and e["value"] > 0
     assert e["sync_full_rows"]["d2h_bytes_per_step"] == 4096 * (548 + 4 + 1) and e["sync_full_rows"]["value"] > 0
