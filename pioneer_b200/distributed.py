@@ -107,9 +107,11 @@ class IterationSync:
         pnr_stats_merge_device                                                  -> merged   [len]          (one kernel)
         [+ pnr_filter_sync_device(merged[8:])]
 
-    With ``cuda_graph=True`` the whole sequence (NCCL included) is captured once and replayed: one graph launch per
-    iteration instead of five host calls.  ``__call__`` returns the merged float64[8] statistics tensor (device, not
-    synchronised; valid until the next call)."""
+    With ``cuda_graph=True`` the whole sequence is captured once and replayed: one graph launch per iteration instead of
+    five host calls.  With more than one rank that capture would include the NCCL all-gather; it is only attempted when
+    ``PNR_GRAPH_COLLECTIVE=1`` (a capture that goes wrong inside a collective can stall every rank), otherwise multi-rank
+    synchronisations run eagerly on the static buffers.  ``__call__`` returns the merged float64[8] statistics tensor
+    (device, not synchronised; valid until the next call)."""
 
     def __init__(self, env, obs_filter=None, group: Optional[dist.ProcessGroup] = None, clear: bool = True,
                  cuda_graph: bool = False):
@@ -125,7 +127,8 @@ class IterationSync:
         self.gathered = torch.zeros((self.world, self.len), dtype=torch.float64, device=dev)
         self.merged = torch.zeros(self.len, dtype=torch.float64, device=dev)
         self._graph = None
-        if cuda_graph:
+        import os
+        if cuda_graph and (self.world == 1 or os.environ.get("PNR_GRAPH_COLLECTIVE") == "1"):
             with torch.cuda.device(dev):
                 # the communicator must exist before the capture; warm it with the (still empty) static buffers -- NOT with
                 # _run(), which clears the statistics window and merges the filter delta

@@ -17,6 +17,20 @@ def run(n, steps, **kw):
     act = (torch.rand((n, 6), device="cuda") - 0.5) * 40
     for _ in range(steps):
         obs, rew, flg = env.step_tensor(act)
+    # a rollout fragment in one launch (pnr_step_many), rows padded to a multiple of 4; RLlib's reset_at for finished rows
+    T, n_pad = 5, (n + 3) // 4 * 4
+    acts = (torch.rand((T, n, 6), device="cuda") - 0.5) * 40
+    obs_t = torch.zeros((T, n_pad, 137), device="cuda")[:, :n]
+    rew_t = torch.zeros((T, n), device="cuda")
+    flg_t = torch.zeros((T, n), dtype=torch.uint8, device="cuda")
+    env.step_many(acts, obs_t, rew_t, flg_t)
+    if env.batch_config.obs_mode == "terminal":
+        env.observe_done(flg_t[-1], obs_t[-1], torch.zeros((n_pad, 137), device="cuda")[:n])
+    if env.batch_config.random_box:
+        env.set_boxes(env.boxes())
+    host = torch.empty((n, 6), dtype=torch.float32).pin_memory()
+    env.step_host_begin(host, compact=True); env.step_host_begin(host, compact=False)
+    env.step_host_end(); env.step_host_end()
     env.observe(indices=[0, n - 1])
     env.reset(indices=[n // 2])
     flt = MeanStdObsFilter(env)
@@ -34,5 +48,8 @@ if __name__ == "__main__":
         total += run(n, 7)
         total += run(n, 7, obs_mode="autoreset", arith="legacy64")
     total += run(777, 4, mode="dynamic", kp=100.0, kd=10.0, torque_scale=100.0, gravity=9.81)
-    total += run(777, 4, obstacles=demo_obstacles(), contact_penalty=0.5)
+    total += run(777, 4, obstacles=demo_obstacles(), contact_penalty=0.5, random_box=True)
+    total += run(130, 2, mode="dynamic", obs_mode="autoreset", obstacles=demo_obstacles(), contact_penalty=0.5, random_box=True,
+                 kp=100.0, kd=10.0, torque_scale=100.0, gravity=9.81)
+    total += run(97, 2, mode="dynamic", stepping="bullet", motor_max_force=5e3, gravity=9.81)
     print("sanitize smoke ok, episodes", total)
