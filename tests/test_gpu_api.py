@@ -219,10 +219,9 @@ def test_seed_reaches_steps_already_captured_in_a_graph():
 @pytest.mark.parametrize("mode,n", [("kinematic", 5000), ("kinematic", 37), ("kinematic", 4097), ("kinematic", 70001),
                                     ("kinematic", 300000), ("dynamic", 70001), ("dynamic", 2048), ("dynamic", 131072)])
 def test_step_many_equals_stepping(mode, n):
-    """pnr_step_many gives bit for bit what T separate pnr_step calls give, call after call.  Kinematic mode: the fragment is
-    ONE launch, every CTA runs the T steps on its own tiles (incl. ragged last tiles, several tiles per CTA, auto-resets
-    between the steps).  Dynamic mode: T launches with programmatic dependent launch, chained tile by tile through per-tile
-    sequence words when the batch spans several waves."""
+    """pnr_step_many gives bit for bit what T separate pnr_step calls give, call after call.  The fragment is ONE launch:
+    every CTA (kinematic mode; a CTA barrier between the steps) or warp (dynamic mode; env state in registers) runs the T
+    steps on its own tiles -- incl. ragged last tiles, several tiles per CTA / warp, auto-resets between the steps."""
     from pioneer_b200 import BatchConfig, BatchedPioneerEnv, SimulationConfig
     kw = dict(seed=4, simulation_config=SimulationConfig(gravity=9.81 if mode == "dynamic" else 0.0),
               batch_config=BatchConfig(mode=mode, kp=2000.0, kd=500.0, torque_scale=1e5, max_episode_steps=5))
