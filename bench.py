@@ -523,21 +523,37 @@ def ours_arm(args):
     total_envs = n * world
     value = total_envs * args.steps / (kernel_ms_max / 1e3)
     clocks = sampler.finish() if sampler else None
-    # the path's one collective: episode statistics, once per iteration.  Snapshot kernel + ONE all-gather + one merge kernel
-    # with static buffers, replayed from a CUDA graph (distributed.IterationSync); timed after warm-up, median of 20
+    # the path's one exchange: episode statistics, once per iteration (distributed.IterationSync).  Within a node it is ONE
+    # kernel per rank over NVLink peer memory (pnr_iteration_sync: snapshot + stores into every rank's window + flags + merge),
+    # replayed from a CUDA graph; the NCCL form (snapshot kernel + all_gather_into_tensor + merge kernel, eager) is timed
+    # beside it.  Median of 20 back-to-back exchanges after warm-up, max over ranks.
     from pioneer_b200.distributed import IterationSync
     stats = reduce_episode_stats(env.episode_stats_tensor()).clone()       # the window of the timed region, for the line
+
+    def time_sync(sync):
+        for _ in range(3):
+            sync()
+        barrier()
+        evs = []
+        for _ in range(20):
+            a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a_.record()
+            sync()
+            b_.record()
+            evs.append((a_, b_))
+        torch.cuda.synchronize()
+        return max_over_ranks(sorted(a_.elapsed_time(b_) for a_, b_ in evs)[10])
+
     it_sync = IterationSync(env, None, None, clear=False, cuda_graph=True)
-    evs = []
-    for _ in range(20):
-        a_, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a_.record()
-        it_sync()
-        b_.record()
-        evs.append((a_, b_))
-    torch.cuda.synchronize()
-    stats_ms = sorted(a_.elapsed_time(b_) for a_, b_ in evs)[10]
-    assert torch.equal(it_sync.merged[:8], stats), "graph-replayed collective disagrees with the eager one"
+    stats_ms = time_sync(it_sync)
+    exchange = {"transport": it_sync.transport, "cuda_graph": it_sync._graph is not None, "ms": stats_ms,
+                "timed_out": it_sync.timed_out()}
+    nccl_sync = IterationSync(env, None, None, clear=False, cuda_graph=False, transport="nccl")
+    exchange["nccl_eager_ms"] = time_sync(nccl_sync)
+    # both merge in rank order: bit-identical; NCCL's all-reduce may associate the float64 sums differently
+    assert torch.equal(it_sync.merged[:8], nccl_sync.merged[:8]), "the peer-memory exchange disagrees with all-gather + merge"
+    assert torch.allclose(it_sync.merged[:8], stats, rtol=1e-12, atol=0.0), "the exchange disagrees with the all-reduce"
+    del nccl_sync
 
     # ---- the round-1 method on the same env: one event pair and one flush per STEP ----------------------
     k1 = min(args.steps, 1000)
@@ -618,6 +634,7 @@ def ours_arm(args):
         "value_l2_warm_cuda_graph": total_envs * graph_steps / (graph_ms / 1e3),
         "ms_per_step_l2_warm_cuda_graph": graph_ms / graph_steps,
         "stats_allreduce_ms": stats_ms,
+        "stats_exchange": exchange,
         "episode_stats": summarize(stats),
         "wall_s_timed_region_incl_flush": wall_s,
         "gpu_launches": launches,
@@ -641,6 +658,7 @@ def ours_arm(args):
                      "algorithmic_bytes_per_launch": BYTES_PER_ENV_STEP * n * min(FRAGMENT, args.steps),
                      "peak_source": peak_src},
     }
+    del it_sync                                              # its graph points into the handle
     env.close()
     del obs_ring, actions
 
@@ -772,8 +790,18 @@ def ours_arm(args):
     if rank == 0:
         os.write(json_fd, (json.dumps(_finite(line)) + "\n").encode())
     if world > 1:
+        # teardown must never outlive the measurement: graphs and envs go first, and a communicator that does not shut down
+        # within 30 s (seen once with NCCL kernels still referenced by live CUDA graphs) is abandoned, not waited for
+        import gc
+        import threading
+        gc.collect()
+        torch.cuda.synchronize()
         dist.barrier()
+        guard = threading.Timer(30.0, lambda: os._exit(0))
+        guard.daemon = True
+        guard.start()
         dist.destroy_process_group()
+        guard.cancel()
 
 
 def rollout_loop(torch, dist, device, rank, world, max_over_ranks, barrier, n=131072, fragment=8, iters=12):

@@ -255,6 +255,32 @@ int pnr_stats_device(pnr_handle* h, double* out_device, int clear, void* stream)
  * delta); out DEVICE double[len] = SUM over slots {0,1,2,3,6,7} and every extra, MAX over slot 4, MIN over slot 5.
  * One kernel on `stream` of the current device; no handle needed. */
 int pnr_stats_merge_device(const double* gathered, int world, int len, double* out, void* stream);
+/* The whole once-per-iteration exchange as ONE kernel over NVLink peer memory: snapshot of this rank's statistics window
+ * (cleared if `clear`) [+ with_filter: this rank's filter delta], stores into every rank's window, a flag per peer, the
+ * merge in rank order (every rank ends with bit-identical results) [+ the Chan merge of the summed delta into the running
+ * filter statistics].  out_device DEVICE double[8 (+ PNR_FILTER_DELTA_LEN)] = what pnr_stats_merge_device would have
+ * produced from an all-gather.  No NCCL call, so the launch can sit in a CUDA graph at any world size.
+ *   pnr_sync_window_create   allocates this handle's window (PNR_SYNC_WINDOW_BYTES, zeroed) and returns its CUDA IPC handle
+ *                            (PNR_SYNC_IPC_BYTES bytes) for the host to exchange over whatever transport it has
+ *                            (torch.distributed, MPI, a socket); pnr_sync_window_ptr returns the raw device pointer for
+ *                            ranks that share a process or map the memory themselves.
+ *   pnr_sync_window_connect  opens the peers' windows: ipc_handles HOST bytes [world][PNR_SYNC_IPC_BYTES] in rank order
+ *                            (entry `rank` is ignored).  pnr_sync_window_connect_ptrs takes mapped device pointers instead.
+ *                            All ranks must have connected (a host barrier) before the first pnr_iteration_sync.
+ *   pnr_iteration_sync       world = 1 (never connected): the same kernel without the exchange.  timeout_ms > 0 bounds
+ *                            the wait for a peer: on expiry the output is NaN and pnr_sync_status reports 1 (0 = wait
+ *                            for ever).  Every rank must make the same sequence of calls with the same with_filter.
+ * The reference moves these numbers from its Ray rollout workers to the trainer process
+ * (pioneer/launch/pioneer_knm_train.py:49, :66). */
+#define PNR_SYNC_MAX_PEERS 16
+#define PNR_SYNC_WINDOW_BYTES 73984
+#define PNR_SYNC_IPC_BYTES 64
+int pnr_sync_window_create(pnr_handle* h, unsigned char* ipc_handle_out);
+int pnr_sync_window_ptr(pnr_handle* h, void** window_out);
+int pnr_sync_window_connect(pnr_handle* h, const unsigned char* ipc_handles, int world, int rank);
+int pnr_sync_window_connect_ptrs(pnr_handle* h, void* const* windows, int world, int rank);
+int pnr_iteration_sync(pnr_handle* h, int with_filter, int clear, double* out_device, int timeout_ms, void* stream);
+int pnr_sync_status(pnr_handle* h, int* timed_out);
 /* Restore the statistics window from HOST double[8] (what pnr_stats returned): checkpoint / resume.  Synchronises. */
 int pnr_set_stats(pnr_handle* h, const double* in8);
 

@@ -28,6 +28,7 @@ PNR_OBSTACLE_NONE, PNR_OBSTACLE_PLANE, PNR_OBSTACLE_BOX, PNR_OBSTACLE_SPHERE = 0
 PNR_STEPPING_EXPLICIT, PNR_STEPPING_BULLET = 0, 1
 PNR_HOST_FULL, PNR_HOST_COMPACT = 0, 1
 PNR_OBS_COMPACT_DIM, PNR_OBS_CONST_BEGIN, PNR_OBS_CONST_END = 101, 18, 54
+PNR_SYNC_MAX_PEERS, PNR_SYNC_WINDOW_BYTES, PNR_SYNC_IPC_BYTES = 16, 73984, 64
 
 _d3 = C.c_double * 3
 _d9 = C.c_double * 9
@@ -106,6 +107,12 @@ SIGNATURES = {
     "pnr_set_stats": (C.c_int, [_H, C.POINTER(C.c_double)]),
     "pnr_stats_merge_device": (C.c_int, [_P, C.c_int, C.c_int, _P, _S]),
     "pnr_stats_device": (C.c_int, [_H, _P, C.c_int, _S]),
+    "pnr_sync_window_create": (C.c_int, [_H, C.POINTER(C.c_ubyte)]),
+    "pnr_sync_window_ptr": (C.c_int, [_H, C.POINTER(C.c_void_p)]),
+    "pnr_sync_window_connect": (C.c_int, [_H, C.POINTER(C.c_ubyte), C.c_int, C.c_int]),
+    "pnr_sync_window_connect_ptrs": (C.c_int, [_H, C.POINTER(C.c_void_p), C.c_int, C.c_int]),
+    "pnr_iteration_sync": (C.c_int, [_H, C.c_int, C.c_int, _P, C.c_int, _S]),
+    "pnr_sync_status": (C.c_int, [_H, C.POINTER(C.c_int)]),
     "pnr_filter_configure": (C.c_int, [_H, C.c_double, C.c_int, C.c_int]),
     "pnr_filter_apply": (C.c_int, [_H, _P, _P, C.c_int64, C.c_int, C.c_int, _S]),
     "pnr_filter_fuse": (C.c_int, [_H, C.c_int, C.c_int]),

@@ -62,6 +62,10 @@ struct pnr_handle {
     int host_next = 0, host_inflight = 0;
     cudaStream_t host_stream = nullptr, copy_stream1 = nullptr, copy_stream2 = nullptr;
     cudaEvent_t host_order_event = nullptr;
+    // pnr_iteration_sync: this rank's window and the peers' windows as mapped into this process
+    unsigned char* sync_window = nullptr;
+    PnrSyncPeers sync_peers = {};
+    bool sync_ipc_opened[PNR_SYNC_MAX_PEERS] = {};
 };
 
 struct PnrDeviceGuard {
@@ -403,6 +407,9 @@ extern "C" void pnr_destroy(pnr_handle* h) {
         for (cudaEvent_t ev : {sl.kernel_done, sl.copy1_done, sl.copy2_done}) if (ev) cudaEventDestroy(ev);
         cudaFree(sl.actions); cudaFree(sl.obs); cudaFree(sl.reward); cudaFree(sl.compact); cudaFree(sl.done);
     }
+    for (int r = 0; r < PNR_SYNC_MAX_PEERS; ++r)
+        if (h->sync_ipc_opened[r]) cudaIpcCloseMemHandle(h->sync_peers.window[r]);
+    cudaFree(h->sync_window);
     cudaFree(h->state); cudaFree(h->stats); cudaFree(h->stats_out); cudaFree(h->box_a); cudaFree(h->box_z);
     cudaFree(h->filt_delta); cudaFree(h->filt_applied); cudaFree(h->filt_state); cudaFree(h->filt_merged);
     if (h->stats_host) cudaFreeHost(h->stats_host);
@@ -761,6 +768,131 @@ extern "C" int pnr_stats_device(pnr_handle* h, double* out_device, int clear, vo
 extern "C" int pnr_stats_merge_device(const double* gathered, int world, int len, double* out, void* stream) {
     if (!gathered || !out || world < 1 || len < PNR_STATS_LEN) return pnr_fail(PNR_ERR_INVALID, "pnr_stats_merge_device: bad argument");
     PNR_CUDA(pnr_launch_stats_merge(gathered, world, len, out, (cudaStream_t)stream));
+    return PNR_OK;
+}
+
+static int pnr_filter_ensure(pnr_handle* h, cudaStream_t stream);
+
+static int pnr_sync_window_ensure(pnr_handle* h) {
+    if (h->sync_window) return PNR_OK;
+    PNR_CUDA(cudaMalloc(&h->sync_window, PNR_SYNC_WINDOW_BYTES));
+    PNR_CUDA(cudaMemset(h->sync_window, 0, PNR_SYNC_WINDOW_BYTES));
+    PNR_CUDA(cudaDeviceSynchronize());
+    return PNR_OK;
+}
+
+extern "C" int pnr_sync_window_create(pnr_handle* h, unsigned char* ipc_handle_out) {
+    if (!h || !ipc_handle_out) return pnr_fail(PNR_ERR_INVALID, "pnr_sync_window_create: null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == PNR_SYNC_IPC_BYTES, "PNR_SYNC_IPC_BYTES is the size of a CUDA IPC handle");
+    PnrDeviceGuard guard(h->device);
+    int rc = pnr_sync_window_ensure(h);
+    if (rc != PNR_OK) return rc;
+    cudaIpcMemHandle_t ipc;
+    PNR_CUDA(cudaIpcGetMemHandle(&ipc, h->sync_window));
+    std::memcpy(ipc_handle_out, &ipc, sizeof(ipc));
+    return PNR_OK;
+}
+
+extern "C" int pnr_sync_window_ptr(pnr_handle* h, void** window_out) {
+    if (!h || !window_out) return pnr_fail(PNR_ERR_INVALID, "pnr_sync_window_ptr: null argument");
+    PnrDeviceGuard guard(h->device);
+    int rc = pnr_sync_window_ensure(h);
+    if (rc != PNR_OK) return rc;
+    *window_out = h->sync_window;
+    return PNR_OK;
+}
+
+static int pnr_sync_disconnect(pnr_handle* h) {
+    for (int r = 0; r < PNR_SYNC_MAX_PEERS; ++r) {
+        if (h->sync_ipc_opened[r]) cudaIpcCloseMemHandle(h->sync_peers.window[r]);
+        h->sync_ipc_opened[r] = false;
+        h->sync_peers.window[r] = nullptr;
+    }
+    h->sync_peers.world = 0;
+    return PNR_OK;
+}
+
+extern "C" int pnr_sync_window_connect_ptrs(pnr_handle* h, void* const* windows, int world, int rank) {
+    if (!h || !windows) return pnr_fail(PNR_ERR_INVALID, "pnr_sync_window_connect_ptrs: null argument");
+    if (world < 1 || world > PNR_SYNC_MAX_PEERS || rank < 0 || rank >= world)
+        return pnr_fail(PNR_ERR_INVALID, "pnr_sync_window_connect_ptrs: need 1 <= world <= PNR_SYNC_MAX_PEERS and 0 <= rank < world");
+    PnrDeviceGuard guard(h->device);
+    int rc = pnr_sync_window_ensure(h);
+    if (rc != PNR_OK) return rc;
+    PNR_CUDA(cudaDeviceSynchronize());                         // no exchange of the old connection is still running
+    pnr_sync_disconnect(h);
+    PNR_CUDA(cudaMemset(h->sync_window, 0, PNR_SYNC_WINDOW_BYTES));   // sequence numbers and flags restart with the connection
+    PNR_CUDA(cudaDeviceSynchronize());
+    for (int r = 0; r < world; ++r) {
+        if (r != rank && !windows[r]) return pnr_fail(PNR_ERR_INVALID, "pnr_sync_window_connect_ptrs: null window");
+        h->sync_peers.window[r] = r == rank ? h->sync_window : static_cast<unsigned char*>(windows[r]);
+    }
+    h->sync_peers.world = world;
+    h->sync_peers.rank = rank;
+    return PNR_OK;
+}
+
+extern "C" int pnr_sync_window_connect(pnr_handle* h, const unsigned char* ipc_handles, int world, int rank) {
+    if (!h || !ipc_handles) return pnr_fail(PNR_ERR_INVALID, "pnr_sync_window_connect: null argument");
+    if (world < 1 || world > PNR_SYNC_MAX_PEERS || rank < 0 || rank >= world)
+        return pnr_fail(PNR_ERR_INVALID, "pnr_sync_window_connect: need 1 <= world <= PNR_SYNC_MAX_PEERS and 0 <= rank < world");
+    PnrDeviceGuard guard(h->device);
+    int rc = pnr_sync_window_ensure(h);
+    if (rc != PNR_OK) return rc;
+    PNR_CUDA(cudaDeviceSynchronize());
+    pnr_sync_disconnect(h);
+    void* mapped[PNR_SYNC_MAX_PEERS] = {};
+    bool opened[PNR_SYNC_MAX_PEERS] = {};
+    for (int r = 0; r < world; ++r) {
+        if (r == rank) continue;
+        cudaIpcMemHandle_t ipc;
+        std::memcpy(&ipc, ipc_handles + (size_t)r * PNR_SYNC_IPC_BYTES, sizeof(ipc));
+        cudaError_t e = cudaIpcOpenMemHandle(&mapped[r], ipc, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) {
+            for (int q = 0; q < r; ++q) if (opened[q]) cudaIpcCloseMemHandle(mapped[q]);
+            cudaGetLastError();
+            return pnr_fail(PNR_ERR_CUDA, std::string("pnr_sync_window_connect: cudaIpcOpenMemHandle(rank ") + std::to_string(r) +
+                                              "): " + cudaGetErrorString(e));
+        }
+        opened[r] = true;
+    }
+    rc = pnr_sync_window_connect_ptrs(h, mapped, world, rank);
+    if (rc != PNR_OK) {
+        for (int r = 0; r < world; ++r) if (opened[r]) cudaIpcCloseMemHandle(mapped[r]);
+        return rc;
+    }
+    for (int r = 0; r < world; ++r) h->sync_ipc_opened[r] = opened[r];
+    return PNR_OK;
+}
+
+extern "C" int pnr_iteration_sync(pnr_handle* h, int with_filter, int clear, double* out_device, int timeout_ms, void* stream) {
+    if (!h || !out_device) return pnr_fail(PNR_ERR_INVALID, "pnr_iteration_sync: null argument");
+    if (reinterpret_cast<uintptr_t>(out_device) & 7)
+        return pnr_fail(PNR_ERR_INVALID, "pnr_iteration_sync: out_device must be 8-byte aligned");
+    if (timeout_ms < 0) return pnr_fail(PNR_ERR_INVALID, "pnr_iteration_sync: timeout_ms < 0");
+    PnrDeviceGuard guard(h->device);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (with_filter) {
+        int rc = pnr_filter_ensure(h, s);
+        if (rc != PNR_OK) return rc;
+    }
+    PnrSyncPeers peers = h->sync_peers;
+    if (peers.world < 1) { peers.world = 1; peers.rank = 0; }
+    PNR_CUDA(pnr_launch_iteration_sync(h->stats, clear, with_filter ? h->filt_delta : nullptr, h->filt_state, h->filt_applied,
+                                       h->filt_demean, h->filt_destd, peers, (unsigned long long)timeout_ms * 1000000ull,
+                                       out_device, s));
+    h->launches += 1;
+    return PNR_OK;
+}
+
+extern "C" int pnr_sync_status(pnr_handle* h, int* timed_out) {
+    if (!h || !timed_out) return pnr_fail(PNR_ERR_INVALID, "pnr_sync_status: null argument");
+    *timed_out = 0;
+    if (!h->sync_window) return PNR_OK;
+    PnrDeviceGuard guard(h->device);
+    uint32_t st = 0;
+    PNR_CUDA(cudaMemcpy(&st, h->sync_window + PNR_SYNC_STATUS_OFF, sizeof(st), cudaMemcpyDeviceToHost));   // synchronises
+    *timed_out = st ? 1 : 0;
     return PNR_OK;
 }
 

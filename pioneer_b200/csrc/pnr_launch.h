@@ -49,6 +49,20 @@ cudaError_t pnr_launch_tick_advance(PnrStats* stats, uint32_t n, int absolute, c
 cudaError_t pnr_launch_env_steps_set(PnrStats* stats, double env_steps, cudaStream_t stream);
 cudaError_t pnr_launch_stats_merge(const double* gathered, int world, int len, double* out, cudaStream_t stream);
 cudaError_t pnr_launch_stats_snapshot(PnrStats* stats, double* out, int clear, cudaStream_t stream);
+// pnr_iteration_sync window layout: double slots[2 parities][MAX_PEERS][288] | uint32 flags[2][MAX_PEERS] | uint32 seq | uint32 status
+#define PNR_SYNC_THREADS 288                                    // >= 8 + PNR_FILTER_DELTA_LEN (283), 9 warps
+#define PNR_SYNC_SLOT_STRIDE PNR_SYNC_THREADS
+#define PNR_SYNC_FLAGS_OFF (2 * PNR_SYNC_MAX_PEERS * PNR_SYNC_SLOT_STRIDE * 8)
+#define PNR_SYNC_SEQ_OFF (PNR_SYNC_FLAGS_OFF + 2 * PNR_SYNC_MAX_PEERS * 4)
+#define PNR_SYNC_STATUS_OFF (PNR_SYNC_SEQ_OFF + 4)
+// pnr_iteration_sync: the windows of all ranks as this process sees them (window[rank] is the local one); world == 1 needs none
+struct PnrSyncPeers {
+    unsigned char* window[PNR_SYNC_MAX_PEERS];
+    int world, rank;
+};
+cudaError_t pnr_launch_iteration_sync(PnrStats* stats, int clear, double* filt_slots, double* filt_state, float* applied,
+                                      int demean, int destd, const PnrSyncPeers& peers, unsigned long long timeout_ns,
+                                      double* out, cudaStream_t stream);
 cudaError_t pnr_launch_filter_fold(double* delta_slots, cudaStream_t stream);
 cudaError_t pnr_launch_filter_refresh(const double* state, float* applied, int demean, int destd, cudaStream_t stream);
 cudaError_t pnr_launch_filter_sync(double* slots, const double* merged, double* state, float* applied, int demean, int destd,

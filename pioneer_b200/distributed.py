@@ -99,40 +99,58 @@ def reduce_episode_stats(local: torch.Tensor, group: Optional[dist.ProcessGroup]
 
 
 class IterationSync:
-    """Everything a rollout worker exchanges once per training iteration, as ONE collective with static buffers:
+    """Everything a rollout worker exchanges once per training iteration -- the episode statistics (optionally clearing the
+    window) and, if given, the observation filter's delta -- with static buffers, over one of two transports:
 
-        snapshot of the episode statistics (pnr_stats_device, optionally clearing the window)
-        [+ the observation filter's delta (pnr_filter_delta_device)]           -> packed float64[8 (+ 275)]
-        all_gather_into_tensor(packed)                                          -> gathered [world, len]   (NCCL)
-        pnr_stats_merge_device                                                  -> merged   [len]          (one kernel)
-        [+ pnr_filter_sync_device(merged[8:])]
+    ``p2p``   pnr_iteration_sync: ONE kernel per rank does snapshot + exchange + merge (+ the filter's Chan merge) over
+              NVLink peer memory: every rank stores its packed float64[8 (+ 275)] into every rank's window and releases a
+              flag there, waits for its own flags, and merges in rank order, so all ranks end with bit-identical numbers.
+              The windows are plain cudaMalloc memory opened across processes with CUDA IPC; torch.distributed only carries
+              the 64-byte handles, once, at construction.  No NCCL call in the step, so with ``cuda_graph=True`` the launch
+              is captured and replayed at any world size.
+    ``nccl``  snapshot (pnr_stats_device [+ pnr_filter_delta_device]) -> all_gather_into_tensor -> pnr_stats_merge_device
+              [+ pnr_filter_sync_device]: five host calls.  Graph capture of this sequence would include the collective; it
+              is only attempted at world > 1 when ``PNR_GRAPH_COLLECTIVE=1``.
 
-    With ``cuda_graph=True`` the whole sequence is captured once and replayed: one graph launch per iteration instead of
-    five host calls.  With more than one rank that capture would include the NCCL all-gather; it is only attempted when
-    ``PNR_GRAPH_COLLECTIVE=1`` (a capture that goes wrong inside a collective can stall every rank), otherwise multi-rank
-    synchronisations run eagerly on the static buffers.  ``__call__`` returns the merged float64[8] statistics tensor
-    (device, not synchronised; valid until the next call)."""
+    ``transport="auto"`` (default) uses p2p when every rank could open every other rank's window (same node, peer access)
+    and nccl otherwise; ``PNR_SYNC_TRANSPORT`` overrides.  ``__call__`` returns the merged float64[8] statistics tensor
+    (device, not synchronised; valid until the next call).  A p2p wait that exceeds ``timeout_s`` yields NaN statistics and
+    ``timed_out()`` reports it (a kernel never spins for ever on a dead peer)."""
 
     def __init__(self, env, obs_filter=None, group: Optional[dist.ProcessGroup] = None, clear: bool = True,
-                 cuda_graph: bool = False):
+                 cuda_graph: bool = False, transport: str = "auto", timeout_s: float = 20.0):
+        import os
         from . import _cabi
         self.env, self.filter, self.group, self.clear = env, obs_filter, group, bool(clear)
         self._cabi, self._lib = _cabi, env._lib
         k = len(STATS_FIELDS)
         self.k = k
         self.len = k + (_cabi.PNR_FILTER_DELTA_LEN if obs_filter is not None else 0)
-        self.world = dist.get_world_size(group) if (dist.is_available() and dist.is_initialized()) else 1
+        active = dist.is_available() and dist.is_initialized()
+        self.world = dist.get_world_size(group) if active else 1
+        self.rank = dist.get_rank(group) if active else 0
+        self.timeout_ms = int(timeout_s * 1000)
         dev = env.device
         self.packed = torch.zeros(self.len, dtype=torch.float64, device=dev)
         self.gathered = torch.zeros((self.world, self.len), dtype=torch.float64, device=dev)
         self.merged = torch.zeros(self.len, dtype=torch.float64, device=dev)
         self._graph = None
-        import os
-        if cuda_graph and (self.world == 1 or os.environ.get("PNR_GRAPH_COLLECTIVE") == "1"):
+        transport = os.environ.get("PNR_SYNC_TRANSPORT", transport)
+        if transport not in ("auto", "p2p", "nccl"):
+            raise ValueError(f"unknown transport {transport!r}")
+        self.transport = "p2p" if self.world == 1 and transport != "nccl" else transport
+        if self.world > 1 and transport != "nccl":
+            self.transport = "p2p" if self._connect_windows() else "nccl"
+            if transport == "p2p" and self.transport != "p2p":
+                raise RuntimeError("IterationSync(transport='p2p'): the ranks could not open each other's windows: "
+                                   + self._connect_error)
+        capture = cuda_graph and (self.transport == "p2p" or self.world == 1
+                                  or os.environ.get("PNR_GRAPH_COLLECTIVE") == "1")
+        if capture:
             with torch.cuda.device(dev):
                 # the communicator must exist before the capture; warm it with the (still empty) static buffers -- NOT with
                 # _run(), which clears the statistics window and merges the filter delta
-                if self.world > 1:
+                if self.world > 1 and self.transport == "nccl":
                     for _ in range(2):
                         dist.all_gather_into_tensor(self.gathered, self.packed, group=self.group)
                 torch.cuda.synchronize(dev)
@@ -142,12 +160,42 @@ class IterationSync:
                         self._run()
                     self._graph = g
                 except Exception:  # noqa: BLE001 - capture of the collective is not available: stay eager
+                    if self.transport == "p2p":
+                        raise
                     self._graph = None
                     torch.cuda.synchronize(dev)
+
+    def _connect_windows(self) -> bool:
+        """Exchange the CUDA IPC handles of the windows (one all-gather of 64 bytes per rank) and open the peers' windows;
+        True when EVERY rank succeeded (otherwise all of them fall back to the NCCL transport together)."""
+        import ctypes as C
+        c, lib, env = self._cabi, self._lib, self.env
+        self._connect_error = ""
+        ipc = (C.c_ubyte * c.PNR_SYNC_IPC_BYTES)()
+        ok = 1
+        if self.world > c.PNR_SYNC_MAX_PEERS or lib.pnr_sync_window_create(env._h, ipc) != 0:
+            ok, self._connect_error = 0, (lib.pnr_last_error() or b"").decode() or "world > PNR_SYNC_MAX_PEERS"
+        mine = torch.tensor(list(ipc), dtype=torch.uint8, device=env.device)
+        everyone = torch.zeros(self.world * c.PNR_SYNC_IPC_BYTES, dtype=torch.uint8, device=env.device)
+        dist.all_gather_into_tensor(everyone, mine, group=self.group)
+        if ok:
+            handles = (C.c_ubyte * (self.world * c.PNR_SYNC_IPC_BYTES))(*everyone.cpu().tolist())
+            if lib.pnr_sync_window_connect(env._h, handles, self.world, self.rank) != 0:
+                ok, self._connect_error = 0, (lib.pnr_last_error() or b"").decode()
+        agreed = torch.tensor([ok], dtype=torch.int32, device=env.device)
+        dist.all_reduce(agreed, op=dist.ReduceOp.MIN, group=self.group)      # doubles as the barrier: every window is open
+        torch.cuda.synchronize(env.device)
+        if int(agreed.item()) != 1 and not self._connect_error:
+            self._connect_error = "another rank failed"
+        return int(agreed.item()) == 1
 
     def _run(self) -> None:
         env, c, lib = self.env, self._cabi, self._lib
         s = env._stream()
+        if self.transport == "p2p":
+            c.check(lib.pnr_iteration_sync(env._h, 1 if self.filter is not None else 0, 1 if self.clear else 0,
+                                           self.merged.data_ptr(), self.timeout_ms, s), "pnr_iteration_sync")
+            return
         c.check(lib.pnr_stats_device(env._h, self.packed.data_ptr(), 1 if self.clear else 0, s), "pnr_stats_device")
         if self.filter is not None:
             c.check(lib.pnr_filter_delta_device(env._h, self.packed.data_ptr() + 8 * self.k, s), "pnr_filter_delta_device")
@@ -168,6 +216,13 @@ class IterationSync:
             else:
                 self._run()
         return self.merged[:self.k]
+
+    def timed_out(self) -> bool:
+        """True if a p2p exchange gave up waiting for a peer (synchronises the device)."""
+        import ctypes as C
+        flag = C.c_int(0)
+        self._cabi.check(self._lib.pnr_sync_status(self.env._h, C.byref(flag)), "pnr_sync_status")
+        return bool(flag.value)
 
 
 def summarize(stats: torch.Tensor) -> Dict[str, float]:

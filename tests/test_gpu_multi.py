@@ -20,7 +20,7 @@ def _actions(n_total):
     return (torch.rand((STEPS, n_total, 6), generator=g) * 2 - 1) * 50.0
 
 
-def _run(env, flt, acts):
+def _run(env, flt, acts, fused_sync=False):
     from pioneer_b200.distributed import reduce_episode_stats
     outs = []
     for t in range(STEPS):
@@ -29,15 +29,27 @@ def _run(env, flt, acts):
         outs.append((obs.clone(), rew.clone(), flg.clone()))
     stats = reduce_episode_stats(env.episode_stats_tensor())
     # the same reduction as ONE graph-replayed collective with static buffers (what the rollout loop and bench.py use)
+    # the same reduction with static buffers (what the rollout loop and bench.py use): over NCCL, and as ONE kernel per rank
+    # over peer memory (eager and replayed from a CUDA graph) -- across real GPUs and processes here
     from pioneer_b200.distributed import IterationSync
-    for graph in (False, True):
-        again = IterationSync(env, None, None, clear=False, cuda_graph=graph)()
-        assert torch.equal(again, stats), graph
-    flt.sync()
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    for transport, graph in (("nccl", False), ("p2p", False), ("p2p", True), ("auto", True)):
+        sync = IterationSync(env, None, None, clear=False, cuda_graph=graph, transport=transport)
+        if world > 1 and transport != "nccl":
+            assert sync.transport == "p2p", "the ranks of one node must be able to open each other's windows"
+        for _ in range(3):
+            again = sync()
+            assert torch.equal(again, stats), (transport, graph)
+        assert not sync.timed_out()
+    if fused_sync:      # statistics + filter delta in the one-kernel exchange (what RolloutWorker.sync does)
+        both = IterationSync(env, flt, None, clear=False, cuda_graph=True)
+        assert torch.equal(both(), stats) and not both.timed_out()
+    else:
+        flt.sync()
     return outs, stats.cpu().numpy(), flt.n, flt.mean, flt.var
 
 
-def _worker(rank, world, port, q):
+def _worker(rank, world, port, q, fused_sync):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))      # NCCL_DEBUG is left as the caller set it
     torch.cuda.set_device(rank)
     dist.init_process_group("nccl", rank=rank, world_size=world, device_id=torch.device("cuda", rank))
@@ -48,14 +60,15 @@ def _worker(rank, world, port, q):
                                 batch_config=BatchConfig(max_episode_steps=LIMIT))
         flt = MeanStdObsFilter(env)
         acts = _actions(world * N_PER)[:, rank * N_PER:(rank + 1) * N_PER]
-        outs, stats, n, mean, var = _run(env, flt, acts)
+        outs, stats, n, mean, var = _run(env, flt, acts, fused_sync)
         q.put((rank, [o[0].cpu().numpy() for o in outs], stats, n, mean, var))
         env.close()
     finally:
         dist.destroy_process_group()
 
 
-def test_two_ranks_equal_one_gpu():
+@pytest.mark.parametrize("fused_sync", [False, True])
+def test_two_ranks_equal_one_gpu(fused_sync):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     with socket.socket() as s:
@@ -63,7 +76,7 @@ def test_two_ranks_equal_one_gpu():
         port = s.getsockname()[1]
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q, fused_sync)) for r in range(2)]
     for p in procs:
         p.start()
     got = {}
@@ -78,7 +91,7 @@ def test_two_ranks_equal_one_gpu():
     from pioneer_b200.obs_filter import MeanStdObsFilter
     env = BatchedPioneerEnv(2 * N_PER, seed=SEED, batch_config=BatchConfig(max_episode_steps=LIMIT))
     flt = MeanStdObsFilter(env)
-    outs, stats, n, mean, var = _run(env, flt, _actions(2 * N_PER))
+    outs, stats, n, mean, var = _run(env, flt, _actions(2 * N_PER), fused_sync)
     for t in range(STEPS):
         whole = outs[t][0].cpu().numpy()
         assert np.array_equal(whole[:N_PER], got[0][0][t]) and np.array_equal(whole[N_PER:], got[1][0][t]), t
