@@ -42,8 +42,40 @@ def run(n, steps, **kw):
     return st["episodes"]
 
 
+def exchange():
+    """pnr_iteration_sync with two handles on one GPU playing two ranks (peer windows by pointer)."""
+    import ctypes as C
+    from pioneer_b200 import _cabi as c
+    envs = [BatchedPioneerEnv(300, seed=2, env_id_base=300 * r, batch_config=BatchConfig(max_episode_steps=3)) for r in range(2)]
+    flts = [MeanStdObsFilter(e) for e in envs]
+    lib = envs[0]._lib
+    ptrs = (C.c_void_p * 2)()
+    for r, e in enumerate(envs):
+        p = C.c_void_p()
+        c.check(lib.pnr_sync_window_ptr(e._h, C.byref(p)))
+        ptrs[r] = p.value
+    for r, e in enumerate(envs):
+        c.check(lib.pnr_sync_window_connect_ptrs(e._h, ptrs, 2, r))
+    outs = [torch.zeros(8 + c.PNR_FILTER_DELTA_LEN, dtype=torch.float64, device="cuda") for _ in range(2)]
+    streams = [torch.cuda.Stream() for _ in range(2)]
+    for it in range(3):
+        for e, f in zip(envs, flts):
+            for _ in range(4):
+                obs, _, _ = e.step_tensor(torch.zeros((300, 6), device="cuda"))
+                f.push(obs)
+        torch.cuda.synchronize()
+        for r in range(2):
+            with torch.cuda.stream(streams[r]):
+                c.check(lib.pnr_iteration_sync(envs[r]._h, it % 2, 1, outs[r].data_ptr(), 20000, streams[r].cuda_stream))
+        torch.cuda.synchronize()
+        assert torch.equal(outs[0], outs[1])
+    for e in envs:
+        e.close()
+    return int(outs[0][0].item())
+
+
 if __name__ == "__main__":
-    total = 0
+    total = exchange()
     for n in (1, 33, 1000, 5000):
         total += run(n, 7)
         total += run(n, 7, obs_mode="autoreset", arith="legacy64")
