@@ -646,6 +646,8 @@ def ours_arm(args):
                        "kernel of step k + 1), 101-column rows (the 36 constant columns are delivered once)",
                 "sync_full_rows": {"value": total_envs * e2e_steps / e2e_sync_s, "d2h_bytes_per_step": n * (OBS_DIM * 4 + 4 + 1),
                                    "api": "BatchedPioneerEnv.step_host -> pnr_step_host (synchronous, 137-column rows)"},
+                # what the host links of the whole box carried: if this stops growing with N the box, not the path, is the limit
+                "host_link_gb_per_s_all_ranks": e2e_value * (DOF * 4 + 101 * 4 + 4 + 1) / 1e9,
                 "numa_node_rank0": numa_node,
                 "timer": "host perf_counter around the calls, max over ranks"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
