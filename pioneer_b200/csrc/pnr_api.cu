@@ -4,6 +4,7 @@
 #include <cstddef>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <new>
 #include <string>
@@ -236,12 +237,19 @@ static int pnr_build_params(const pnr_model& m, const pnr_config& c, int64_t n_e
     p.contact_penalty = (float)c.contact_penalty;
     p.n_obstacles = (c.contact_penalty != 0.0) ? c.n_obstacles : 0;
     p.n_capsules = m.n_capsules;
-    for (int i = 0; i < m.n_capsules; ++i) {
+    for (int i = 0; i < m.n_capsules; ++i)
         if (m.capsule_body[i] < 0 || m.capsule_body[i] >= PNR_DOF)
             return pnr_fail(PNR_ERR_INVALID, "pnr_model.capsule_body out of range");
-        p.capsule_body[i] = m.capsule_body[i];
-        p.capsule_radius[i] = (float)m.capsule_radius[i];
-        for (int k = 0; k < 3; ++k) { p.capsule_p0[i][k] = (float)m.capsule_p0[i][k]; p.capsule_p1[i][k] = (float)m.capsule_p1[i][k]; }
+    // the kernels walk the chain base-to-tip ONCE and visit the capsules of a body when its frame is current: the device table
+    // is ordered by body (stable, so capsules of one body keep the caller's order)
+    int order[PNR_MAX_CAPSULES];
+    for (int i = 0; i < m.n_capsules; ++i) order[i] = i;
+    std::stable_sort(order, order + m.n_capsules, [&](int a, int b) { return m.capsule_body[a] < m.capsule_body[b]; });
+    for (int slot = 0; slot < m.n_capsules; ++slot) {
+        const int i = slot, src = order[slot];
+        p.capsule_body[i] = m.capsule_body[src];
+        p.capsule_radius[i] = (float)m.capsule_radius[src];
+        for (int k = 0; k < 3; ++k) { p.capsule_p0[i][k] = (float)m.capsule_p0[src][k]; p.capsule_p1[i][k] = (float)m.capsule_p1[src][k]; }
     }
     for (int i = 0; i < c.n_obstacles; ++i) {
         const int t = c.obstacle_type[i];

@@ -216,7 +216,10 @@ __device__ __forceinline__ void pnr_fk_tip(const PnrParams& p, const float (&sn)
 // over the capsule's axis segment -- exact for every kind: plane (linear: the nearer end point), sphere (closest point of the
 // segment), axis-aligned box (below).  Same definition as oracle/contact.h and oracle/reach_oracle.py::contact_depth, which
 // enumerate the breakpoints of the piecewise function in float64 instead.
-// Rare configuration => not inlined; the sin/cos travel by value so the caller's arrays stay in registers.
+// INLINED into the obstacle instantiations: as a separate function it received the kernel parameters by reference, and every
+// table entry (capsule end points, axis codes, joint origins, obstacle geometry) became a generic LD.E through that pointer
+// instead of a constant-bank operand -- 144 dependent loads on the task warp's critical path; the variant ran 5x slower
+// than the plain kernel (49 us vs 9 us per step at 65,536 envs) for ~4 k instructions of arithmetic.
 // ---------------------------------------------------------------------------------------------
 struct PnrSinCos { float sn[PNR_DOF], cs[PNR_DOF]; };
 struct PnrBox { float px, py, pz, ex, ey, ez; };
@@ -251,22 +254,130 @@ __device__ __forceinline__ float pnr_segment_box(float ax, float ay, float az, f
                  pnr_box_sdf(fmaf(hi, dx, ax), fmaf(hi, dy, ay), fmaf(hi, dz, az), ex, ey, ez));
 }
 
-// `rb`: this env's random box (used for obstacle p.random_box when that is >= 0)
-static __device__ __noinline__ float pnr_contact_depth(const PnrParams& p, PnrSinCos sc, PnrBox rb) {
-    float total = 0.f;
-    for (int c = 0; c < p.n_capsules; ++c) {
-        const int body = p.capsule_body[c];
-        float ax = p.capsule_p0[c][0], ay = p.capsule_p0[c][1], az = p.capsule_p0[c][2];
-        float bx = p.capsule_p1[c][0], by = p.capsule_p1[c][1], bz = p.capsule_p1[c][2];
+// Outside the box the squared distance F(t) = sum_i max(|x_i(t)| - e_i, 0)^2 along the segment is convex and piecewise
+// quadratic with at most six breakpoints (x_i = +-e_i), so g = F'/2 is piecewise LINEAR and non-decreasing: evaluate g at
+// the breakpoints that fall inside the current bracket (no sorting: each one either raises the lower end or lowers the
+// upper end), then solve the remaining linear piece -- the exact minimiser in 8 evaluations of g instead of 24 halvings.
+// F ~ 0 there means the axis grazes or enters the box; only then the signed (negative) distance needs the search above.
+__device__ __forceinline__ float pnr_box_gap_slope(float t, float ax, float ay, float az, float dx, float dy, float dz,
+                                                   float ex, float ey, float ez) {
+    const float x = fmaf(t, dx, ax), y = fmaf(t, dy, ay), z = fmaf(t, dz, az);
+    const float qx = fmaxf(fabsf(x) - ex, 0.f), qy = fmaxf(fabsf(y) - ey, 0.f), qz = fmaxf(fabsf(z) - ez, 0.f);
+    return fmaf(copysignf(qx, x), dx, fmaf(copysignf(qy, y), dy, copysignf(qz, z) * dz));
+}
+__device__ __forceinline__ float pnr_segment_box_exact(float ax, float ay, float az, float dx, float dy, float dz,
+                                                       float ex, float ey, float ez) {
+    float lo = 0.f, hi = 1.f;
+    float glo = pnr_box_gap_slope(0.f, ax, ay, az, dx, dy, dz, ex, ey, ez);
+    float ghi = pnr_box_gap_slope(1.f, ax, ay, az, dx, dy, dz, ex, ey, ez);
+    float t;
+    if (glo >= 0.f) t = 0.f;                                   // F does not decrease from the first end point
+    else if (ghi <= 0.f) t = 1.f;                              // ... or still decreases at the second
+    else {
+        const float a3[3] = {ax, ay, az}, d3[3] = {dx, dy, dz}, e3[3] = {ex, ey, ez};
 #pragma unroll
-        for (int j = PNR_DOF - 1; j >= 0; --j) {
-            if (j <= body) {
-                pnr_fk_stage(p, j, sc.sn[j], sc.cs[j], ax, ay, az);
-                pnr_fk_stage(p, j, sc.sn[j], sc.cs[j], bx, by, bz);
+        for (int i = 0; i < 3; ++i) {
+            const float inv = 1.f / d3[i];                     // d_i = 0: the candidates are inf / NaN and fail both tests
+#pragma unroll
+            for (int sgn = 0; sgn < 2; ++sgn) {
+                const float tb = ((sgn ? -e3[i] : e3[i]) - a3[i]) * inv;
+                if (tb > lo && tb < hi) {
+                    const float gb = pnr_box_gap_slope(tb, ax, ay, az, dx, dy, dz, ex, ey, ez);
+                    if (gb < 0.f) { lo = tb; glo = gb; } else { hi = tb; ghi = gb; }
+                }
             }
         }
+        const float w = ghi - glo;                             // glo < 0 <= ghi
+        t = w > 0.f ? fmaf(hi - lo, -glo / w, lo) : lo;
+        t = fminf(fmaxf(t, lo), hi);
+    }
+    const float x = fmaf(t, dx, ax), y = fmaf(t, dy, ay), z = fmaf(t, dz, az);
+    const float qx = fmaxf(fabsf(x) - ex, 0.f), qy = fmaxf(fabsf(y) - ey, 0.f), qz = fmaxf(fabsf(z) - ez, 0.f);
+    const float f2 = qx * qx + qy * qy + qz * qz;
+    if (f2 > 1e-8f) return sqrtf(f2);                          // clear of the box by more than 1e-4
+    return pnr_segment_box(ax, ay, az, dx, dy, dz, ex, ey, ez);   // grazing or inside: rounding cannot tell which
+}
+
+// world frame of body j from that of body j - 1 (x_world = o + R x_body, R row-major):
+//   o += R origin_j;   R <- R R_origin_j Rot(axis_j, q_j)         (URDF: child = parent * T(origin) * Rot(axis, q))
+__device__ __forceinline__ void pnr_frame_advance(const PnrParams& p, int j, float sn, float c, float (&R)[9], float (&o)[3]) {
+    const float tx = p.origin_xyz[j][0], ty = p.origin_xyz[j][1], tz = p.origin_xyz[j][2];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) o[r] = fmaf(R[3 * r], tx, fmaf(R[3 * r + 1], ty, fmaf(R[3 * r + 2], tz, o[r])));
+    if (p.origin_has_rot[j]) {
+        const float* Q = p.origin_rot[j];
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float a = R[3 * r], b = R[3 * r + 1], d = R[3 * r + 2];
+            R[3 * r] = a * Q[0] + b * Q[3] + d * Q[6];
+            R[3 * r + 1] = a * Q[1] + b * Q[4] + d * Q[7];
+            R[3 * r + 2] = a * Q[2] + b * Q[5] + d * Q[8];
+        }
+    }
+    const float s = sn * p.axis_sign[j];
+    const int code = p.axis_code[j];             // warp-uniform (constant bank)
+    // a rotation about a coordinate axis mixes two columns (u, w) of R: u' = c u + s w, w' = -s u + c w with
+    // (u, w) = columns (1, 2) for X, (2, 0) for Y, (0, 1) for Z
+    if (code == PNR_AXIS_X) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float cu = R[3 * r + 1], cw = R[3 * r + 2];
+            R[3 * r + 1] = fmaf(c, cu, s * cw); R[3 * r + 2] = fmaf(c, cw, -s * cu);
+        }
+    } else if (code == PNR_AXIS_Y) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float cu = R[3 * r + 2], cw = R[3 * r];
+            R[3 * r + 2] = fmaf(c, cu, s * cw); R[3 * r] = fmaf(c, cw, -s * cu);
+        }
+    } else if (code == PNR_AXIS_Z) {
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float cu = R[3 * r], cw = R[3 * r + 1];
+            R[3 * r] = fmaf(c, cu, s * cw); R[3 * r + 1] = fmaf(c, cw, -s * cu);
+        }
+    } else {                                     // Rodrigues: Rot = c I + s [k]x + (1 - c) k k^T
+        const float kx = p.axis[j][0], ky = p.axis[j][1], kz = p.axis[j][2], v = 1.f - c;
+        const float M[9] = {fmaf(v, kx * kx, c), fmaf(v, kx * ky, -s * kz), fmaf(v, kx * kz, s * ky),
+                            fmaf(v, ky * kx, s * kz), fmaf(v, ky * ky, c), fmaf(v, ky * kz, -s * kx),
+                            fmaf(v, kz * kx, -s * ky), fmaf(v, kz * ky, s * kx), fmaf(v, kz * kz, c)};
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float a = R[3 * r], b = R[3 * r + 1], d = R[3 * r + 2];
+            R[3 * r] = a * M[0] + b * M[3] + d * M[6];
+            R[3 * r + 1] = a * M[1] + b * M[4] + d * M[7];
+            R[3 * r + 2] = a * M[2] + b * M[5] + d * M[8];
+        }
+    }
+}
+
+// `rb`: this env's random box (used for obstacle p.random_box when that is >= 0).  The chain is walked base-to-tip ONCE: the
+// capsule table is ordered by body (pnr_create), so a capsule's end points are two matrix-vector products in the frame
+// that is current when its body is reached (before: every end point was carried through every joint stage up to its body,
+// 12 stages per capsule).
+__device__ __forceinline__ float pnr_contact_depth(const PnrParams& p, const PnrSinCos& sc, const PnrBox& rb) {
+    float sn[PNR_DOF], cs[PNR_DOF];              // indexed by the running joint counter: lives in local memory
+#pragma unroll
+    for (int i = 0; i < PNR_DOF; ++i) { sn[i] = sc.sn[i]; cs[i] = sc.cs[i]; }
+    float R[9] = {1.f, 0.f, 0.f, 0.f, 1.f, 0.f, 0.f, 0.f, 1.f}, org[3] = {0.f, 0.f, 0.f};
+    int joint = 0;
+    float total = 0.f;
+#pragma unroll 1
+    for (int c = 0; c < p.n_capsules; ++c) {
+        const int body = p.capsule_body[c];
+#pragma unroll 1
+        for (; joint <= body; ++joint) pnr_frame_advance(p, joint, sn[joint], cs[joint], R, org);
+        const float u0 = p.capsule_p0[c][0], u1 = p.capsule_p0[c][1], u2 = p.capsule_p0[c][2];
+        const float w0 = p.capsule_p1[c][0], w1 = p.capsule_p1[c][1], w2 = p.capsule_p1[c][2];
+        const float ax = fmaf(R[0], u0, fmaf(R[1], u1, fmaf(R[2], u2, org[0])));
+        const float ay = fmaf(R[3], u0, fmaf(R[4], u1, fmaf(R[5], u2, org[1])));
+        const float az = fmaf(R[6], u0, fmaf(R[7], u1, fmaf(R[8], u2, org[2])));
+        const float bx = fmaf(R[0], w0, fmaf(R[1], w1, fmaf(R[2], w2, org[0])));
+        const float by = fmaf(R[3], w0, fmaf(R[4], w1, fmaf(R[5], w2, org[1])));
+        const float bz = fmaf(R[6], w0, fmaf(R[7], w1, fmaf(R[8], w2, org[2])));
         const float radius = p.capsule_radius[c];
         const float dx = bx - ax, dy = by - ay, dz = bz - az;
+#pragma unroll 1
         for (int o = 0; o < p.n_obstacles; ++o) {
             float px = p.obstacle_p[o][0], py = p.obstacle_p[o][1], pz = p.obstacle_p[o][2];
             float ex = p.obstacle_e[o][0], ey = p.obstacle_e[o][1], ez = p.obstacle_e[o][2];
@@ -283,7 +394,7 @@ static __device__ __noinline__ float pnr_contact_depth(const PnrParams& p, PnrSi
                 const float cx = fmaf(t, dx, ax) - px, cy = fmaf(t, dy, ay) - py, cz = fmaf(t, dz, az) - pz;
                 d = sqrtf(cx * cx + cy * cy + cz * cz) - ex;
             } else {
-                d = pnr_segment_box(ax - px, ay - py, az - pz, dx, dy, dz, ex, ey, ez);
+                d = pnr_segment_box_exact(ax - px, ay - py, az - pz, dx, dy, dz, ex, ey, ez);
             }
             total += fmaxf(0.f, radius - d);
         }

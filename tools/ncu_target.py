@@ -1,6 +1,6 @@
 """Developer tool: a short, deterministic launch sequence for ncu captures of the two step kernels.
 
-    python tools/ncu_target.py [kinematic|dynamic] [n_envs] [fragments]
+    python tools/ncu_target.py [kinematic|dynamic|obstacles] [n_envs] [fragments]
 Runs `fragments` rollout fragments of 8 steps (pnr_step_many) on pre-aged envs, an L2 flush between fragments, exactly as
 bench.py times them."""
 import os
@@ -17,6 +17,10 @@ frags = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 if mode == "dynamic":
     env = BatchedPioneerEnv(n, seed=0, simulation_config=SimulationConfig(gravity=9.81),
                             batch_config=BatchConfig(mode="dynamic", kp=2000.0, kd=500.0, torque_scale=1e5, max_episode_steps=500))
+elif mode == "obstacles":
+    from pioneer_b200 import demo_obstacles
+    env = BatchedPioneerEnv(n, seed=0, batch_config=BatchConfig(max_episode_steps=500, obstacles=demo_obstacles(),
+                                                               contact_penalty=0.5))
 else:
     env = BatchedPioneerEnv(n, seed=0, batch_config=BatchConfig(max_episode_steps=500))
 g = torch.Generator(device="cuda").manual_seed(0)
