@@ -103,7 +103,7 @@ pnr_step_dynamic_kernel(const __grid_constant__ PnrParams p, float4* __restrict_
             PnrSinCos sc;
 #pragma unroll
             for (int i = 0; i < PNR_DOF; ++i) { sc.sn[i] = o.sn[i]; sc.cs[i] = o.cs[i]; }
-            rew = __fsub_rn(rew, __fmul_rn(p.contact_penalty, pnr_contact_depth(p, sc, pnr_load_box(p, env))));
+            rew = __fsub_rn(rew, __fmul_rn(p.contact_penalty, pnr_contact_depth(p, sc, pnr_load_box(p, env), 0, 1)));
         }
         s.pot = pot_new;
         s.t += 1;

@@ -94,6 +94,8 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
     float* row = tile + lane * PNR_OBS_DIM;
     float* scratch = tiles + PNR_STEP_BUFS * PNR_TILE_FLOATS; // FILTER only: raw r, cos r, sin r per env, per buffer
     float* srow = scratch + lane * PNR_FSCRATCH_STRIDE;
+    // OBSTACLES only: partial contact depths of the three joint warps, per buffer [joint warp][env]
+    float* const pen = scratch + (FILTER ? PNR_STEP_BUFS * PNR_FSCRATCH_FLOATS : 0);
     const int64_t N = p.n_envs;
     const int64_t n_tiles = (N + PNR_TILE_ENVS - 1) / PNR_TILE_ENVS;
     const int64_t stride = gridDim.x;
@@ -225,6 +227,10 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         PNR_MARK(5);
 
         bool do_reset = false;
+        // OBSTACLES: what the task warp carries across the DONE barrier (the penalty is summed from the joint warps' partials)
+        float d_rew = 0.f, d_ep = 0.f, d_pot = 0.f;
+        int32_t d_t = 0;
+        bool d_done = false, d_reached = false;
         if (part < 3) {
             // --- the other 15 dynamic columns of each joint; latch the new action (stored unclipped, :144)
             const bool fast = !p.trig_slow && fmaxf(fabsf(c_act.x), fabsf(c_act.y)) <= PNR_TRIG_FAST_LIMIT;
@@ -233,6 +239,17 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             if (active) {
                 rv_plane[env] = make_float4(r1[0], r1[1], v1[0], v1[1]);
                 a_plane[env] = c_act;
+            }
+            if (OBSTACLES) {
+                // capsule penetration depths, the capsule table split over the three joint warps (on the task warp alone
+                // they were the CTA's critical path: 59 % of the stall samples were joint warps parked at DONE).  Every
+                // joint's sin/cos is needed: the joint warps meet once their heads are in the tile.
+                pnr_bar_sync<PNR_BAR_JOINT, 3 * 32>();
+                const float* head = FILTER ? srow : row;
+                PnrSinCos sc;
+#pragma unroll
+                for (int i = 0; i < PNR_DOF; ++i) { sc.cs[i] = head[6 + i]; sc.sn[i] = head[12 + i]; }
+                pen[(buf * 3 + part) * 32 + lane] = pnr_contact_depth(p, sc, pnr_load_box(p, env), part, 3);
             }
             if (FILTER) {                                      // column pass over this warp's 30 changing columns
                 __syncwarp();
@@ -286,22 +303,18 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
             // (potential - old_potential) + (-penalty_step) + (award_done | 0), pioneer_knm_env.py:162-165
             float rew = __fadd_rn(__fadd_rn(__fsub_rn(pot_new, pot_old), -p.penalty_step),
                                   reached ? p.award_done : 0.f);
-            if (OBSTACLES) {                                   // obstacle variant: capsule penetration penalty
-                PnrSinCos sc;
-#pragma unroll
-                for (int i = 0; i < PNR_DOF; ++i) { sc.sn[i] = o.sn[i]; sc.cs[i] = o.cs[i]; }
-                rew = __fsub_rn(rew, __fmul_rn(p.contact_penalty, pnr_contact_depth(p, sc, pnr_load_box(p, env))));
-            }
             t += 1;
-            ep_ret = __fadd_rn(ep_ret, rew);
             const bool timeout = p.max_episode_steps > 0 && t >= p.max_episode_steps;
             const bool is_done = reached || timeout;
             const uint8_t flags = (is_done ? PNR_DONE : 0) | ((timeout && !reached) ? PNR_TRUNCATED : 0);
-            if (active) {
-                reward_s[env] = rew;
-                done_s[env] = flags;
+            if (active) done_s[env] = flags;
+            if (OBSTACLES) {                                   // the penalty arrives with DONE: reward, return and statistics wait
+                d_rew = rew; d_ep = ep_ret; d_pot = pot_new; d_t = t; d_done = is_done; d_reached = reached;
+            } else {
+                ep_ret = __fadd_rn(ep_ret, rew);
+                if (active) reward_s[env] = rew;
+                pnr_episode_stats(stats, is_done && active, reached && active, ep_ret, t, lane);
             }
-            pnr_episode_stats(stats, is_done && active, reached && active, ep_ret, t, lane);
 
             // observation tail: pointer, target, difference, distance, potential (terminal values)
             float tail[11] = {o.ptr[0], o.ptr[1], o.ptr[2], tgt[0], tgt[1], tgt[2],
@@ -319,7 +332,7 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
 
             if (active) {
                 x0_plane[env] = make_float4(tgt[0], tgt[1], tgt[2], __int_as_float(t));
-                x1_plane[env] = make_float2(pot_new, ep_ret);
+                if (!OBSTACLES) x1_plane[env] = make_float2(pot_new, ep_ret);
             }
             do_reset = is_done && active && (p.auto_reset != 0);   // handled after B2 (rare)
         }
@@ -331,6 +344,17 @@ pnr_step_kernel(const __grid_constant__ PnrParams p, float4* __restrict__ state,
         else pnr_bar_sync2<PNR_BAR_DONE, PNR_STEP_THREADS>(buf);   // tile complete, joint planes stored
         PNR_MARK(7);
 
+        if (OBSTACLES && part == 3) {                         // obstacle variant: capsule penetration penalty, then the deferred writes
+            const float* pb = pen + buf * PNR_PEN_FLOATS + lane;
+            const float depth = (pb[0] + pb[32]) + pb[64];
+            const float rew = __fsub_rn(d_rew, __fmul_rn(p.contact_penalty, depth));
+            const float ep_ret = __fadd_rn(d_ep, rew);
+            if (active) {
+                reward_s[env] = rew;
+                x1_plane[env] = make_float2(d_pot, ep_ret);
+            }
+            pnr_episode_stats(stats, d_done && active, d_reached && active, ep_ret, d_t, lane);
+        }
         if (part == 3) {
             // rare: auto-reset (reset_world, :76-105).  Only the auto-reset observation mode rewrites the row, so only there
             // does the reset have to precede the tile's store; terminal mode resets AFTER handing the tile to the copy engine
@@ -655,7 +679,7 @@ cudaError_t pnr_launch_step(const PnrParams& p, int device, int arith, int obs_m
     const int filt = f_applied != nullptr ? 1 : 0;
     if (filt && (arith != PNR_ARITH_F32 || obs_mode != PNR_OBS_TERMINAL)) return cudaErrorInvalidValue;
     Kern k = filt ? fused[obst] : kernels[arith][obs_mode][obst];
-    const size_t smem = filt ? PNR_STEP_SMEM_FILTER : PNR_STEP_SMEM;
+    const size_t smem = (filt ? PNR_STEP_SMEM_FILTER : PNR_STEP_SMEM) + (obst ? PNR_STEP_SMEM_OBST : 0);
     int& resident = grids[device % PNR_MAX_DEVICES][arith][obs_mode][obst][filt];
     if (resident == 0) {
         cudaError_t e = pnr_prepare(k, smem, &resident);

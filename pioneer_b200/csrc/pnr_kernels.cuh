@@ -355,7 +355,9 @@ __device__ __forceinline__ void pnr_frame_advance(const PnrParams& p, int j, flo
 // capsule table is ordered by body (pnr_create), so a capsule's end points are two matrix-vector products in the frame
 // that is current when its body is reached (before: every end point was carried through every joint stage up to its body,
 // 12 stages per capsule).
-__device__ __forceinline__ float pnr_contact_depth(const PnrParams& p, const PnrSinCos& sc, const PnrBox& rb) {
+// Capsules c_first, c_first + c_step, ... are summed (K1 splits the table over its three joint warps; K2 passes 0, 1).
+__device__ __forceinline__ float pnr_contact_depth(const PnrParams& p, const PnrSinCos& sc, const PnrBox& rb, int c_first,
+                                                   int c_step) {
     float sn[PNR_DOF], cs[PNR_DOF];              // indexed by the running joint counter: lives in local memory
 #pragma unroll
     for (int i = 0; i < PNR_DOF; ++i) { sn[i] = sc.sn[i]; cs[i] = sc.cs[i]; }
@@ -363,7 +365,7 @@ __device__ __forceinline__ float pnr_contact_depth(const PnrParams& p, const Pnr
     int joint = 0;
     float total = 0.f;
 #pragma unroll 1
-    for (int c = 0; c < p.n_capsules; ++c) {
+    for (int c = c_first; c < p.n_capsules; c += c_step) {
         const int body = p.capsule_body[c];
 #pragma unroll 1
         for (; joint <= body; ++joint) pnr_frame_advance(p, joint, sn[joint], cs[joint], R, org);

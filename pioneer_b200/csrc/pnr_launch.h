@@ -18,6 +18,9 @@
 #define PNR_BAR_HEAD 1                                                       // named barrier ids: HEAD[2], DONE[2], FREE[2]
 #define PNR_BAR_DONE 3
 #define PNR_BAR_FREE 5
+#define PNR_BAR_JOINT 7                                                      // obstacle variant: the three joint warps among themselves
+#define PNR_PEN_FLOATS (3 * 32)                                              // obstacle variant: per-buffer partial contact depths [joint warp][env]
+#define PNR_STEP_SMEM_OBST (PNR_STEP_BUFS * PNR_PEN_FLOATS * sizeof(float))
 #define PNR_STEP_SMEM (PNR_STEP_BUFS * 32 * PNR_OBS_DIM * sizeof(float))     // step kernel: 17,536 B per tile buffer
 #define PNR_RO_SMEM (PNR_STEP_WARPS * 32 * PNR_OBS_DIM * sizeof(float))      // reset/observe: one tile per warp
 #define PNR_MAX_DEVICES 16
