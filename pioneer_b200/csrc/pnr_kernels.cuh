@@ -214,8 +214,8 @@ __device__ __forceinline__ void pnr_fk_tip(const PnrParams& p, const float (&sn)
 // pioneer_knm_env.py:249-261, and a per-episode random box only in its legacy path, pioneer/temp/pioneer_env.py:169-192):
 // sum over (link capsule, obstacle) pairs of max(0, radius - d), d = the minimum of the obstacle's signed-distance function
 // over the capsule's axis segment -- exact for every kind: plane (linear: the nearer end point), sphere (closest point of the
-// segment), axis-aligned box (below).  Same definition as oracle/contact.h and oracle/reach_oracle.py::contact_depth, which
-// enumerate the breakpoints of the piecewise function in float64 instead.
+// segment), axis-aligned box (below: breakpoint enumeration, as oracle/contact.h and oracle/reach_oracle.py::contact_depth
+// do in float64).
 // INLINED into the obstacle instantiations: as a separate function it received the kernel parameters by reference, and every
 // table entry (capsule end points, axis codes, joint origins, obstacle geometry) became a generic LD.E through that pointer
 // instead of a constant-bank operand -- 144 dependent loads on the task warp's critical path; the variant ran 5x slower
@@ -224,41 +224,44 @@ __device__ __forceinline__ void pnr_fk_tip(const PnrParams& p, const float (&sn)
 struct PnrSinCos { float sn[PNR_DOF], cs[PNR_DOF]; };
 struct PnrBox { float px, py, pz, ex, ey, ez; };
 
-// signed distance of x (relative to the box centre) and its derivative along d (a subgradient at kinks)
-__device__ __forceinline__ float pnr_box_sdf(float x, float y, float z, float ex, float ey, float ez) {
-    const float qx = fabsf(x) - ex, qy = fabsf(y) - ey, qz = fabsf(z) - ez;
-    const float ox = fmaxf(qx, 0.f), oy = fmaxf(qy, 0.f), oz = fmaxf(qz, 0.f);
-    return sqrtf(ox * ox + oy * oy + oz * oz) + fminf(fmaxf(qx, fmaxf(qy, qz)), 0.f);
+// The signed distance to the box (coordinates relative to its centre) is |max(q, 0)| + min(max_i q_i, 0), q_i = |x_i| - e_i.
+// Inside the box the signed distance is max_i(|x_i| - e_i): along the segment a convex, piecewise LINEAR function of t whose
+// minimum lies at an end point, at a kink of one term (x_i = 0) or where two terms cross -- 2 + 3 + 12 candidates, each
+// evaluated exactly (a candidate that is no breakpoint of the maximum, or lies outside the box, only yields a larger value).
+__device__ __forceinline__ float pnr_box_face_term(float t, float ax, float ay, float az, float dx, float dy, float dz,
+                                                   float ex, float ey, float ez) {
+    t = fminf(fmaxf(t, 0.f), 1.f);                             // fmaxf drops a NaN candidate (0 / 0): it becomes t = 0
+    return fmaxf(fabsf(fmaf(t, dx, ax)) - ex, fmaxf(fabsf(fmaf(t, dy, ay)) - ey, fabsf(fmaf(t, dz, az)) - ez));
 }
-// The box signed-distance function is convex, so along the segment a + t d it is a convex function of t whose derivative
-// changes sign exactly once: PNR_BOX_BISECTIONS halvings of [0, 1] on the sign of the directional derivative pin the
-// minimiser to 2^-24 of the segment (below float32 resolution of the distance itself); straight-line code, no divisions.
-#define PNR_BOX_BISECTIONS 24
-__device__ __forceinline__ float pnr_segment_box(float ax, float ay, float az, float dx, float dy, float dz,
-                                                 float ex, float ey, float ez) {
-    float lo = 0.f, hi = 1.f;
-#pragma unroll 1
-    for (int it = 0; it < PNR_BOX_BISECTIONS; ++it) {
-        const float t = 0.5f * (lo + hi);
-        const float x = fmaf(t, dx, ax), y = fmaf(t, dy, ay), z = fmaf(t, dz, az);
-        const float qx = fabsf(x) - ex, qy = fabsf(y) - ey, qz = fabsf(z) - ez;
-        const float gx = x < 0.f ? -dx : dx, gy = y < 0.f ? -dy : dy, gz = z < 0.f ? -dz : dz;   // d|x_i|/dt = sign(x_i) d_i
-        float g;
-        if (fmaxf(qx, fmaxf(qy, qz)) > 0.f)                    // outside: sign of d/dt |max(q, 0)|^2
-            g = fmaxf(qx, 0.f) * gx + fmaxf(qy, 0.f) * gy + fmaxf(qz, 0.f) * gz;
-        else                                                   // inside: the nearest face decides
-            g = (qx >= qy && qx >= qz) ? gx : (qy >= qz ? gy : gz);
-        if (g < 0.f) lo = t; else hi = t;
+__device__ __forceinline__ float pnr_segment_box_inside(float ax, float ay, float az, float dx, float dy, float dz,
+                                                        float ex, float ey, float ez) {
+    const float a3[3] = {ax, ay, az}, d3[3] = {dx, dy, dz}, e3[3] = {ex, ey, ez};
+    float best = fminf(pnr_box_face_term(0.f, ax, ay, az, dx, dy, dz, ex, ey, ez),
+                       pnr_box_face_term(1.f, ax, ay, az, dx, dy, dz, ex, ey, ez));
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+        best = fminf(best, pnr_box_face_term(__fdividef(-a3[i], d3[i]), ax, ay, az, dx, dy, dz, ex, ey, ez));
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+#pragma unroll
+        for (int j = i + 1; j < 3; ++j) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {                      // s_i (a_i + t d_i) - e_i = s_j (a_j + t d_j) - e_j, s = +-1
+                const float si = (k & 1) ? -1.f : 1.f, sj = (k & 2) ? -1.f : 1.f;
+                const float num = (sj * a3[j] - e3[j]) - (si * a3[i] - e3[i]);
+                const float den = si * d3[i] - sj * d3[j];
+                best = fminf(best, pnr_box_face_term(__fdividef(num, den), ax, ay, az, dx, dy, dz, ex, ey, ez));
+            }
+        }
     }
-    return fminf(pnr_box_sdf(fmaf(lo, dx, ax), fmaf(lo, dy, ay), fmaf(lo, dz, az), ex, ey, ez),
-                 pnr_box_sdf(fmaf(hi, dx, ax), fmaf(hi, dy, ay), fmaf(hi, dz, az), ex, ey, ez));
+    return best;
 }
 
 // Outside the box the squared distance F(t) = sum_i max(|x_i(t)| - e_i, 0)^2 along the segment is convex and piecewise
 // quadratic with at most six breakpoints (x_i = +-e_i), so g = F'/2 is piecewise LINEAR and non-decreasing: evaluate g at
 // the breakpoints that fall inside the current bracket (no sorting: each one either raises the lower end or lowers the
 // upper end), then solve the remaining linear piece -- the exact minimiser in 8 evaluations of g instead of 24 halvings.
-// F ~ 0 there means the axis grazes or enters the box; only then the signed (negative) distance needs the search above.
+// F ~ 0 there means the axis grazes or enters the box; only then the signed (negative) distance needs the candidates above.
 __device__ __forceinline__ float pnr_box_gap_slope(float t, float ax, float ay, float az, float dx, float dy, float dz,
                                                    float ex, float ey, float ez) {
     const float x = fmaf(t, dx, ax), y = fmaf(t, dy, ay), z = fmaf(t, dz, az);
@@ -277,7 +280,7 @@ __device__ __forceinline__ float pnr_segment_box_exact(float ax, float ay, float
         const float a3[3] = {ax, ay, az}, d3[3] = {dx, dy, dz}, e3[3] = {ex, ey, ez};
 #pragma unroll
         for (int i = 0; i < 3; ++i) {
-            const float inv = 1.f / d3[i];                     // d_i = 0: the candidates are inf / NaN and fail both tests
+            const float inv = __fdividef(1.f, d3[i]);          // d_i = 0: the candidates are inf / NaN and fail both tests
 #pragma unroll
             for (int sgn = 0; sgn < 2; ++sgn) {
                 const float tb = ((sgn ? -e3[i] : e3[i]) - a3[i]) * inv;
@@ -295,7 +298,8 @@ __device__ __forceinline__ float pnr_segment_box_exact(float ax, float ay, float
     const float qx = fmaxf(fabsf(x) - ex, 0.f), qy = fmaxf(fabsf(y) - ey, 0.f), qz = fmaxf(fabsf(z) - ez, 0.f);
     const float f2 = qx * qx + qy * qy + qz * qz;
     if (f2 > 1e-8f) return sqrtf(f2);                          // clear of the box by more than 1e-4
-    return pnr_segment_box(ax, ay, az, dx, dy, dz, ex, ey, ez);   // grazing or inside: rounding cannot tell which
+    const float in = pnr_segment_box_inside(ax, ay, az, dx, dy, dz, ex, ey, ez);   // grazing or inside: rounding cannot tell which
+    return in < 0.f ? in : sqrtf(f2);
 }
 
 // world frame of body j from that of body j - 1 (x_world = o + R x_body, R row-major):
