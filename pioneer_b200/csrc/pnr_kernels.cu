@@ -18,6 +18,9 @@
 //   HEAD[b]  joint warps arrive once r, cos r, sin r of their joints are in buffer b; the task warp waits on it
 //   DONE[b]  joint warps arrive once all their columns and planes are written; the task warp waits, then stores
 //   FREE[b]  the task warp arrives once the bulk store of buffer b has been read; joint warps wait before reuse
+//   JOINT    (OBSTACLES only) the three joint warps among themselves, once their heads are in the tile: each then sums the
+//            penetration depths of its share of the capsule table into shared memory; the task warp adds the three partials
+//            behind DONE and only then writes reward, return and episode statistics
 // so the joint warps of a CTA work on tile i+1 while its task warp finishes tile i (before: 49 % of stall samples
 // were joint warps parked at a CTA-wide barrier).  Each warp prefetches its own planes of the CTA's next tile.
 // Grid = min(tiles, resident CTAs of the whole GPU); grid-stride over tiles.
