@@ -13,7 +13,8 @@
  *             is a convex piecewise function: quadratic (under the root) between the parameters where a coordinate
  *             crosses a face plane, linear inside the box between the parameters where the deepest face changes.
  *             All breakpoints are enumerated and sorted, every piece is minimised in closed form.
- * The CUDA path finds the same minimum by bisection on the sign of the directional derivative (pnr_kernels.cuh).
+ * The CUDA path finds the same minimum from the same breakpoints, unsorted: a bracket on the piecewise-linear derivative
+ * outside the box, a candidate list inside (pnr_segment_box_exact / pnr_segment_box_inside in pnr_kernels.cuh).
  */
 #ifndef ORC_CONTACT_H_
 #define ORC_CONTACT_H_

@@ -169,7 +169,7 @@ def segment_box_distance(a, b, centre, ext) -> float:
     """EXACT minimum of the box signed-distance function over the segment [a, b].  The function is convex along the
     segment and piecewise: the root of a quadratic between the parameters where a coordinate crosses a face plane, linear
     inside the box between the parameters where the nearest face changes.  Every breakpoint is enumerated, every piece
-    minimised in closed form (same method as oracle/contact.h; the CUDA path bisects on the derivative instead)."""
+    minimised in closed form (same method as oracle/contact.h; the CUDA path enumerates the same breakpoints without sorting them, pnr_segment_box_exact)."""
     a0 = np.array(a, f64) - np.array(centre, f64)
     d = np.array(b, f64) - np.array(a, f64)
     e = np.array(ext, f64)

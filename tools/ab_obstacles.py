@@ -22,7 +22,7 @@ def run(name, make, steps=160):
     bench.pre_age(torch, e, 500, 3)
     a, o, r, f = bench.make_buffers(torch, e, e.n_envs, dev, seed=3)
     ms, _ = bench.time_fragments(torch, e, a, o, r, f, steps, 16, flush)
-    print(f"{name:44s} n={e.n_envs:8d}  {ms / steps * 1e3:8.2f} us/step  {e.n_envs * steps / ms / 1e6:9.1f} M env-steps/s", flush=True)
+    print(f"{name:44s} n={e.n_envs:8d}  {ms / steps * 1e3:8.2f} us/step  {e.n_envs * steps / ms / 1e6:9.2f} G env-steps/s", flush=True)
     e.close()
 
 
