@@ -621,7 +621,8 @@ def ours_arm(args):
                            "steps on its own tiles), each fragment timed by its own CUDA-event pair on the launching stream; within a "
                            f"fragment the {n * 96 // 1000000} MB of env state stay L2-resident as in any rollout loop, the "
                            f"{obs_ring.shape[0]} x {n * OBS_DIM * 4 // 1000000} MB observation slots do not fit",
-                   "parallelism": f"env-sharded x{world}, no data-path collective; one stats all-gather per iteration"},
+                   "parallelism": f"env-sharded x{world}, no data-path collective; one statistics exchange per iteration "
+                                  "(stats_exchange: a peer-memory kernel within the node, NCCL all-gather + merge otherwise)"},
         "substeps_per_sec": value * FRAME_SKIP,
         "fragment_steps": FRAGMENT,
         "fragment_ms_per_step_percentiles": {"p5": frag_ms[len(frag_ms) // 20], "p50": frag_ms[len(frag_ms) // 2],
@@ -833,7 +834,7 @@ def rollout_loop(torch, dist, device, rank, world, max_over_ranks, barrier, n=13
     ms = max_over_ranks(s.elapsed_time(e))
     steps = iters * fragment
     out = {"workload": f"BASELINE.json configs[4]: {n} envs per GPU ({world * n} in total), fragment length {fragment}, fused "
-                       "observation filter, bf16 137-256-256-12 policy stub, CUDA-graph fragments, one packed collective per "
+                       "observation filter, bf16 137-256-256-12 policy stub, CUDA-graph fragments, one packed exchange (statistics + filter delta) per "
                        "iteration; the policy sees the reset observation after every done (pnr_observe_done)",
            "value": world * n * steps / (ms / 1e3), "unit": UNIT, "ms_per_env_step_batch": ms / steps, "iterations": iters,
            "episode_stats": summarize(stats)}
