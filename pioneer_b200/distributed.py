@@ -115,10 +115,12 @@ class IterationSync:
     ``transport="auto"`` (default) uses p2p when every rank could open every other rank's window (same node, peer access)
     and nccl otherwise; ``PNR_SYNC_TRANSPORT`` overrides.  ``__call__`` returns the merged float64[8] statistics tensor
     (device, not synchronised; valid until the next call).  A p2p wait that exceeds ``timeout_s`` yields NaN statistics and
-    ``timed_out()`` reports it (a kernel never spins for ever on a dead peer)."""
+    ``timed_out()`` reports it (a kernel never spins for ever on a dead peer); the ranks' sequence numbers may then disagree,
+    so the next object must be built with ``reconnect=True`` on every rank (it re-opens the windows and restarts the
+    protocol; graphs captured by earlier objects on that env must not be replayed afterwards)."""
 
     def __init__(self, env, obs_filter=None, group: Optional[dist.ProcessGroup] = None, clear: bool = True,
-                 cuda_graph: bool = False, transport: str = "auto", timeout_s: float = 20.0):
+                 cuda_graph: bool = False, transport: str = "auto", timeout_s: float = 20.0, reconnect: bool = False):
         import os
         from . import _cabi
         self.env, self.filter, self.group, self.clear = env, obs_filter, group, bool(clear)
@@ -130,6 +132,7 @@ class IterationSync:
         self.world = dist.get_world_size(group) if active else 1
         self.rank = dist.get_rank(group) if active else 0
         self.timeout_ms = int(timeout_s * 1000)
+        self._reconnect = bool(reconnect)
         dev = env.device
         self.packed = torch.zeros(self.len, dtype=torch.float64, device=dev)
         self.gathered = torch.zeros((self.world, self.len), dtype=torch.float64, device=dev)
@@ -171,6 +174,12 @@ class IterationSync:
         import ctypes as C
         c, lib, env = self._cabi, self._lib, self.env
         self._connect_error = ""
+        # one connection per (handle, group): a second IterationSync on the same env reuses it -- re-opening the windows
+        # would unmap the addresses an earlier object's captured graph still launches with.  Every rank takes this branch
+        # together (the objects are constructed in the same order on all ranks, as any collective is).
+        key = (self.world, self.rank, id(self.group) if self.group is not None else 0)
+        if getattr(env, "_sync_connection", None) == key and not self._reconnect:
+            return True
         ipc = (C.c_ubyte * c.PNR_SYNC_IPC_BYTES)()
         ok = 1
         if self.world > c.PNR_SYNC_MAX_PEERS or lib.pnr_sync_window_create(env._h, ipc) != 0:
@@ -187,6 +196,8 @@ class IterationSync:
         torch.cuda.synchronize(env.device)
         if int(agreed.item()) != 1 and not self._connect_error:
             self._connect_error = "another rank failed"
+        if int(agreed.item()) == 1:
+            env._sync_connection = key
         return int(agreed.item()) == 1
 
     def _run(self) -> None:
