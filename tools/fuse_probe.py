@@ -1,3 +1,5 @@
+"""Developer probe: the step with and without the fused observation normaliser and its statistics (the measurement behind
+the PNR_FILTER_SLOTS comment in pioneer_b200/csrc/pnr_launch.h).   python tools/fuse_probe.py"""
 import sys, os; sys.path.insert(0, os.getcwd())
 import torch
 from pioneer_b200 import BatchedPioneerEnv, BatchConfig
